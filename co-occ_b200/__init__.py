@@ -1,0 +1,11 @@
+"""coocc_b200 -- B200-native fused-voxel hot path of Co-Occ (GSFusion -> 3D conv decoder/head ->
+volume-render regulariser) behind the reference's mmdet3d-plugin module API.
+
+Host code is Python/PyTorch (device memory, streams, autograd plumbing); all arithmetic on the
+path runs in hand-written sm_100a CUDA reached through the C-ABI in include/coocc_b200.h
+(csrc/libcoocc_b200.so).  There is no CPU fallback: constructing or calling a module without
+the library raises.
+"""
+__version__ = "0.1.0"
+
+from . import synthetic  # noqa: F401

@@ -1,0 +1,139 @@
+"""make_golden -- TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the
+UNMODIFIED reference Python (imported from /root/reference through oracle/refshim.py) on the
+seeded synthetic inputs of coocc_b200.synthetic.  Run in the build container only:
+
+    python -m oracle.make_golden
+
+The reference has no tests of its own for BiFuser_N / CustomResNet3D / FPN3D / OccHead / the
+render block, so these fixtures are what pins the oracle (and, through it, the
+CUDA path) to the reference for those rows.  Large tensors are stored as strided samples
+plus sums to keep the fixtures small.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+import coocc_b200  # noqa: E402
+from coocc_b200 import synthetic as S  # noqa: E402
+from oracle import refshim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+STRIDE = 97      # sample stride for large float tensors
+
+
+def sample(t):
+    f = t.detach().reshape(-1)
+    return f[::STRIDE].numpy().astype(np.float32)
+
+
+def stats(t):
+    t = t.detach().double()
+    return np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()], dtype=np.float64)
+
+
+def sub(prefix, p):
+    return {k[len(prefix):]: v for k, v in p.items() if k.startswith(prefix)}
+
+
+def golden_for(name, ns):
+    cfg = S.CONFIGS[name]
+    C, K = cfg["C"], cfg["K"]
+    inp = S.make_inputs(name)
+    P = S.make_params(name)
+    torch.use_deterministic_algorithms(True)
+    g = {}
+    nc = dict(type="SyncBN", requires_grad=True)
+
+    # ---- GSFusion (reference BiFuser_N, torch tie order) -----------------------------------
+    fuser = ns.BiFuser_N(C, C, knum=K)
+    fuser.load_state_dict(P["occ_fuser"], strict=True)
+    fuser.train()
+    img = inp["img_voxel_feats"].clone().requires_grad_(True)
+    pts = inp["pts_voxel_feats"].clone().requires_grad_(True)
+    inds_img = torch.nonzero(img.sum(1))
+    inds_pts = torch.nonzero(pts.sum(1))
+    g["n_img"], g["n_pts"] = np.int64(len(inds_img)), np.int64(len(inds_pts))
+    nn_img = fuser.fps_NN_fast(inds_pts.contiguous(), inds_img.contiguous(), 2048, 6, 200, 13.3, K)
+    nn_pts = fuser.fps_NN_fast(inds_img.contiguous(), inds_pts.contiguous(), 2048, 6, 200, 13.3, K)
+    g["nn_img"] = nn_img.numpy().astype(np.int32)
+    g["nn_pts"] = nn_pts.numpy().astype(np.int32)
+    fused = fuser(img, pts)
+    g["fused_sample"], g["fused_stats"] = sample(fused), stats(fused)
+    wsum = torch.linspace(-1, 1, fused.numel()).reshape(fused.shape)
+    (fused * wsum).sum().backward()
+    g["fused_dimg_sample"], g["fused_dimg_stats"] = sample(img.grad), stats(img.grad)
+    g["fused_dpts_sample"], g["fused_dpts_stats"] = sample(pts.grad), stats(pts.grad)
+    g["fused_dknn_w"] = fuser.knn_enc[0].weight.grad.numpy().astype(np.float32)[:, ::5]
+    g["fused_dknn_b"] = fuser.knn_enc[0].bias.grad.numpy().astype(np.float32)
+
+    # ---- dense conv stack on a fixed seeded input -------------------------------------------
+    gx = torch.Generator().manual_seed(1234)
+    x = (torch.randn(1, C, *cfg["grid"], generator=gx) * 0.5).requires_grad_(True)
+    planes = [C, 2 * C, 4 * C, 8 * C]
+    enc = ns.CustomResNet3D(depth=18, n_input_channels=C, block_inplanes=planes,
+                            out_indices=(0, 1, 2, 3), norm_cfg=nc)
+    enc.load_state_dict(P["semantic_encoder"], strict=True)
+    neck = ns.FPN3D(with_cp=True, in_channels=planes, out_channels=2 * C, norm_cfg=nc)
+    neck.load_state_dict(P["semantic_neck"], strict=True)
+    head = ns.OccHead(norm_cfg=nc, soft_weights=True, cascade_ratio=2, sample_from_voxel=False,
+                      sample_from_img=False, final_occ_size=[2 * s for s in cfg["grid"]],
+                      fine_topk=15000, empty_idx=0, num_level=4, in_channels=[2 * C] * 4,
+                      out_channel=17, point_cloud_range=[-50, -50, -5.0, 50, 50, 3.0])
+    head.load_state_dict(P["pts_bbox_head"], strict=True)
+    for m in (enc, neck, head):
+        m.train()
+    mid = enc(x)
+    nk = neck(mid)
+    o = head.forward_coarse_voxel(nk)
+    occ, feats = o["occ"][0], o["out_voxel_feats"][0]
+    for i, t in enumerate(mid):
+        g["mid%d_sample" % i], g["mid%d_stats" % i] = sample(t), stats(t)
+    for i, t in enumerate(nk):
+        g["neck%d_sample" % i], g["neck%d_stats" % i] = sample(t), stats(t)
+    g["occ_sample"], g["occ_stats"] = sample(occ), stats(occ)
+    g["occfeat_sample"], g["occfeat_stats"] = sample(feats), stats(feats)
+    wocc = torch.linspace(-1, 1, occ.numel()).reshape(occ.shape)
+    (occ * wocc).sum().backward()
+    g["stack_dx_sample"], g["stack_dx_stats"] = sample(x.grad), stats(x.grad)
+    g["stack_dw_proj"] = enc.input_proj[0].weight.grad.reshape(-1)[::13].numpy().astype(np.float32)
+    g["stack_dw_pred"] = head.occ_pred_conv[3].weight.grad.reshape(-1).numpy().astype(np.float32)
+
+    # ---- render block (reference lines executed as-is) -------------------------------------
+    mlp_s = ns.MLP(input_dim=C, output_dim=1, net_depth=1, skip_layer=None)
+    mlp_r = ns.MLP(input_dim=C, output_dim=3, net_depth=3, skip_layer=None)
+    mlp_s.load_state_dict(sub("sigma_head.", P["render"]))
+    mlp_r.load_state_dict(sub("rgb_head.", P["render"]))
+    gv = torch.Generator().manual_seed(4321)
+    vf = (torch.randn(1, C, *cfg["grid"], generator=gv) * 0.5).requires_grad_(True)
+    rgbs, depths, losses = refshim.reference_render_block(
+        vf, inp["geom"].clone(), mlp_s, mlp_r, inp["gt_depth"], inp["gt_img"])
+    g["render_rgbs_sample"], g["render_rgbs_stats"] = sample(rgbs), stats(rgbs)
+    g["render_depths_sample"], g["render_depths_stats"] = sample(depths), stats(depths)
+    g["loss_depth_render"] = np.float64(losses["loss_depth_render"].item())
+    g["loss_rgb"] = np.float64(losses["loss_rgb"].item())
+    (losses["loss_depth_render"] + losses["loss_rgb"]).backward()
+    g["render_dvf_sample"], g["render_dvf_stats"] = sample(vf.grad), stats(vf.grad)
+    g["render_dw_sigma_out"] = mlp_s.output_layer.weight.grad.reshape(-1).numpy().astype(np.float32)
+    g["render_dw_rgb_out"] = mlp_r.output_layer.weight.grad.reshape(-1).numpy().astype(np.float32)
+    return g
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = refshim.load_reference()
+    for name in ("c1", "c1k1"):
+        g = golden_for(name, ns)
+        path = os.path.join(OUT, "reference_%s.npz" % name)
+        np.savez_compressed(path, **g)
+        print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()
