@@ -1,0 +1,67 @@
+"""ctypes binding of csrc/libcoocc_b200.so (the C ABI declared in include/coocc_b200.h).
+
+There is no fallback: if the shared library is missing or fails to load, `lib()` raises.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(CSRC, "libcoocc_b200.so")
+
+_lib = None
+
+c_int, c_ll, c_void_p, c_float = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_float
+
+ERRORS = {-1: "invalid argument", -2: "pointer/stride not 16-byte aligned", -3: "CUDA driver entry point missing",
+          -4: "tensor map encode failed", -5: "CUDA launch/runtime error", -6: "capacity exceeded"}
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("X", c_int), ("Y", c_int), ("Z", c_int), ("Cin", c_int), ("Cout", c_int),
+                ("ksize", c_int), ("stride", c_int), ("dtype", c_int), ("ldx", c_ll), ("ldy", c_ll)]
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into csrc/libcoocc_b200.so (nvcc cross-compiles
+    without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("building libcoocc_b200.so failed")
+    return SO_PATH
+
+
+_SIGS = {
+    "coocc_version": (c_int, []),
+    "coocc_conv3d_fwd": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p]),
+    "coocc_conv3d_dgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "coocc_conv3d_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(SO_PATH):
+            raise RuntimeError(
+                "coocc_b200: %s not found -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the hot path)" % SO_PATH)
+        _lib = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(_lib, name)      # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS.keys())
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("coocc_b200.%s failed: %s (%d)" % (what, ERRORS.get(rc, "unknown"), rc))

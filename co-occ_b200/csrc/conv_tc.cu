@@ -1,0 +1,662 @@
+// conv_tc.cu -- 3D convolution (1x1x1 / 3x3x3, stride 1 / 2) and plain GEMM on the B200 5th-gen
+// tensor cores: TMA (im2col mode) -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+//
+// Replaces, for the fused-voxel hot path, the cuDNN Conv3d / cuBLAS Linear calls of the reference
+// (P/coocc/fuser/bifuser_n.py:23-30, P/coocc/backbones/resnet3d.py:16-31, P/coocc/necks/fpn3d.py:48-67,
+//  P/coocc/dense_heads/occ_head.py:102-132, P/utils/nerf_mlp.py:92-105).
+//
+// Data layout: activations NDHWC (= torch channels_last_3d of [1,C,X,Y,Z]) i.e. a row-major
+// [V = X*Y*Z, C] matrix with row stride `ld`; weights [Cout][kx][ky][kz][Cin] (= channels_last_3d of
+// the reference's [Cout,Cin,3,3,3] parameter) i.e. row-major [Cout, taps*Cin].
+//
+// One kernel template, three uses:
+//   fprop : D[v, co] = sum_{tap,ci} X[v*s + tap - pad, ci] * W[co, tap, ci]
+//           A = X, K-major, TMA im2col;  B = W rows, K-major, TMA tiled.
+//   dgrad : dX[v, ci] = sum_{tap,co} dY[v - tap + pad, co] * W[co, tap, ci]      (stride 1)
+//           A = dY, K-major, TMA im2col with mirrored taps;  B = W read *in place* as an
+//           MN-major operand (ci contiguous), so no transposed weight copy is ever made.
+//   wgrad : dW[co, tap, ci] = sum_v dY[v, co] * X[v*s + tap - pad, ci]
+//           A = dY MN-major (TMA tiled), B = X MN-major (TMA im2col), split-K over voxel blocks,
+//           fp32 red.global.add epilogue.
+//
+// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+// epilogue.  Persistent grid (<= #SMs), 4-stage smem ring, 2 TMEM accumulator buffers so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/coocc_b200.h"
+#include "tc_common.cuh"
+
+namespace coocc {
+
+constexpr int kStages = 4;
+constexpr int kBM = 128;              // MMA M (TMEM lanes)
+constexpr int kMaxBN = 256;           // MMA N upper bound (TMEM columns per accumulator buffer)
+constexpr int kABytes = kBM * 128;    // 16 KiB per stage
+constexpr int kBBytesMax = kMaxBN * 128;
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kThreads = 256;
+
+enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+
+struct TcParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int mode;
+  int M, N;            // output rows / cols (fprop: V_out, Cout; dgrad: V, Cin; wgrad: Cout, Cin)
+  int BN;              // N tile (multiple of 16, <= 256)
+  int taps;            // 1 or 27
+  int Kc;              // reduction channels per tap (fprop: Cin, dgrad: Cout); wgrad: unused
+  int a_im2col;        // A (fprop/dgrad) or B (wgrad) loaded through im2col
+  int oX, oY, oZ;      // spatial dims of the *pixel* index space of the im2col operand
+  int cstride;         // conv stride (im2col traversal stride)
+  int lo;              // im2col lower corner (= -pad)
+  int wK;              // row length of the weight matrix in elements (taps * Cin)  [dgrad B coords]
+  int Cin;             // weight inner channel count (B K-offset per tap)
+  // epilogue
+  float* out;
+  long long ldc;
+  const float* bias;
+  int relu;
+  float* stats;        // [2][N] sum / sum of squares over rows, or nullptr
+  // wgrad
+  int nvb;             // number of voxel (K) blocks
+  int ksplit;
+};
+
+template <int ES> struct Elt {
+  static constexpr int BKE = 128 / ES;       // K elements per stage for K-major operands
+  static constexpr int CH = 128 / ES;        // MN elements per 128B chunk for MN-major operands
+  static constexpr int KR = 128 / ES;        // K rows per stage for MN-major operands
+  static constexpr int UK = 32 / ES;         // K elements per tcgen05.mma
+  static constexpr int NUK = BKE / UK;       // MMAs per stage (= 4)
+  static constexpr bool TF32 = (ES == 4);
+  static constexpr uint32_t FMT = (ES == 4) ? 2u : 1u;                // TF32 : BF16
+  static constexpr uint32_t MN_LAYOUT = (ES == 4) ? 1u : 2u;          // SW128_BASE32B : SW128
+  static constexpr uint32_t MN_SBO = (ES == 4) ? 512u : 1024u;        // K-atom stride (4 / 8 rows)
+  static constexpr uint32_t MN_CHUNK = KR * 128;                      // bytes per MN chunk
+  static constexpr uint32_t MN_KSTEP = UK * 128;                      // bytes per MMA K step
+};
+
+__device__ __forceinline__ void pixel_to_whd(const TcParams& p, int pix, int& w, int& h, int& d) {
+  const int z = pix % p.oZ;
+  const int t = pix / p.oZ;
+  const int y = t % p.oY;
+  const int x = t / p.oY;
+  w = p.lo + z * p.cstride;
+  h = p.lo + y * p.cstride;
+  d = p.lo + x * p.cstride;
+}
+
+template <int ES>
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
+  using E = Elt<ES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool wgrad = (p.mode == MODE_WGRAD);
+  const bool a_mn = wgrad;
+  const bool b_mn = (p.mode != MODE_FPROP);
+
+  // ---- tile bookkeeping (identical in every role) ---------------------------------------
+  const int ntn = (p.N + p.BN - 1) / p.BN;
+  const int ntm = (p.M + kBM - 1) / kBM;
+  const int ntiles = wgrad ? ntm * ntn * p.taps * p.ksplit : ntm * ntn;
+  const int kb_per_tap = (p.Kc + E::BKE - 1) / E::BKE;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t a_bytes = kABytes;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int mt, nt, tap0, tap1, kb0, kb1;
+        if (!wgrad) {
+          nt = tile % ntn;
+          mt = tile / ntn;
+          tap0 = 0; tap1 = p.taps; kb0 = 0; kb1 = kb_per_tap;
+        } else {
+          int t = tile;
+          const int sp = t % p.ksplit; t /= p.ksplit;
+          nt = t % ntn; t /= ntn;
+          mt = t % ntm; t /= ntm;
+          tap0 = t; tap1 = t + 1;
+          kb0 = (int)((long long)p.nvb * sp / p.ksplit);
+          kb1 = (int)((long long)p.nvb * (sp + 1) / p.ksplit);
+        }
+        for (int tap = tap0; tap < tap1; ++tap) {
+          // filter offsets of this tap in the im2col operand (W<->z, H<->y, D<->x)
+          const int kx = (p.taps == 1) ? 0 : tap / 9, ky = (p.taps == 1) ? 0 : (tap / 3) % 3,
+                    kz = (p.taps == 1) ? 0 : tap % 3;
+          // dgrad walks the mirrored tap of the weight tensor
+          const int wtap = (p.mode == MODE_DGRAD) ? (p.taps - 1 - tap) : tap;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+            if (!wgrad) {
+              // ---- A: [128 pixels x BKE channels], K-major
+              if (p.a_im2col) {
+                int w, h, d;
+                pixel_to_whd(p, mt * kBM, w, h, d);
+                tma_load_im2col_5d(sa, &p.tmA, &full_bar[stage], kb * E::BKE, w, h, d, 0,
+                                   (uint16_t)kz, (uint16_t)ky, (uint16_t)kx);
+              } else {
+                tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * E::BKE, mt * kBM);
+              }
+              // ---- B
+              if (!b_mn) {   // weights rows, K-major: box {BKE, BN}
+                tma_load_2d(sb, &p.tmB, &full_bar[stage], wtap * p.Cin + kb * E::BKE, nt * p.BN);
+              } else {       // dgrad: W in place, MN-major chunks of CH input channels x KR couts
+                const int nch = p.BN / E::CH;
+                for (int j = 0; j < nch; ++j)
+                  tma_load_2d(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
+                              wtap * p.Cin + nt * p.BN + j * E::CH, kb * E::KR);
+              }
+            } else {
+              // ---- A: dY^T tile, MN-major: chunks of CH couts x KR voxels
+              for (int j = 0; j < kBM / E::CH; ++j)
+                tma_load_2d(sa + j * E::MN_CHUNK, &p.tmA, &full_bar[stage],
+                            mt * kBM + j * E::CH, kb * E::KR);
+              // ---- B: X tile (shifted by tap), MN-major: chunks of CH cins x KR pixels
+              const int nch = p.BN / E::CH;
+              int w = 0, h = 0, d = 0;
+              if (p.a_im2col) pixel_to_whd(p, kb * E::KR, w, h, d);
+              for (int j = 0; j < nch; ++j) {
+                if (p.a_im2col)
+                  tma_load_im2col_5d(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
+                                     nt * p.BN + j * E::CH, w, h, d, 0, (uint16_t)kz, (uint16_t)ky,
+                                     (uint16_t)kx);
+                else
+                  tma_load_2d(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
+                              nt * p.BN + j * E::CH, kb * E::KR);
+              }
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer =============================================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(E::FMT, a_mn ? 1u : 0u, b_mn ? 1u : 0u, kBM, (uint32_t)p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int nk;
+        if (!wgrad) {
+          nk = p.taps * kb_per_tap;
+        } else {
+          const int sp = tile % p.ksplit;
+          nk = (int)((long long)p.nvb * (sp + 1) / p.ksplit) - (int)((long long)p.nvb * sp / p.ksplit);
+        }
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
+        for (int k = 0; k < nk; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int j = 0; j < E::NUK; ++j) {
+            const uint64_t ad = a_mn ? make_smem_desc(sa + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
+                                     : make_smem_desc(sa + j * 32, 16, 1024, 2);
+            const uint64_t bd = b_mn ? make_smem_desc(sb + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
+                                     : make_smem_desc(sb + j * 32, 16, 1024, 2);
+            umma<E::TF32>(d_tmem, ad, bd, idesc, (k | j) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (nk > 0) {
+          umma_commit(&tfull_bar[acc]);            // accumulator complete -> epilogue
+        } else {
+          mbar_arrive(&tfull_bar[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int q = warp & 3;                 // TMEM lane quadrant of this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int mt, nt, tap = 0, nk = 1;
+      if (!wgrad) {
+        nt = tile % ntn;
+        mt = tile / ntn;
+      } else {
+        int t = tile;
+        const int sp = t % p.ksplit; t /= p.ksplit;
+        nt = t % ntn; t /= ntn;
+        mt = t % ntm; t /= ntm;
+        tap = t;
+        nk = (int)((long long)p.nvb * (sp + 1) / p.ksplit) - (int)((long long)p.nvb * sp / p.ksplit);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = mt * kBM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        if (nk > 0) {
+          tmem_ld_32x32(t_base + (uint32_t)c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        const int col0 = nt * p.BN + c0;
+        if (!wgrad) {
+          if (p.stats != nullptr) {
+            // per-column sum / sum of squares over the rows of this warp (raw accumulators):
+            // butterfly transpose-reduce, lane l ends with the totals of column c0 + l
+            float s[32], ss[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = row_ok ? __uint_as_float(v[i]) : 0.f;
+              s[i] = f;
+              ss[i] = f * f;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send_s = up ? s[i] : s[i + off];
+                const float send_q = up ? ss[i] : ss[i + off];
+                const float recv_s = __shfl_xor_sync(0xffffffffu, send_s, off);
+                const float recv_q = __shfl_xor_sync(0xffffffffu, send_q, off);
+                s[i] = (up ? s[i + off] : s[i]) + recv_s;
+                ss[i] = (up ? ss[i + off] : ss[i]) + recv_q;
+              }
+            }
+            // after the butterfly lane l holds column index bitwise == l (bit `off` set <-> upper half)
+            const int col = col0 + lane;
+            if (col < p.N) {
+              atomicAdd(&p.stats[col], s[0]);
+              atomicAdd(&p.stats[p.N + col], ss[0]);
+            }
+          }
+          if (row_ok) {
+            float* o = p.out + (long long)row * p.ldc + col0;
+            if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 f;
+                f.x = __uint_as_float(v[i]); f.y = __uint_as_float(v[i + 1]);
+                f.z = __uint_as_float(v[i + 2]); f.w = __uint_as_float(v[i + 3]);
+                if (p.bias) {
+                  f.x += p.bias[col0 + i]; f.y += p.bias[col0 + i + 1];
+                  f.z += p.bias[col0 + i + 2]; f.w += p.bias[col0 + i + 3];
+                }
+                if (p.relu) {
+                  f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f);
+                  f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(o + i) = f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (col0 + i < p.N) {
+                  float f = __uint_as_float(v[i]);
+                  if (p.bias) f += p.bias[col0 + i];
+                  if (p.relu) f = fmaxf(f, 0.f);
+                  o[i] = f;
+                }
+              }
+            }
+          }
+        } else if (row_ok && nk > 0) {
+          // wgrad: accumulate the split-K partial into dW[row][tap][col]
+          float* o = p.out + ((long long)row * p.taps + tap) * p.ldc + col0;
+          if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i),
+                           "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                           "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                           : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.N) atomicAdd(o + i, __uint_as_float(v[i]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                     cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled g_encodeTiled = nullptr;
+static PFN_encodeIm2col g_encodeIm2col = nullptr;
+static int g_num_sms = 0;
+static int g_driver_version = 0;
+
+static int init_driver_api() {
+  if (g_encodeTiled && g_encodeIm2col) return 0;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+    return COOCC_ERR_DRIVER;
+  g_encodeTiled = reinterpret_cast<PFN_encodeTiled>(fn);
+  fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+    return COOCC_ERR_DRIVER;
+  g_encodeIm2col = reinterpret_cast<PFN_encodeIm2col>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDriverGetVersion(&g_driver_version);
+  return 0;
+}
+
+static CUtensorMapDataType tm_dtype(int es) {
+  // TFLOAT32: the TMA unit rounds fp32 to tf32 (round-to-nearest) on its way to shared memory,
+  // so the MMA consumes correctly rounded operands instead of truncated ones.
+  return es == 4 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+
+// 2-D row-major matrix [rows][cols] with row stride ld (elements); box {box_c, box_r}
+static int make_tm_2d(CUtensorMap* tm, const void* ptr, int es, long long rows, long long cols,
+                      long long ld, int box_c, int box_r, bool mn_major) {
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = (mn_major && es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = g_encodeTiled(tm, tm_dtype(es), 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[coocc_b200] cuTensorMapEncodeTiled failed: %d (rows=%lld cols=%lld ld=%lld box=%d,%d)\n",
+            (int)r, rows, cols, ld, box_c, box_r);
+    return COOCC_ERR_TENSORMAP;
+  }
+  return 0;
+}
+
+// NDHWC tensor [1][X][Y][Z][C] with pixel stride ld (elements), im2col box {chan, pixels}
+static int make_tm_im2col(CUtensorMap* tm, const void* ptr, int es, int X, int Y, int Z, int C,
+                          long long ld, int lo, int hi, int stride, int chan, int pixels,
+                          bool mn_major) {
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, 1};
+  cuuint64_t gstr[4] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * Z, (cuuint64_t)ld * es * Z * Y,
+                        (cuuint64_t)ld * es * Z * Y * X};
+  int lower[3] = {lo, lo, lo};
+  int upper[3] = {hi, hi, hi};
+  cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUtensorMapSwizzle sw = (mn_major && es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = g_encodeIm2col(tm, tm_dtype(es), 5, const_cast<void*>(ptr), gdim, gstr, lower, upper,
+                              (cuuint32_t)chan, (cuuint32_t)pixels, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[coocc_b200] cuTensorMapEncodeIm2col failed: %d (X=%d Y=%d Z=%d C=%d ld=%lld lo=%d hi=%d s=%d box=%d,%d)\n",
+            (int)r, X, Y, Z, C, ld, lo, hi, stride, chan, pixels);
+    return COOCC_ERR_TENSORMAP;
+  }
+  // Same workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): drivers <= 13.1
+  // mis-encode im2col maps of tensors smaller than 128 KiB; clear bit 21 of the second word.
+  if (g_driver_version <= 13010) {
+    const long long bytes = (long long)ld * es * Z * Y * X;
+    if (bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  }
+  return 0;
+}
+
+static int out_dim(int in, int ksize, int stride) {
+  const int pad = ksize / 2;
+  return (in + 2 * pad - ksize) / stride + 1;
+}
+
+template <int ES>
+static int launch(const TcParams& p, int ntiles, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return COOCC_ERR_CUDA;
+    attr_set = true;
+  }
+  int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
+  if (grid < 1) return 0;
+  tc_conv_kernel<ES><<<grid, kThreads, kSmemBytes, st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+
+static int pick_bn(int n) {
+  int bn = ((n + 15) / 16) * 16;
+  if (bn <= kMaxBN) return bn;
+  // largest multiple-of-32 tile <= 256 that divides n, else 256 with a masked tail
+  for (int t = 256; t >= 64; t -= 32)
+    if (n % t == 0) return t;
+  return 256;
+}
+
+}  // namespace coocc
+
+using namespace coocc;
+
+static int check_desc(const coocc_conv_desc* d) {
+  if (!d) return COOCC_ERR_ARG;
+  if (d->ksize != 1 && d->ksize != 3) return COOCC_ERR_ARG;
+  if (d->stride != 1 && d->stride != 2) return COOCC_ERR_ARG;
+  if (d->dtype != COOCC_DTYPE_TF32 && d->dtype != COOCC_DTYPE_BF16) return COOCC_ERR_ARG;
+  if (d->X < 1 || d->Y < 1 || d->Z < 1 || d->Cin < 1 || d->Cout < 1) return COOCC_ERR_ARG;
+  const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
+  if (((long long)d->ldx * es) % 16 || ((long long)d->ldy * es) % 16) return COOCC_ERR_ALIGN;
+  if (((long long)d->Cin * es) % 16) return COOCC_ERR_ALIGN;   // weight rows (taps*Cin) must be 16B multiples
+  if (d->ldx < d->Cin || d->ldy < d->Cout) return COOCC_ERR_ARG;
+  return 0;
+}
+
+extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, float* y,
+                                long long ldo, const float* bias, int relu, float* stats,
+                                void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if ((rc = init_driver_api())) return rc;
+  const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
+  const int taps = d->ksize == 3 ? 27 : 1;
+  const int oX = out_dim(d->X, d->ksize, d->stride), oY = out_dim(d->Y, d->ksize, d->stride),
+            oZ = out_dim(d->Z, d->ksize, d->stride);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = MODE_FPROP;
+  p.M = oX * oY * oZ;
+  p.N = d->Cout;
+  p.BN = pick_bn(d->Cout);
+  p.taps = taps;
+  p.Kc = d->Cin;
+  p.Cin = d->Cin;
+  p.oX = oX; p.oY = oY; p.oZ = oZ;
+  p.cstride = d->stride;
+  p.lo = -(d->ksize / 2);
+  p.out = y; p.ldc = ldo; p.bias = bias; p.relu = relu; p.stats = stats;
+  p.ksplit = 1;
+  const int bke = 128 / es;
+  const bool plain = (d->ksize == 1 && d->stride == 1);
+  p.a_im2col = plain ? 0 : 1;
+  if (plain) {
+    rc = make_tm_2d(&p.tmA, x, es, p.M, d->Cin, d->ldx, bke, kBM, false);
+  } else {
+    const int pad = d->ksize / 2;
+    rc = make_tm_im2col(&p.tmA, x, es, d->X, d->Y, d->Z, d->Cin, d->ldx, -pad, pad - (d->ksize - 1),
+                        d->stride, bke, kBM, false);
+  }
+  if (rc) return rc;
+  rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, bke,
+                  p.BN, false);
+  if (rc) return rc;
+  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN);
+  return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+}
+
+// dX[v, ci] = sum_{tap,co} dY[v - tap + pad, co] W[co, tap, ci]; stride-1 convolutions only
+// (for stride 2 the caller scatters dY onto the input lattice first, see conv3d_dgrad docs).
+extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, float* dx,
+                                  long long ldo, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (d->stride != 1) return COOCC_ERR_ARG;
+  if ((rc = init_driver_api())) return rc;
+  const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
+  const int taps = d->ksize == 3 ? 27 : 1;
+  const int ch = 128 / es;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = MODE_DGRAD;
+  p.M = d->X * d->Y * d->Z;
+  p.N = d->Cin;
+  // MN-major B tiles are loaded in chunks of `ch` input channels
+  p.BN = ((d->Cin + ch - 1) / ch) * ch;
+  if (p.BN > kMaxBN) {
+    p.BN = kMaxBN;
+    for (int t = 256; t >= ch; t -= ch)
+      if (d->Cin % t == 0) { p.BN = t; break; }
+  }
+  p.taps = taps;
+  p.Kc = d->Cout;
+  p.Cin = d->Cin;
+  p.oX = d->X; p.oY = d->Y; p.oZ = d->Z;
+  p.cstride = 1;
+  p.lo = -(d->ksize / 2);
+  p.out = dx; p.ldc = ldo; p.bias = nullptr; p.relu = 0; p.stats = nullptr;
+  p.ksplit = 1;
+  const bool plain = (d->ksize == 1);
+  p.a_im2col = plain ? 0 : 1;
+  if (plain) {
+    rc = make_tm_2d(&p.tmA, dy, es, p.M, d->Cout, d->ldy, ch, kBM, false);
+  } else {
+    const int pad = d->ksize / 2;
+    rc = make_tm_im2col(&p.tmA, dy, es, d->X, d->Y, d->Z, d->Cout, d->ldy, -pad,
+                        pad - (d->ksize - 1), 1, ch, kBM, false);
+  }
+  if (rc) return rc;
+  rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, ch, ch, true);
+  if (rc) return rc;
+  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN);
+  return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+}
+
+// dW[co, tap, ci] += sum_v dY[v, co] X[v*s + tap - pad, ci]   (dw must be zero-filled by the caller)
+extern "C" int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const void* dy, float* dw,
+                                  void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if ((rc = init_driver_api())) return rc;
+  const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
+  const int taps = d->ksize == 3 ? 27 : 1;
+  const int ch = 128 / es;
+  const int oX = out_dim(d->X, d->ksize, d->stride), oY = out_dim(d->Y, d->ksize, d->stride),
+            oZ = out_dim(d->Z, d->ksize, d->stride);
+  const long long Vo = (long long)oX * oY * oZ;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = MODE_WGRAD;
+  p.M = d->Cout;
+  p.N = d->Cin;
+  p.BN = ((d->Cin + ch - 1) / ch) * ch;
+  if (p.BN > kMaxBN) {
+    p.BN = kMaxBN;
+    for (int t = 256; t >= ch; t -= ch)
+      if (d->Cin % t == 0) { p.BN = t; break; }
+  }
+  p.taps = taps;
+  p.Cin = d->Cin;
+  p.oX = oX; p.oY = oY; p.oZ = oZ;
+  p.cstride = d->stride;
+  p.lo = -(d->ksize / 2);
+  p.out = dw; p.ldc = d->Cin;
+  p.nvb = (int)((Vo + ch - 1) / ch);
+  const int base_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN) * taps;
+  int ks = (2 * g_num_sms + base_tiles - 1) / base_tiles;      // aim for >= 2 waves of work
+  if (ks < 1) ks = 1;
+  if (ks > p.nvb) ks = p.nvb;
+  if (ks > 64) ks = 64;
+  p.ksplit = ks;
+  const bool plain = (d->ksize == 1 && d->stride == 1);
+  p.a_im2col = plain ? 0 : 1;
+  rc = make_tm_2d(&p.tmA, dy, es, Vo, d->Cout, d->ldy, ch, ch, true);
+  if (rc) return rc;
+  if (plain) {
+    rc = make_tm_2d(&p.tmB, x, es, Vo, d->Cin, d->ldx, ch, ch, true);
+  } else {
+    const int pad = d->ksize / 2;
+    rc = make_tm_im2col(&p.tmB, x, es, d->X, d->Y, d->Z, d->Cin, d->ldx, -pad, pad - (d->ksize - 1),
+                        d->stride, ch, ch, true);
+  }
+  if (rc) return rc;
+  const int ntiles = base_tiles * ks;
+  return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+}

@@ -1,0 +1,591 @@
+// gsf_index.cu -- GSFusion index pipeline (integer-exact, no autograd):
+//   pack      : strided [C,X,Y,Z] fp32 -> NDHWC rows + occupancy flag (sum over channels != 0)
+//   compact   : flags -> ordered occupied-voxel list + voxel->rank table (torch.nonzero order)
+//   fps       : furthest point sampling of the occupied voxels, one thread-block cluster
+//   rep_topk  : exact K nearest keys of every representative, window search on the voxel lattice
+//   ball_assign: ball-query propagation + "last writer wins" assignment as an atomicMax
+//
+// Replaces P/coocc/fuser/bifuser_n.py:38-125,129-135 and the two CUDA ops it calls
+// (mmdet3d/ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:26-141,
+//  mmdet3d/ops/ball_query/src/ball_query_cuda.cu:11-54).
+//
+// All coordinates are integer voxel indices, so every distance is an exact integer:
+// `val < 13.3` <=> d2 <= 176 and `d2 < 6*6` are evaluated in int32.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/coocc_b200.h"
+
+namespace cg = cooperative_groups;
+
+namespace coocc {
+
+// ------------------------------------------------------------------------------------------
+// pack: transpose a strided channel-major grid into NDHWC rows and flag occupied voxels
+// ------------------------------------------------------------------------------------------
+// grid: (tiles along the fast axis, other axis a, other axis b); block 32x8.
+// Each block owns 32 voxels along the axis with the smallest stride and loops over all channels.
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, long long sC,
+                                                   long long sX, long long sY, long long sZ, int C,
+                                                   int X, int Y, int Z, int fast, float* __restrict__ dst,
+                                                   long long ldo, uint8_t* __restrict__ flags) {
+  __shared__ float tile[32][33];
+  __shared__ float rowsum[8][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  // decode block -> (fast-axis start, a, b)
+  const int dims[3] = {X, Y, Z};
+  const int a_ax = (fast == 0) ? 1 : 0;
+  const int b_ax = (fast == 2) ? 1 : 2;
+  const int f0 = blockIdx.x * 32;
+  const int ca = blockIdx.y, cb = blockIdx.z;
+  int c3[3];
+  c3[a_ax] = ca;
+  c3[b_ax] = cb;
+  const long long strides[3] = {sX, sY, sZ};
+  const int nf = dims[fast];
+  // voxel handled by lane `l` of this block: fast coordinate f0 + l
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // ty handles voxels ty*4 .. ty*4+3 in the write phase
+  for (int cbase = 0; cbase < C; cbase += 32) {
+    // read: warp ty reads channels cbase + ty*4 + j, lane = position along the fast axis
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = cbase + ty * 4 + j;
+      const int f = f0 + tx;
+      float v = 0.f;
+      if (c < C && f < nf) {
+        c3[fast] = f;
+        v = src[c * sC + c3[0] * strides[0] + c3[1] * strides[1] + c3[2] * strides[2]];
+      }
+      tile[ty * 4 + j][tx] = v;
+    }
+    __syncthreads();
+    // write: warp ty writes voxel rows ty*4 + j, lane = channel
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = ty * 4 + j;
+      const int f = f0 + l;
+      const float v = tile[tx][l];
+      if (f < nf && cbase + tx < C) {
+        c3[fast] = f;
+        const long long vox = ((long long)c3[0] * Y + c3[1]) * Z + c3[2];
+        dst[vox * ldo + cbase + tx] = v;
+      }
+      float s = v;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      acc[j] += s;
+    }
+    __syncthreads();
+  }
+  if (tx == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rowsum[ty][j] = acc[j];
+  }
+  __syncthreads();
+  if (ty == 0) {
+    const int f = f0 + tx;
+    if (f < nf) {
+      c3[fast] = f;
+      const long long vox = ((long long)c3[0] * Y + c3[1]) * Z + c3[2];
+      flags[vox] = rowsum[tx >> 2][tx & 3] != 0.f ? 1 : 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// compact: ordered stream compaction of the flags (3 passes, deterministic)
+// ------------------------------------------------------------------------------------------
+constexpr int kChunk = 2048;   // voxels per block in passes 1 and 3 (256 threads x 8)
+
+__global__ void __launch_bounds__(256) count_kernel(const uint8_t* __restrict__ flags, int V,
+                                                    int* __restrict__ chunk_cnt) {
+  const int base = blockIdx.x * kChunk;
+  int c = 0;
+  for (int i = threadIdx.x; i < kChunk; i += 256) {
+    const int v = base + i;
+    c += (v < V && flags[v]) ? 1 : 0;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int i = 0; i < 8; ++i) s += ws[i];
+    chunk_cnt[blockIdx.x] = s;
+  }
+}
+
+// single block: exclusive scan of the chunk counts in place; total -> *count
+__global__ void __launch_bounds__(1024) scan_kernel(int* __restrict__ chunk_cnt, int nchunks,
+                                                    int* __restrict__ count) {
+  __shared__ int ws[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nchunks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nchunks ? chunk_cnt[i] : 0;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if ((threadIdx.x & 31) >= o) s += t;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = ws[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += t;
+      }
+      ws[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+    const int incl = s + warp_off + carry;
+    if (i < nchunks) chunk_cnt[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry;
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(const uint8_t* __restrict__ flags, int V,
+                                                      const int* __restrict__ chunk_off,
+                                                      int* __restrict__ list, int* __restrict__ rank) {
+  // thread t owns 8 consecutive voxels so that ranks are assigned in voxel order
+  const int base = blockIdx.x * kChunk + threadIdx.x * 8;
+  int f[8], c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int v = base + i;
+    f[i] = (v < V && flags[v]) ? 1 : 0;
+    c += f[i];
+  }
+  int s = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) >= o) s += t;
+  }
+  __shared__ int ws[8];
+  if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  int off = chunk_off[blockIdx.x] + s - c;
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) off += ws[w];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int v = base + i;
+    if (v < V) {
+      if (f[i]) {
+        list[off] = v;
+        rank[v] = off;
+        ++off;
+      } else {
+        rank[v] = -1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// FPS: one thread-block cluster, running min-distance in registers, packed coords in smem
+// ------------------------------------------------------------------------------------------
+constexpr int kFpsThreads = 512;
+constexpr uint32_t kInfDist = 0x7fffffffu;   // stands in for the reference's 1e10 initial value
+
+struct FpsCand {
+  uint32_t d;      // running min squared distance of the candidate (maximised)
+  uint32_t t;      // tie key (minimised): bitrev(k mod bs) << 22 | k / bs
+  uint32_t c;      // packed coordinate x | y << 10 | z << 20
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t pack_xyz(int v, int Y, int Z) {
+  const int z = v % Z;
+  const int t = v / Z;
+  const int y = t % Y;
+  const int x = t / Y;
+  return (uint32_t)x | ((uint32_t)y << 10) | ((uint32_t)z << 20);
+}
+__device__ __forceinline__ int d2_packed(uint32_t a, uint32_t b) {
+  const int dx = (int)(a & 1023u) - (int)(b & 1023u);
+  const int dy = (int)((a >> 10) & 1023u) - (int)((b >> 10) & 1023u);
+  const int dz = (int)(a >> 20) - (int)(b >> 20);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+// better(a, b): a beats b  (larger distance, then smaller tie key)
+__device__ __forceinline__ void warp_best(uint32_t& d, uint32_t& t, uint32_t& c) {
+  const uint32_t md = __reduce_max_sync(0xffffffffu, d);
+  const uint32_t mt = __reduce_min_sync(0xffffffffu, d == md ? t : 0xffffffffu);
+  const uint32_t src = __ffs(__ballot_sync(0xffffffffu, d == md && t == mt)) - 1;
+  c = __shfl_sync(0xffffffffu, c, src);
+  d = md;
+  t = mt;
+}
+
+struct FpsJob {
+  const int* list;   // occupied voxel ids (ascending), the points
+  const int* count;  // device pointer to N
+  int* out;          // [m] sampled indices into list
+};
+
+template <int PPT>
+__global__ void __launch_bounds__(kFpsThreads, 1)
+fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned CS = cluster.num_blocks();
+  const unsigned rank = cluster.block_rank();
+  const FpsJob job = (blockIdx.y == 0) ? job0 : job1;
+  const int n = *job.count;
+  extern __shared__ uint32_t coords[];                // [PPT * kFpsThreads]
+  __shared__ FpsCand wbest[2][kFpsThreads / 32];
+  __shared__ FpsCand cbest[2][16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // block-size rule of the reference launcher (opt_n_threads): 2^floor(log2 n), capped at 1024
+  int log2bs = 0;
+  if (log2bs_override >= 0) {
+    log2bs = log2bs_override;
+  } else {
+    while ((2 << log2bs) <= n && log2bs < 10) ++log2bs;
+  }
+  const uint32_t bsmask = (1u << log2bs) - 1u;
+
+  uint32_t dist[PPT];
+  const int stride = CS * kFpsThreads;
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int k = i * stride + rank * kFpsThreads + tid;
+    coords[i * kFpsThreads + tid] = k < n ? pack_xyz(job.list[k], Y, Z) : 0u;
+    dist[i] = kInfDist;
+  }
+  uint32_t cur = pack_xyz(job.list[0], Y, Z);          // start index 0 (furthest_point_sample.py)
+  if (rank == 0 && tid == 0 && m > 0) job.out[0] = 0;
+  __syncthreads();
+  if (CS > 1) cluster.sync();
+
+  for (int j = 1; j < m; ++j) {
+    const int par = j & 1;
+    uint32_t bd = 0, bt = 0xffffffffu, bc = 0;
+    bool have = false;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int k = i * stride + rank * kFpsThreads + tid;
+      if (k < n) {
+        const uint32_t c = coords[i * kFpsThreads + tid];
+        const uint32_t d = min((uint32_t)d2_packed(c, cur), dist[i]);
+        dist[i] = d;
+        const uint32_t t = (__brev((uint32_t)k & bsmask) >> (32 - log2bs) << 22) | ((uint32_t)k >> log2bs);
+        if (!have || d > bd || (d == bd && t < bt)) {
+          bd = d; bt = t; bc = c; have = true;
+        }
+      }
+    }
+    if (!have) { bd = 0; bt = 0xffffffffu; }
+    warp_best(bd, bt, bc);
+    if (lane == 0) {
+      wbest[par][warp].d = bd; wbest[par][warp].t = bt; wbest[par][warp].c = bc;
+    }
+    __syncthreads();
+    // every warp reduces the per-warp candidates redundantly (no second block barrier)
+    {
+      const bool ok = lane < kFpsThreads / 32;
+      bd = ok ? wbest[par][lane].d : 0u;
+      bt = ok ? wbest[par][lane].t : 0xffffffffu;
+      bc = ok ? wbest[par][lane].c : 0u;
+      warp_best(bd, bt, bc);
+    }
+    if (CS > 1) {
+      if (warp == 0 && lane < CS) {
+        FpsCand* remote = cluster.map_shared_rank(&cbest[par][rank], lane);
+        remote->d = bd; remote->t = bt; remote->c = bc;
+      }
+      cluster.sync();
+      const bool ok = lane < CS;
+      bd = ok ? cbest[par][lane].d : 0u;
+      bt = ok ? cbest[par][lane].t : 0xffffffffu;
+      bc = ok ? cbest[par][lane].c : 0u;
+      warp_best(bd, bt, bc);
+    }
+    cur = bc;
+    if (rank == 0 && tid == 0) {
+      const uint32_t kmod = __brev(bt >> 22) >> (32 - log2bs);
+      job.out[j] = (int)(((bt & 0x3fffffu) << log2bs) | kmod);
+    }
+  }
+  if (CS > 1) cluster.sync();
+}
+
+// ------------------------------------------------------------------------------------------
+// rep_topk: K nearest keys (d2 <= 176) of every representative, ordered (d2 asc, key asc)
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxK = 8;
+constexpr int kTopkR = 13;            // floor(sqrt(176))
+constexpr int kTopkD2 = 176;          // val < 13.3  <=>  d2 <= 176 on integer coordinates
+
+__global__ void __launch_bounds__(128) rep_topk_kernel(const int* __restrict__ rep_idx, int nrep,
+                                                       const int* __restrict__ qlist,
+                                                       const int* __restrict__ key_rank, int X, int Y,
+                                                       int Z, int K, int* __restrict__ out_idx,
+                                                       int* __restrict__ out_d2) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= nrep) return;
+  const int v0 = qlist[rep_idx[r]];
+  const int z0 = v0 % Z, y0 = (v0 / Z) % Y, x0 = v0 / (Z * Y);
+  uint32_t bd[kMaxK], bv[kMaxK];
+#pragma unroll
+  for (int i = 0; i < kMaxK; ++i) { bd[i] = 0xffffffffu; bv[i] = 0xffffffffu; }
+  const int W = 2 * kTopkR + 1;
+  const int zlo = max(0, z0 - kTopkR), zhi = min(Z - 1, z0 + kTopkR);
+  const int nz = zhi - zlo + 1;
+  const int total = W * W * nz;
+  for (int e = lane; e < total; e += 32) {
+    const int z = zlo + e % nz;
+    const int t = e / nz;
+    const int dy = t % W - kTopkR, dx = t / W - kTopkR;
+    const int x = x0 + dx, y = y0 + dy;
+    if (x < 0 || x >= X || y < 0 || y >= Y) continue;
+    const int dz = z - z0;
+    const uint32_t d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 > (uint32_t)kTopkD2) continue;
+    const int v = (x * Y + y) * Z + z;
+    if (key_rank[v] < 0) continue;
+    // insert (d2, v) into the lane-local sorted list
+    uint32_t cd = d2, cv = (uint32_t)v;
+#pragma unroll
+    for (int i = 0; i < kMaxK; ++i) {
+      if (i < K) {
+        const bool lt = cd < bd[i] || (cd == bd[i] && cv < bv[i]);
+        if (lt) {
+          const uint32_t td = bd[i], tv = bv[i];
+          bd[i] = cd; bv[i] = cv; cd = td; cv = tv;
+        }
+      }
+    }
+  }
+  // K rounds of warp arg-min; the winning lane pops its head
+  for (int k = 0; k < K; ++k) {
+    const uint32_t md = __reduce_min_sync(0xffffffffu, bd[0]);
+    const uint32_t mv = __reduce_min_sync(0xffffffffu, bd[0] == md ? bv[0] : 0xffffffffu);
+    const bool win = (bd[0] == md && bv[0] == mv && md != 0xffffffffu);
+    if (win) {
+#pragma unroll
+      for (int i = 0; i + 1 < kMaxK; ++i) { bd[i] = bd[i + 1]; bv[i] = bv[i + 1]; }
+      bd[kMaxK - 1] = 0xffffffffu; bv[kMaxK - 1] = 0xffffffffu;
+    }
+    if (lane == 0) {
+      const bool valid = md != 0xffffffffu;
+      out_idx[r * K + k] = valid ? key_rank[mv] : -1;
+      out_d2[r * K + k] = valid ? (int)md : -1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ball_assign: for every representative, the first `nsample` occupied query voxels (ascending
+// voxel order) with d2 < radius^2 inherit its neighbours; the reference's duplicate-index
+// scatter is resolved as "largest representative position wins" (= last writer in
+// (representative, slot) order) with an atomicMax per (k, query).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ball_assign_kernel(const int* __restrict__ rep_idx, int nrep,
+                                                          const int* __restrict__ qlist,
+                                                          const int* __restrict__ q_rank,
+                                                          const int* __restrict__ topk_idx, int X,
+                                                          int Y, int Z, int K, int radius, int nsample,
+                                                          int nq_stride, int* __restrict__ winner,
+                                                          int* __restrict__ group_out) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= nrep) return;
+  const int v0 = qlist[rep_idx[r]];
+  const int z0 = v0 % Z, y0 = (v0 / Z) % Y, x0 = v0 / (Z * Y);
+  uint32_t vmask = 0;
+  for (int k = 0; k < K; ++k) vmask |= (topk_idx[r * K + k] >= 0 ? 1u : 0u) << k;
+  if (vmask == 0 && group_out == nullptr) return;
+  const int W = 2 * radius - 1;            // |d| <= radius-1 suffices for d2 < radius^2
+  const int R = radius - 1;
+  const int r2 = radius * radius;
+  const int total = W * W * W;
+  int cnt = 0;
+  int first = -1;
+  for (int e0 = 0; e0 < total && cnt < nsample; e0 += 32) {
+    const int e = e0 + lane;
+    int q = -1;
+    if (e < total) {
+      const int dz = e % W - R, dy = (e / W) % W - R, dx = e / (W * W) - R;
+      const int x = x0 + dx, y = y0 + dy, z = z0 + dz;
+      if (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z &&
+          dx * dx + dy * dy + dz * dz < r2)
+        q = q_rank[(x * Y + y) * Z + z];
+    }
+    const uint32_t hit = __ballot_sync(0xffffffffu, q >= 0);
+    const int pos = cnt + __popc(hit & ((1u << lane) - 1u));
+    if (q >= 0 && pos < nsample) {
+      for (int k = 0; k < K; ++k)
+        if (vmask & (1u << k)) atomicMax(&winner[k * nq_stride + q], r);
+      if (group_out) group_out[r * nsample + pos] = q;
+    }
+    if (first < 0 && hit) first = __shfl_sync(0xffffffffu, q, __ffs(hit) - 1);
+    cnt += __popc(hit);
+  }
+  if (group_out) {
+    // ball_query pads the unused slots with the first hit (ball_query_cuda.cu:43-47)
+    const int c = min(cnt, nsample);
+    for (int s = c + lane; s < nsample; s += 32) group_out[r * nsample + s] = first < 0 ? 0 : first;
+  }
+}
+
+// K == 1 brute-force branch of the reference (N_q <= 2048, bifuser_n.py:55-60): every query is
+// its own representative; nn[q] = nearest key within the threshold or -1.
+__global__ void __launch_bounds__(128) direct_nn_kernel(const int* __restrict__ qlist,
+                                                        const int* __restrict__ qcount,
+                                                        const int* __restrict__ key_rank, int X, int Y,
+                                                        int Z, int* __restrict__ nn) {
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= *qcount) return;
+  const int v0 = qlist[q];
+  const int z0 = v0 % Z, y0 = (v0 / Z) % Y, x0 = v0 / (Z * Y);
+  const int W = 2 * kTopkR + 1;
+  const int zlo = max(0, z0 - kTopkR), zhi = min(Z - 1, z0 + kTopkR);
+  const int nz = zhi - zlo + 1;
+  uint32_t bd = 0xffffffffu, bv = 0xffffffffu;
+  for (int e = lane; e < W * W * nz; e += 32) {
+    const int z = zlo + e % nz;
+    const int t = e / nz;
+    const int dy = t % W - kTopkR, dx = t / W - kTopkR;
+    const int x = x0 + dx, y = y0 + dy;
+    if (x < 0 || x >= X || y < 0 || y >= Y) continue;
+    const int dz = z - z0;
+    const uint32_t d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 > (uint32_t)kTopkD2) continue;
+    const int v = (x * Y + y) * Z + z;
+    if (key_rank[v] < 0) continue;
+    if (d2 < bd || (d2 == bd && (uint32_t)v < bv)) { bd = d2; bv = (uint32_t)v; }
+  }
+  const uint32_t md = __reduce_min_sync(0xffffffffu, bd);
+  const uint32_t mv = __reduce_min_sync(0xffffffffu, bd == md ? bv : 0xffffffffu);
+  if (lane == 0) nn[q] = md != 0xffffffffu ? key_rank[mv] : -1;
+}
+
+}  // namespace coocc
+
+using namespace coocc;
+
+extern "C" int coocc_gsf_pack(const float* src, long long sC, long long sX, long long sY, long long sZ,
+                              int C, int X, int Y, int Z, float* dst, long long ldo,
+                              unsigned char* flags, void* stream) {
+  if (!src || !dst || !flags || C < 1 || X < 1 || Y < 1 || Z < 1) return COOCC_ERR_ARG;
+  // fast axis = spatial axis with the smallest stride (coalesced reads along it)
+  int fast = 2;
+  long long best = sZ;
+  if (sY < best) { best = sY; fast = 1; }
+  if (sX < best) { best = sX; fast = 0; }
+  const int dims[3] = {X, Y, Z};
+  const int a_ax = (fast == 0) ? 1 : 0;
+  const int b_ax = (fast == 2) ? 1 : 2;
+  if (dims[a_ax] > 65535 || dims[b_ax] > 65535) return COOCC_ERR_CAPACITY;
+  dim3 grid((dims[fast] + 31) / 32, dims[a_ax], dims[b_ax]);
+  pack_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, sC, sX, sY, sZ, C, X, Y, Z, fast, dst,
+                                                            ldo, flags);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+
+extern "C" long long coocc_gsf_compact_workspace(int V) {
+  return (long long)((V + kChunk - 1) / kChunk) * sizeof(int);
+}
+
+extern "C" int coocc_gsf_compact(const unsigned char* flags, int V, int* list, int* rank, int* count,
+                                 void* workspace, void* stream) {
+  if (!flags || !list || !rank || !count || !workspace || V < 1) return COOCC_ERR_ARG;
+  const int nchunks = (V + kChunk - 1) / kChunk;
+  int* chunk = reinterpret_cast<int*>(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  count_kernel<<<nchunks, 256, 0, st>>>(flags, V, chunk);
+  scan_kernel<<<1, 1024, 0, st>>>(chunk, nchunks, count);
+  scatter_kernel<<<nchunks, 256, 0, st>>>(flags, V, chunk, list, rank);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+
+template <int PPT>
+static int launch_fps(FpsJob j0, FpsJob j1, int njobs, int m, int Y, int Z, int cs, int log2bs,
+                      cudaStream_t st) {
+  const size_t smem = (size_t)PPT * kFpsThreads * sizeof(uint32_t);
+  cudaError_t e = cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return COOCC_ERR_CUDA;
+  if (cs > 8) {
+    e = cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return COOCC_ERR_CUDA;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(cs, njobs, 1);
+  cfg.blockDim = dim3(kFpsThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, fps_kernel<PPT>, j0, j1, m, Y, Z, log2bs);
+  return e == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+
+// Runs one or two independent FPS problems (both GSFusion directions) in one launch, one cluster
+// each.  n_max = upper bound of the point counts (sizes the cluster); the exact counts are read
+// on the device from count0/count1.
+extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, const int* list1,
+                             const int* count1, int* out1, int n_max, int m, int Y, int Z,
+                             void* stream) {
+  if (!list0 || !count0 || !out0 || n_max < 1 || m < 1) return COOCC_ERR_ARG;
+  if (Y > 1023 || Z > 1023) return COOCC_ERR_CAPACITY;
+  const int njobs = list1 ? 2 : 1;
+  FpsJob j0{list0, count0, out0}, j1{list1 ? list1 : list0, list1 ? count1 : count0, list1 ? out1 : out0};
+  int cs = 1;
+  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 8) cs *= 2;
+  const int ppt = (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ppt <= 4) return launch_fps<4>(j0, j1, njobs, m, Y, Z, cs, -1, st);
+  if (ppt <= 8) return launch_fps<8>(j0, j1, njobs, m, Y, Z, cs, -1, st);
+  if (ppt <= 16) return launch_fps<16>(j0, j1, njobs, m, Y, Z, cs, -1, st);
+  if (ppt <= 32) return launch_fps<32>(j0, j1, njobs, m, Y, Z, cs, -1, st);
+  if (ppt <= 64) return launch_fps<64>(j0, j1, njobs, m, Y, Z, cs, -1, st);
+  return COOCC_ERR_CAPACITY;
+}
+
+extern "C" int coocc_gsf_rep_topk(const int* rep_idx, int nrep, const int* qlist, const int* key_rank,
+                                  int X, int Y, int Z, int K, int* out_idx, int* out_d2, void* stream) {
+  if (!rep_idx || !qlist || !key_rank || !out_idx || !out_d2 || K < 1 || K > kMaxK) return COOCC_ERR_ARG;
+  rep_topk_kernel<<<(nrep + 3) / 4, 128, 0, (cudaStream_t)stream>>>(rep_idx, nrep, qlist, key_rank, X, Y,
+                                                                   Z, K, out_idx, out_d2);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+
+extern "C" int coocc_gsf_ball_assign(const int* rep_idx, int nrep, const int* qlist, const int* q_rank,
+                                     const int* topk_idx, int X, int Y, int Z, int K, int radius,
+                                     int nsample, int nq_stride, int* winner, int* group_out,
+                                     void* stream) {
+  if (!rep_idx || !qlist || !q_rank || !topk_idx || !winner || K < 1 || K > kMaxK || radius < 1)
+    return COOCC_ERR_ARG;
+  ball_assign_kernel<<<(nrep + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      rep_idx, nrep, qlist, q_rank, topk_idx, X, Y, Z, K, radius, nsample, nq_stride, winner, group_out);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+
+extern "C" int coocc_gsf_direct_nn(const int* qlist, const int* qcount, int nq_max, const int* key_rank,
+                                   int X, int Y, int Z, int* nn, void* stream) {
+  if (!qlist || !qcount || !key_rank || !nn || nq_max < 1) return COOCC_ERR_ARG;
+  direct_nn_kernel<<<(nq_max + 3) / 4, 128, 0, (cudaStream_t)stream>>>(qlist, qcount, key_rank, X, Y, Z, nn);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
