@@ -1,0 +1,280 @@
+// gsf_feat.cu -- GSFusion feature path, forward and backward.
+//
+// Reference: P/coocc/fuser/bifuser_n.py:138-172 -- gather the K neighbour rows of every query,
+// `knn_enc` = ReLU(Linear(K*C -> C)), modulate by the query's own row, scatter into a zero grid,
+// concatenate [img, pts, fused_img, fused_pts].
+//
+// Restructuring (result-preserving): the Linear is linear before its ReLU,
+//     Linear(cat_k f_k) = b + sum_k W_k f_k ,
+// and only the <= 2048 representatives (+ one "index -1 -> last key" row, Q3) have distinct
+// neighbours, so P[k][r] = W_k * feat(key_k(r)) is computed once per representative (a tiny fp32
+// GEMM) and every query just sums K rows of P that stay L2-resident.  Outputs are written
+// straight into the channel slices of the [V, 4C] concat buffer the first con_enc conv reads.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/coocc_b200.h"
+
+namespace coocc {
+
+// rows[k][r][:] = grid[ lookup[idx] ][:]  with idx = topk_idx[r][k] (r < nrep) or -1 (r == nrep);
+// idx == -1 selects the LAST lookup entry (python negative indexing, bifuser_n.py:139,144);
+// rows of invalid (r, k) pairs are zero.  err[0] is set if an index exceeds the lookup table
+// (the reference raises IndexError there).
+__global__ void __launch_bounds__(128) gather_rows_kernel(const float* __restrict__ grid, long long ld,
+                                                          const int* __restrict__ lookup,
+                                                          const int* __restrict__ lookup_count,
+                                                          const int* __restrict__ topk_idx, int nrep,
+                                                          int K, int C, float* __restrict__ rows,
+                                                          int* __restrict__ err) {
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int total = (nrep + 1) * K;
+  if (w >= total) return;
+  const int k = w / (nrep + 1), r = w % (nrep + 1);
+  const int n = *lookup_count;
+  int idx = (r < nrep) ? topk_idx[r * K + k] : -1;
+  float* dst = rows + ((long long)k * (nrep + 1) + r) * C;
+  bool zero = (r < nrep && idx < 0) || n <= 0;
+  if (!zero) {
+    if (idx < 0) idx = n - 1;
+    if (idx >= n) {
+      if (lane == 0) atomicExch(err, 1);
+      zero = true;
+    }
+  }
+  if (zero) {
+    for (int c = lane; c < C; c += 32) dst[c] = 0.f;
+    return;
+  }
+  const float* src = grid + (long long)lookup[idx] * ld;
+  for (int c = lane; c < C; c += 32) dst[c] = src[c];
+}
+
+// Generic small fp32 GEMM, C[i][j] (+)= sum_k A(i,k) * B(k,j), arbitrary element strides.
+// 64x64 tile, 256 threads, 4x4 micro-tile; sizes here are <= (2049*K) x 128 x 128.
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int Kd, const float* __restrict__ A,
+                                                    long long sAi, long long sAk,
+                                                    const float* __restrict__ B, long long sBk,
+                                                    long long sBj, float* __restrict__ Cm, long long ldc,
+                                                    int accumulate) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < Kd; k0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      // choose the mapping whose consecutive threads walk the unit-stride axis
+      int kk, ii;
+      if (sAk == 1) { kk = e % 16; ii = e / 16; } else { ii = e % 64; kk = e / 64; }
+      const int gi = i0 + ii, gk = k0 + kk;
+      As[kk][ii] = (gi < M && gk < Kd) ? A[gi * sAi + gk * sAk] : 0.f;
+      int kb, jj;
+      if (sBk == 1) { kb = e % 16; jj = e / 16; } else { jj = e % 64; kb = e / 64; }
+      const int gj = j0 + jj, gk2 = k0 + kb;
+      Bs[kb][jj] = (gj < N && gk2 < Kd) ? B[gk2 * sBk + gj * sBj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = As[kk][ti * 4 + u]; b[u] = Bs[kk][tj * 4 + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int gi = i0 + ti * 4 + u;
+    if (gi >= M) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int gj = j0 + tj * 4 + v;
+      if (gj < N) {
+        float* o = Cm + gi * ldc + gj;
+        *o = accumulate ? (*o + acc[u][v]) : acc[u][v];
+      }
+    }
+  }
+}
+
+// out[v_q][:] = relu(bias + sum_k P[k][w_k(q)][:]) * own[v_q][:]
+// w_k(q) = winner[k][q] (a representative position) or nrep when the query is unassigned.
+__global__ void __launch_bounds__(128) modulate_fwd_kernel(const float* __restrict__ P,
+                                                           const float* __restrict__ bias,
+                                                           const int* __restrict__ winner, int nq_stride,
+                                                           const int* __restrict__ qlist,
+                                                           const int* __restrict__ qcount, int nrep,
+                                                           int K, int C, const float* __restrict__ own,
+                                                           long long ld_own, float* __restrict__ dst,
+                                                           long long ld_dst) {
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= *qcount) return;
+  const long long v = qlist[q];
+  for (int c = lane; c < C; c += 32) {
+    float s = bias[c];
+    for (int k = 0; k < K; ++k) {
+      int w = winner[k * nq_stride + q];
+      if (w < 0) w = nrep;
+      s += P[((long long)k * (nrep + 1) + w) * C + c];
+    }
+    dst[v * ld_dst + c] = fmaxf(s, 0.f) * own[v * ld_own + c];
+  }
+}
+
+// Backward of modulate for one direction.  g = d(out)[v_q]; recomputes s.
+//   d_own[v_q] += g * relu(s);  ds = g * own * [s > 0];  dP[k][w_k(q)] += ds;  dbias += sum_q ds
+__global__ void __launch_bounds__(128) modulate_bwd_kernel(const float* __restrict__ P,
+                                                           const float* __restrict__ bias,
+                                                           const int* __restrict__ winner, int nq_stride,
+                                                           const int* __restrict__ qlist,
+                                                           const int* __restrict__ qcount, int nrep,
+                                                           int K, int C, const float* __restrict__ own,
+                                                           long long ld_own, const float* __restrict__ g,
+                                                           long long ld_g, float* __restrict__ d_own,
+                                                           long long ld_down, float* __restrict__ dP,
+                                                           float* __restrict__ dbias) {
+  extern __shared__ float sb[];   // [C] block partial of dbias
+  for (int c = threadIdx.x; c < C; c += 128) sb[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int n = *qcount;
+  for (int q = blockIdx.x * 4 + (threadIdx.x >> 5); q < n; q += gridDim.x * 4) {
+    const long long v = qlist[q];
+    int w[8];
+    for (int k = 0; k < K; ++k) {
+      w[k] = winner[k * nq_stride + q];
+      if (w[k] < 0) w[k] = nrep;
+    }
+    for (int c = lane; c < C; c += 32) {
+      float s = bias[c];
+      for (int k = 0; k < K; ++k) s += P[((long long)k * (nrep + 1) + w[k]) * C + c];
+      const float gv = g[v * ld_g + c];
+      d_own[v * ld_down + c] += gv * fmaxf(s, 0.f);
+      const float ds = s > 0.f ? gv * own[v * ld_own + c] : 0.f;
+      if (ds != 0.f) {
+        for (int k = 0; k < K; ++k) atomicAdd(&dP[((long long)k * (nrep + 1) + w[k]) * C + c], ds);
+        atomicAdd(&sb[c], ds);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 128)
+    if (sb[c] != 0.f) atomicAdd(&dbias[c], sb[c]);
+}
+
+// d_grid[ lookup[idx(r,k)] ][:] += dF[k][r][:]   (duplicates across r, k -> atomics)
+__global__ void __launch_bounds__(128) scatter_rows_kernel(const float* __restrict__ dF,
+                                                           const int* __restrict__ lookup,
+                                                           const int* __restrict__ lookup_count,
+                                                           const int* __restrict__ topk_idx, int nrep,
+                                                           int K, int C, float* __restrict__ d_grid,
+                                                           long long ld) {
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int total = (nrep + 1) * K;
+  if (w >= total) return;
+  const int k = w / (nrep + 1), r = w % (nrep + 1);
+  const int n = *lookup_count;
+  int idx = (r < nrep) ? topk_idx[r * K + k] : -1;
+  if ((r < nrep && idx < 0) || n <= 0) return;
+  if (idx < 0) idx = n - 1;
+  if (idx >= n) return;
+  const float* src = dF + ((long long)k * (nrep + 1) + r) * C;
+  float* dst = d_grid + (long long)lookup[idx] * ld;
+  for (int c = lane; c < C; c += 32) {
+    const float x = src[c];
+    if (x != 0.f) atomicAdd(&dst[c], x);
+  }
+}
+
+__global__ void iota_kernel(int* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+// small-N direct mode (K == 1): winner[q] = q where nn[q] >= 0, else -1
+__global__ void direct_winner_kernel(const int* __restrict__ nn, const int* __restrict__ qcount,
+                                     int* __restrict__ winner, int nq_max) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq_max) winner[q] = (q < *qcount && nn[q] >= 0) ? q : -1;
+}
+
+}  // namespace coocc
+
+using namespace coocc;
+
+#define CK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA)
+
+extern "C" int coocc_gsf_gather_rows(const float* grid, long long ld, const int* lookup,
+                                     const int* lookup_count, const int* topk_idx, int nrep, int K, int C,
+                                     float* rows, int* err, void* stream) {
+  if (!grid || !lookup || !lookup_count || !topk_idx || !rows || !err || K < 1 || K > 8) return COOCC_ERR_ARG;
+  const int total = (nrep + 1) * K;
+  gather_rows_kernel<<<(total + 3) / 4, 128, 0, (cudaStream_t)stream>>>(grid, ld, lookup, lookup_count,
+                                                                       topk_idx, nrep, K, C, rows, err);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_sgemm(int M, int N, int Kd, const float* A, long long sAi, long long sAk,
+                           const float* B, long long sBk, long long sBj, float* Cm, long long ldc,
+                           int accumulate, void* stream) {
+  if (!A || !B || !Cm || M < 1 || N < 1 || Kd < 1) return COOCC_ERR_ARG;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  sgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, Kd, A, sAi, sAk, B, sBk, sBj, Cm, ldc, accumulate);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_gsf_modulate_fwd(const float* P, const float* bias, const int* winner, int nq_stride,
+                                      const int* qlist, const int* qcount, int nq_max, int nrep, int K,
+                                      int C, const float* own, long long ld_own, float* dst,
+                                      long long ld_dst, void* stream) {
+  if (!P || !bias || !winner || !qlist || !qcount || !own || !dst || nq_max < 1 || K < 1 || K > 8) return COOCC_ERR_ARG;
+  modulate_fwd_kernel<<<(nq_max + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      P, bias, winner, nq_stride, qlist, qcount, nrep, K, C, own, ld_own, dst, ld_dst);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_gsf_modulate_bwd(const float* P, const float* bias, const int* winner, int nq_stride,
+                                      const int* qlist, const int* qcount, int nq_max, int nrep, int K,
+                                      int C, const float* own, long long ld_own, const float* g,
+                                      long long ld_g, float* d_own, long long ld_down, float* dP,
+                                      float* dbias, void* stream) {
+  if (!P || !bias || !winner || !qlist || !qcount || !own || !g || !d_own || !dP || !dbias || nq_max < 1 ||
+      K < 1 || K > 8)
+    return COOCC_ERR_ARG;
+  int blocks = (nq_max + 3) / 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  modulate_bwd_kernel<<<blocks, 128, C * sizeof(float), (cudaStream_t)stream>>>(
+      P, bias, winner, nq_stride, qlist, qcount, nrep, K, C, own, ld_own, g, ld_g, d_own, ld_down, dP, dbias);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_gsf_scatter_rows(const float* dF, const int* lookup, const int* lookup_count,
+                                      const int* topk_idx, int nrep, int K, int C, float* d_grid,
+                                      long long ld, void* stream) {
+  if (!dF || !lookup || !lookup_count || !topk_idx || !d_grid || K < 1 || K > 8) return COOCC_ERR_ARG;
+  const int total = (nrep + 1) * K;
+  scatter_rows_kernel<<<(total + 3) / 4, 128, 0, (cudaStream_t)stream>>>(dF, lookup, lookup_count, topk_idx,
+                                                                        nrep, K, C, d_grid, ld);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_iota(int* p, int n, void* stream) {
+  if (!p || n < 1) return COOCC_ERR_ARG;
+  iota_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, n);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_gsf_direct_winner(const int* nn, const int* qcount, int* winner, int nq_max,
+                                       void* stream) {
+  if (!nn || !qcount || !winner || nq_max < 1) return COOCC_ERR_ARG;
+  direct_winner_kernel<<<(nq_max + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nn, qcount, winner, nq_max);
+  return CK_LAUNCH();
+}

@@ -1,0 +1,484 @@
+"""torch.autograd plumbing around the C ABI (include/coocc_b200.h).
+
+Tensors cross the boundary as raw device pointers + sizes; PyTorch only owns the memory, the
+stream and the autograd graph.  Activations are "2-D channels-last": a [V, C] fp32 view of the
+reference's [1,C,X,Y,Z] tensor (torch.channels_last_3d), row stride a multiple of 4 elements.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+FPS_NUM = 2048        # P/coocc/fuser/bifuser_n.py:137
+BALL_RADIUS = 6
+BALL_SAMPLES = 200
+
+DT_TF32, DT_BF16 = 0, 1
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _pb(t, byte_off):
+    return ctypes.c_void_p(t.data_ptr() + byte_off)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("coocc_b200 has no CPU path: tensors must live on a CUDA device")
+
+
+# ----------------------------------------------------------------------------------------
+# layout helpers
+# ----------------------------------------------------------------------------------------
+def to_cl2d(x5d):
+    """[1,C,X,Y,Z] -> ([V,C] view, (X,Y,Z)).  Zero-copy when x5d is channels_last_3d."""
+    B, C, X, Y, Z = x5d.shape
+    assert B == 1, "the hot path is batch-1 like the reference (coocc_ray.py:365)"
+    x = x5d.permute(0, 2, 3, 4, 1)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    return x.reshape(X * Y * Z, C), (X, Y, Z)
+
+
+def to_5d(x2d, dims):
+    X, Y, Z = dims
+    return x2d.reshape(1, X, Y, Z, x2d.shape[1]).permute(0, 4, 1, 2, 3)
+
+
+def _rows_ok(t):
+    return t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 \
+        and t.dtype == torch.float32
+
+
+def _as_rows(t):
+    """fp32 [R,C] matrix whose rows are 16-byte aligned (pads the row stride if needed)."""
+    if _rows_ok(t):
+        return t
+    R, C = t.shape
+    ld = (C + 3) // 4 * 4
+    buf = torch.zeros(R, ld, device=t.device, dtype=torch.float32)
+    buf[:, :C] = t
+    return buf[:, :C]
+
+
+def weight_rows(w5d):
+    """[Cout,Cin,k,k,k] parameter -> [Cout, k^3*Cin] matrix in (kx,ky,kz,Cin) order (zero-copy
+    when the parameter is stored channels_last_3d)."""
+    w = w5d.permute(0, 2, 3, 4, 1)
+    if not w.is_contiguous():
+        w = w.contiguous()
+    return w.reshape(w5d.shape[0], -1)
+
+
+def out_dim(n, k, s):
+    return (n + 2 * (k // 2) - k) // s + 1
+
+
+# ----------------------------------------------------------------------------------------
+# convolution / linear on tcgen05
+# ----------------------------------------------------------------------------------------
+def _conv_desc(dims, cin, cout, k, s, ldx, ldy, dtype=DT_TF32):
+    X, Y, Z = dims
+    return _lib.ConvDesc(X, Y, Z, cin, cout, k, s, dtype, ldx, ldy)
+
+
+def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=None, out=None):
+    L = _lib.lib()
+    odims = tuple(out_dim(n, k, s) for n in dims)
+    vo = odims[0] * odims[1] * odims[2]
+    ldo = (cout + 3) // 4 * 4
+    if out is None:
+        out = torch.empty(vo, ldo, device=x2d.device, dtype=torch.float32)
+    d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), ldo)
+    rc = L.coocc_conv3d_fwd(ctypes.byref(d), _p(x2d), _p(w2d), _p(out), out.stride(0), _p(bias),
+                            1 if relu else 0, _p(stats), _stream())
+    _lib.check(rc, "conv3d_fwd")
+    return out[:, :cout], odims
+
+
+class _Conv3dFn(torch.autograd.Function):
+    """y[Vout,Cout] = conv3d(x[V,Cin], w[Cout,Cin,k,k,k]) (+bias)(relu), padding k//2."""
+
+    @staticmethod
+    def forward(ctx, x2d, w5d, bias, dims, k, s, relu):
+        _require_cuda(x2d, w5d)
+        x2d = _as_rows(x2d)
+        w2d = weight_rows(w5d)
+        cout, cin = w5d.shape[0], w5d.shape[1]
+        y, odims = conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias, relu)
+        ctx.save_for_backward(x2d, w5d, y if relu else None)
+        ctx.meta = (dims, odims, k, s, relu, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w5d, y = ctx.saved_tensors
+        dims, odims, k, s, relu, has_bias = ctx.meta
+        L = _lib.lib()
+        cout, cin = w5d.shape[0], w5d.shape[1]
+        if relu:
+            dy = dy * (y > 0)
+        dy = _as_rows(dy)
+        w2d = weight_rows(w5d)
+        dx = dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw2d = torch.zeros(cout, k ** 3 * cin, device=dy.device, dtype=torch.float32)
+            d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), dy.stride(0))
+            _lib.check(L.coocc_conv3d_wgrad(ctypes.byref(d), _p(x2d), _p(dy), _p(dw2d), _stream()), "conv3d_wgrad")
+            # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
+            dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
+        if ctx.needs_input_grad[0]:
+            if s != 1:
+                # scatter dy onto the input lattice (even positions), then a stride-1 dgrad
+                X, Y, Z = dims
+                up = torch.zeros(X, Y, Z, dy.shape[1], device=dy.device, dtype=torch.float32)
+                up[::2, ::2, ::2][:odims[0], :odims[1], :odims[2]] = dy.reshape(*odims, dy.shape[1])
+                dy_in = up.reshape(X * Y * Z, dy.shape[1])
+            else:
+                dy_in = dy
+            ldo = (cin + 3) // 4 * 4
+            dxb = torch.empty(dims[0] * dims[1] * dims[2], ldo, device=dy.device, dtype=torch.float32)
+            d = _conv_desc(dims, cin, cout, k, 1, ldo, dy_in.stride(0))
+            _lib.check(L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(w2d), _p(dxb), dxb.stride(0), _stream()),
+                       "conv3d_dgrad")
+            dx = dxb[:, :cin]
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db, None, None, None, None
+
+
+def conv3d(x2d, w5d, dims, k, s=1, bias=None, relu=False):
+    return _Conv3dFn.apply(x2d, w5d, bias, dims, k, s, relu)
+
+
+def linear(x2d, weight, bias=None, relu=False):
+    """nn.Linear on the tensor cores: a 1x1x1 convolution over `rows` voxels."""
+    w5d = weight.reshape(weight.shape[0], weight.shape[1], 1, 1, 1)
+    return _Conv3dFn.apply(x2d, w5d, bias, (x2d.shape[0], 1, 1), 1, 1, relu)
+
+
+# ----------------------------------------------------------------------------------------
+# GSFusion
+# ----------------------------------------------------------------------------------------
+class ReferenceQuirk(RuntimeError):
+    pass
+
+
+def _gsf_direction(L, st, qlist, qrank, qcnt, nq, klist, krank, dims, K, dev, want_group=False):
+    """Index pipeline for one direction: returns dict(rep_idx, nrep, topk_idx, winner[K,nq])."""
+    X, Y, Z = dims
+    V = X * Y * Z
+    out = {}
+    if nq <= FPS_NUM:
+        if K != 1:
+            # bifuser_n.py:88-93 applies a 2-D mask to a 1-D row
+            raise IndexError("too many indices for tensor of dimension 1")
+        nn = torch.empty(max(nq, 1), device=dev, dtype=torch.int32)
+        _lib.check(L.coocc_gsf_direct_nn(_p(qlist), _p(qcnt), max(nq, 1), _p(krank), X, Y, Z, _p(nn), st), "direct_nn")
+        winner = torch.empty(1, V, device=dev, dtype=torch.int32)
+        _lib.check(L.coocc_gsf_direct_winner(_p(nn), _p(qcnt), _p(winner), V, st), "direct_winner")
+        rep_idx = torch.empty(max(nq, 1), device=dev, dtype=torch.int32)
+        _lib.check(L.coocc_iota(_p(rep_idx), max(nq, 1), st), "iota")
+        out.update(rep_idx=rep_idx, nrep=nq, topk_idx=nn.reshape(-1, 1), winner=winner, topk_d2=None, group=None)
+        return out
+    return None
+
+
+def gsf_index(img5d, pts5d, K, fix_k1_fps=False, want_parts=False):
+    """Runs pack + compact + (FPS, top-K, ball-assign | direct NN) for both directions.
+    Returns the [V,4C] concat buffer with img/pts slices filled and the index state."""
+    L = _lib.lib()
+    st = _stream()
+    _require_cuda(img5d, pts5d)
+    B, C, X, Y, Z = img5d.shape
+    assert B == 1 and pts5d.shape == img5d.shape
+    assert img5d.dtype == torch.float32 and pts5d.dtype == torch.float32
+    dev = img5d.device
+    V = X * Y * Z
+    dims = (X, Y, Z)
+    cat = torch.zeros(V, 4 * C, device=dev, dtype=torch.float32)
+    flags = torch.empty(2, V, device=dev, dtype=torch.uint8)
+    lists = torch.empty(2, V, device=dev, dtype=torch.int32)
+    ranks = torch.empty(2, V, device=dev, dtype=torch.int32)
+    counts = torch.zeros(2, device=dev, dtype=torch.int32)
+    ws = torch.empty(max(int(L.coocc_gsf_compact_workspace(V)), 4), device=dev, dtype=torch.uint8)
+    for i, t in enumerate((img5d, pts5d)):
+        sB, sC, sX, sY, sZ = t.stride()
+        _lib.check(L.coocc_gsf_pack(_p(t), sC, sX, sY, sZ, C, X, Y, Z, _pb(cat, i * C * 4), 4 * C,
+                                    _p(flags[i]), st), "gsf_pack")
+        _lib.check(L.coocc_gsf_compact(_p(flags[i]), V, _p(lists[i]), _p(ranks[i]), _pb(counts, 4 * i),
+                                       _p(ws), st), "gsf_compact")
+    n_img, n_pts = (int(v) for v in counts.tolist())          # the one host sync of the fuser
+    state = dict(dims=dims, C=C, K=K, n_img=n_img, n_pts=n_pts, lists=lists, ranks=ranks, counts=counts)
+
+    # direction A: queries = LiDAR voxels, keys = image voxels (bifuser_n.py:137)
+    # direction B: queries = image voxels, keys = LiDAR voxels (bifuser_n.py:151)
+    specs = [("A", 1, 0, n_pts), ("B", 0, 1, n_img)]
+    fps_jobs = []
+    for name, qi, ki, nq in specs:
+        if nq <= FPS_NUM:
+            state[name] = _gsf_direction(L, st, lists[qi], ranks[qi], counts[qi:qi + 1], nq, lists[ki], ranks[ki],
+                                         dims, K, dev)
+        else:
+            if K == 1 and not fix_k1_fps:
+                # bifuser_n.py:62-85: the K==1 FPS branch never returns (Q11) -> None ->
+                # the caller's gather broadcasts [1,4,C] against [N,C] and fails
+                raise ReferenceQuirk("reference BiFuser_N(knum=1) fails for N_query > 2048 (fps_NN_fast returns "
+                                     "None, bifuser_n.py:62-85); pass fix_k1_fps=True for the intended result")
+            fps_jobs.append((name, qi, ki, nq))
+    if fps_jobs:
+        reps = [torch.empty(FPS_NUM, device=dev, dtype=torch.int32) for _ in fps_jobs]
+        j0 = fps_jobs[0]
+        j1 = fps_jobs[1] if len(fps_jobs) > 1 else None
+        _lib.check(L.coocc_gsf_fps(_p(lists[j0[1]]), _pb(counts, 4 * j0[1]), _p(reps[0]),
+                                   _p(lists[j1[1]]) if j1 else None, _pb(counts, 4 * j1[1]) if j1 else None,
+                                   _p(reps[1]) if j1 else None, max(j[3] for j in fps_jobs), FPS_NUM, Y, Z, st),
+                   "gsf_fps")
+        for (name, qi, ki, nq), rep in zip(fps_jobs, reps):
+            topk_idx = torch.empty(FPS_NUM, K, device=dev, dtype=torch.int32)
+            topk_d2 = torch.empty(FPS_NUM, K, device=dev, dtype=torch.int32)
+            _lib.check(L.coocc_gsf_rep_topk(_p(rep), FPS_NUM, _p(lists[qi]), _p(ranks[ki]), X, Y, Z, K,
+                                            _p(topk_idx), _p(topk_d2), st), "gsf_rep_topk")
+            winner = torch.full((K, V), -1, device=dev, dtype=torch.int32)
+            group = torch.empty(FPS_NUM, BALL_SAMPLES, device=dev, dtype=torch.int32) if want_parts else None
+            _lib.check(L.coocc_gsf_ball_assign(_p(rep), FPS_NUM, _p(lists[qi]), _p(ranks[qi]), _p(topk_idx), X, Y, Z,
+                                               K, BALL_RADIUS, BALL_SAMPLES, V, _p(winner), _p(group), st),
+                       "gsf_ball_assign")
+            state[name] = dict(rep_idx=rep, nrep=FPS_NUM, topk_idx=topk_idx, topk_d2=topk_d2, winner=winner,
+                               group=group)
+    return cat, state
+
+
+def gsf_nn_indices(state, name):
+    """Reference-style result of fps_NN_fast for direction `name`: int64 [K, N_q] (-1 = unassigned)."""
+    d = state[name]
+    qi = 1 if name == "A" else 0
+    nq = state["n_pts"] if name == "A" else state["n_img"]
+    w = d["winner"][:, :nq].long()
+    tk = d["topk_idx"].long()                      # [nrep, K]
+    K = w.shape[0]
+    out = torch.full_like(w, -1)
+    for k in range(K):
+        ok = w[k] >= 0
+        out[k][ok] = tk[w[k][ok], k]
+    return out
+
+
+class _GSFusionFn(torch.autograd.Function):
+    """cat[V,4C] = [img | pts | fused_img | fused_pts]  (bifuser_n.py:129-172)."""
+
+    @staticmethod
+    def forward(ctx, img5d, pts5d, knn_w, knn_b, K, fix_k1_fps):
+        L = _lib.lib()
+        st = _stream()
+        cat, state = gsf_index(img5d, pts5d, K, fix_k1_fps)
+        X, Y, Z = state["dims"]
+        C = state["C"]
+        dev = cat.device
+        lists, counts = state["lists"], state["counts"]
+        err = torch.zeros(1, device=dev, dtype=torch.int32)
+        knn_w = knn_w.contiguous()
+        knn_b = knn_b.contiguous()
+        quirk_q2 = K > 1        # bifuser_n.py:158 indexes the image table with LiDAR-table positions
+        # (direction, query list idx, own column, key grid column, lookup list idx, dst column)
+        plan = [("A", 1, 1, 0, 0, 2), ("B", 0, 0, 1, 0 if quirk_q2 else 1, 3)]
+        saved = {}
+        for name, qi, own_col, key_col, look, dst_col in plan:
+            d = state[name]
+            nrep, nq = d["nrep"], (state["n_pts"] if name == "A" else state["n_img"])
+            rows = torch.empty(K, nrep + 1, C, device=dev, dtype=torch.float32)
+            _lib.check(L.coocc_gsf_gather_rows(_pb(cat, key_col * C * 4), 4 * C, _p(lists[look]),
+                                               _pb(counts, 4 * look), _p(d["topk_idx"]), nrep, K, C, _p(rows),
+                                               _p(err), st), "gsf_gather_rows")
+            P = torch.empty(K, nrep + 1, C, device=dev, dtype=torch.float32)
+            for k in range(K):
+                # P[k] = rows[k] @ W_k^T,  W_k = knn_w[:, k*C:(k+1)*C]
+                _lib.check(L.coocc_sgemm(nrep + 1, C, C, _p(rows[k]), C, 1, _pb(knn_w, k * C * 4), 1, K * C,
+                                         _p(P[k]), C, 0, st), "sgemm")
+            if nq > 0:
+                _lib.check(L.coocc_gsf_modulate_fwd(_p(P), _p(knn_b), _p(d["winner"]), d["winner"].stride(0),
+                                                    _p(lists[qi]), _pb(counts, 4 * qi), nq, nrep, K, C,
+                                                    _pb(cat, own_col * C * 4), 4 * C, _pb(cat, dst_col * C * 4), 4 * C,
+                                                    st), "gsf_modulate_fwd")
+            saved[name] = (rows, P)
+        if quirk_q2 and state["n_pts"] > state["n_img"] and int(err.item()) != 0:
+            raise IndexError("index out of range: LiDAR-table position used on the image table "
+                             "(reference bifuser_n.py:158, SURVEY Q2)")
+        ctx.state, ctx.saved, ctx.plan = state, saved, plan
+        ctx.save_for_backward(cat, knn_w, knn_b)
+        return cat
+
+    @staticmethod
+    def backward(ctx, dcat):
+        L = _lib.lib()
+        st = _stream()
+        cat, knn_w, knn_b = ctx.saved_tensors
+        state, saved, plan = ctx.state, ctx.saved, ctx.plan
+        K, C = state["K"], state["C"]
+        X, Y, Z = state["dims"]
+        dev = cat.device
+        lists, counts = state["lists"], state["counts"]
+        dcat = dcat.contiguous()
+        dgrid = [dcat[:, 0:C].contiguous(), dcat[:, C:2 * C].contiguous()]     # d_img, d_pts
+        dW = torch.zeros_like(knn_w)
+        db = torch.zeros_like(knn_b)
+        for name, qi, own_col, key_col, look, dst_col in plan:
+            d = state[name]
+            rows, P = saved[name]
+            nrep, nq = d["nrep"], (state["n_pts"] if name == "A" else state["n_img"])
+            if nq == 0:
+                continue
+            dP = torch.zeros_like(P)
+            _lib.check(L.coocc_gsf_modulate_bwd(_p(P), _p(knn_b), _p(d["winner"]), d["winner"].stride(0),
+                                                _p(lists[qi]), _pb(counts, 4 * qi), nq, nrep, K, C,
+                                                _pb(cat, own_col * C * 4), 4 * C, _pb(dcat, dst_col * C * 4), 4 * C,
+                                                _p(dgrid[own_col]), C, _p(dP), _p(db), st), "gsf_modulate_bwd")
+            dF = torch.empty_like(P)
+            for k in range(K):
+                # dW[:, kC:(k+1)C] += dP[k]^T @ rows[k]
+                _lib.check(L.coocc_sgemm(C, C, nrep + 1, _p(dP[k]), 1, C, _p(rows[k]), C, 1,
+                                         _pb(dW, k * C * 4), K * C, 1, st), "sgemm")
+                # dF[k] = dP[k] @ W_k
+                _lib.check(L.coocc_sgemm(nrep + 1, C, C, _p(dP[k]), C, 1, _pb(knn_w, k * C * 4), K * C, 1,
+                                         _p(dF[k]), C, 0, st), "sgemm")
+            _lib.check(L.coocc_gsf_scatter_rows(_p(dF), _p(lists[look]), _pb(counts, 4 * look), _p(d["topk_idx"]),
+                                                nrep, K, C, _p(dgrid[key_col]), C, st), "gsf_scatter_rows")
+        d_img = to_5d(dgrid[0], (X, Y, Z))
+        d_pts = to_5d(dgrid[1], (X, Y, Z))
+        return d_img, d_pts, dW, db, None, None
+
+
+def gsfusion_concat(img5d, pts5d, knn_w, knn_b, K, fix_k1_fps=False):
+    return _GSFusionFn.apply(img5d, pts5d, knn_w, knn_b, K, fix_k1_fps)
+
+
+# ----------------------------------------------------------------------------------------
+# Volume rendering
+# ----------------------------------------------------------------------------------------
+def render_box(dims):
+    L = _lib.lib()
+    bx, by, bz = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    L.coocc_render_box(dims[0], dims[1], dims[2], ctypes.byref(bx), ctypes.byref(by), ctypes.byref(bz))
+    return bx.value, by.value, bz.value
+
+
+class _BoxRowsFn(torch.autograd.Function):
+    """feature rows of the render box, [T,C], from the [V,C] grid."""
+
+    @staticmethod
+    def forward(ctx, x2d, dims):
+        L = _lib.lib()
+        x2d = _as_rows(x2d)
+        box = render_box(dims)
+        ctx.dims = dims
+        ctx.shape = x2d.shape
+        if box == tuple(dims):
+            ctx.full = True
+            return x2d.view_as(x2d)
+        ctx.full = False
+        T = box[0] * box[1] * box[2]
+        rows = torch.empty(T, x2d.shape[1], device=x2d.device, dtype=torch.float32)
+        _lib.check(L.coocc_render_box_gather(_p(x2d), x2d.stride(0), dims[0], dims[1], dims[2], x2d.shape[1],
+                                             _p(rows), _stream()), "render_box_gather")
+        return rows
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.full:
+            return g, None
+        L = _lib.lib()
+        g = g.contiguous()
+        dx = torch.zeros(ctx.shape, device=g.device, dtype=torch.float32)
+        _lib.check(L.coocc_render_box_scatter_add(_p(g), g.shape[1], ctx.dims[0], ctx.dims[1], ctx.dims[2],
+                                                  _p(dx), dx.stride(0), _stream()), "render_box_scatter_add")
+        return dx, None
+
+
+class _CompositeFn(torch.autograd.Function):
+    """tab[T,4] (rgb_raw, relu(sigma)) + geom -> (rgb_map [N,H,W,3], depth_map [N,H,W])."""
+
+    @staticmethod
+    def forward(ctx, tab, geom, dims):
+        L = _lib.lib()
+        N, D, H, W, _ = geom.shape
+        tab = tab.contiguous()
+        geom = geom.contiguous()
+        rgb_map = torch.empty(N, H, W, 3, device=tab.device, dtype=torch.float32)
+        depth_map = torch.empty(N, H, W, device=tab.device, dtype=torch.float32)
+        err = torch.zeros(1, device=tab.device, dtype=torch.int32)
+        _lib.check(L.coocc_render_composite_fwd(_p(geom), N, D, H, W, _p(tab), dims[0], dims[1], dims[2],
+                                                _p(rgb_map), _p(depth_map), _p(err), _stream()),
+                   "render_composite_fwd")
+        box = render_box(dims)
+        if box != (100, 100, 8) and int(err.item()) != 0:
+            raise IndexError("render sample inside the 100x100x8 box but outside the feature grid "
+                             "(reference coocc_ray.py:385 raises, SURVEY Q6)")
+        ctx.save_for_backward(tab, geom)
+        ctx.dims = dims
+        return rgb_map, depth_map
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth):
+        L = _lib.lib()
+        tab, geom = ctx.saved_tensors
+        N, D, H, W, _ = geom.shape
+        d_tab = torch.zeros_like(tab)
+        _lib.check(L.coocc_render_composite_bwd(_p(geom), N, D, H, W, _p(tab), ctx.dims[0], ctx.dims[1],
+                                                ctx.dims[2], _p(g_rgb.contiguous()), _p(g_depth.contiguous()),
+                                                _p(d_tab), _stream()), "render_composite_bwd")
+        return d_tab, None, None
+
+
+class _UpsampleLossFn(torch.autograd.Function):
+    """x16 bilinear + (loss_depth_render, loss_rgb)  (coocc_ray.py:412-433)."""
+
+    @staticmethod
+    def forward(ctx, rgb_map, depth_map, gt_img, gt_depth, D):
+        L = _lib.lib()
+        N, H, W, _ = rgb_map.shape
+        dev = rgb_map.device
+        rgbs = torch.empty(N, 16 * H, 16 * W, 3, device=dev, dtype=torch.float32)
+        depths = torch.empty(N, 16 * H, 16 * W, device=dev, dtype=torch.float32)
+        acc = torch.empty(3, device=dev, dtype=torch.float32)
+        losses = torch.empty(2, device=dev, dtype=torch.float32)
+        gt_img = gt_img.contiguous()
+        gt_depth = gt_depth.contiguous()
+        _lib.check(L.coocc_render_upsample_loss_fwd(_p(rgb_map.contiguous()), _p(depth_map.contiguous()), N, H, W, D,
+                                                    _p(gt_img), _p(gt_depth), _p(rgbs), _p(depths), _p(acc),
+                                                    _p(losses), _stream()), "render_upsample_loss_fwd")
+        ctx.save_for_backward(rgbs, depths, gt_img, gt_depth, acc)
+        ctx.meta = (N, H, W, D)
+        ctx.mark_non_differentiable(rgbs, depths)
+        return losses, rgbs, depths
+
+    @staticmethod
+    def backward(ctx, g_losses, _g1, _g2):
+        L = _lib.lib()
+        rgbs, depths, gt_img, gt_depth, acc = ctx.saved_tensors
+        N, H, W, D = ctx.meta
+        g_rgb = torch.empty(N, H, W, 3, device=rgbs.device, dtype=torch.float32)
+        g_depth = torch.empty(N, H, W, device=rgbs.device, dtype=torch.float32)
+        _lib.check(L.coocc_render_upsample_loss_bwd(_p(rgbs), _p(depths), N, H, W, D, _p(gt_img), _p(gt_depth),
+                                                    _p(acc), _p(g_losses.contiguous()), _p(g_rgb), _p(g_depth),
+                                                    _stream()), "render_upsample_loss_bwd")
+        return g_rgb, g_depth, None, None, None
+
+
+def box_rows(x2d, dims):
+    return _BoxRowsFn.apply(x2d, tuple(dims))
+
+
+def composite(tab, geom, dims):
+    return _CompositeFn.apply(tab, geom, tuple(dims))
+
+
+def upsample_losses(rgb_map, depth_map, gt_img, gt_depth, D):
+    return _UpsampleLossFn.apply(rgb_map, depth_map, gt_img, gt_depth, D)

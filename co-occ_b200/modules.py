@@ -1,0 +1,334 @@
+"""The reference's plugin modules of the hot path, re-implemented on the C ABI.
+
+Same registry names, constructor arguments, forward signatures and state_dict keys as
+  BiFuser_N       P/coocc/fuser/bifuser_n.py:13-174
+  CustomResNet3D  P/coocc/backbones/resnet3d.py:105-205
+  FPN3D           P/coocc/necks/fpn3d.py:13-108
+  OccHead         P/coocc/dense_heads/occ_head.py:15-171 (coarse path; fine stage/losses are §8f "next")
+  MLP             P/utils/nerf_mlp.py:14-105 (the two render heads)
+torch.nn layers are used only as *parameter containers* (identical names, shapes and default
+initialisers); their forward() is never called -- every convolution / linear runs in
+csrc/conv_tc.cu, the fusion in csrc/gsf_*.cu, the renderer in csrc/render.cu.
+Tensors between modules are the reference's [1,C,X,Y,Z], physically channels_last_3d.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as CF
+from .registry import BACKBONES, FUSION_LAYERS, HEADS, NECKS
+
+
+def _norm_layer(norm_cfg, c):
+    cfg = dict(norm_cfg or dict(type="BN3d"))
+    typ = cfg.pop("type")
+    cfg.pop("requires_grad", None)
+    if typ not in ("BN3d", "SyncBN", "BN"):
+        raise NotImplementedError("coocc_b200 hot path implements BatchNorm (BN3d/SyncBN) only, got %s" % typ)
+    return nn.BatchNorm3d(c, **cfg)
+
+
+def _cl3d_(conv):
+    """Keep conv weights physically [Cout,kx,ky,kz,Cin] so the kernels read them in place."""
+    w = conv.weight
+    if w.dim() == 5 and not w.permute(0, 2, 3, 4, 1).is_contiguous():
+        w.data = w.data.contiguous(memory_format=torch.channels_last_3d)
+    return w
+
+
+def batch_norm2d(x2d, bn):
+    """BatchNorm3d over a [V,C] view (N*D*H*W = V rows), same running-stat updates."""
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    mom = 0.0 if bn.momentum is None else bn.momentum
+    use_batch = bn.training or bn.running_mean is None
+    return F.batch_norm(x2d, bn.running_mean if not bn.training or bn.track_running_stats else None,
+                        bn.running_var if not bn.training or bn.track_running_stats else None,
+                        bn.weight, bn.bias, use_batch, mom, bn.eps)
+
+
+def conv_bn_act(x2d, dims, conv, bn=None, relu=True):
+    k = conv.kernel_size[0]
+    s = conv.stride[0]
+    y = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, bias=conv.bias)
+    odims = tuple(CF.out_dim(n, k, s) for n in dims)
+    if bn is not None:
+        y = batch_norm2d(y, bn)
+    if relu:
+        y = F.relu(y)
+    return y, odims
+
+
+def resize_trilinear(x2d, dims, size):
+    """F.interpolate(..., mode='trilinear', align_corners=False) on a [V,C] view."""
+    if tuple(size) == tuple(dims):
+        return x2d
+    x5 = CF.to_5d(x2d, dims)
+    y5 = F.interpolate(x5, size=list(size), mode="trilinear", align_corners=False)
+    return CF.to_cl2d(y5)[0]
+
+
+# ----------------------------------------------------------------------------------------
+@FUSION_LAYERS.register_module(force=True)
+class BiFuser_N(nn.Module):
+    def __init__(self, in_channels, out_channels, knum=1, norm_cfg=None, fix_k1_fps=False):
+        super().__init__()
+        self.in_channels, self.out_channels, self.knum = in_channels, out_channels, knum
+        self.fix_k1_fps = fix_k1_fps
+        # container layers mirror bifuser_n.py:23-36 (plain BatchNorm3d defaults)
+        self.con_enc = nn.Sequential(
+            nn.Conv3d(in_channels * 4, out_channels * 2, 3, padding=1, bias=False),
+            nn.BatchNorm3d(out_channels * 2), nn.ReLU(True),
+            nn.Conv3d(in_channels * 2, out_channels, 3, padding=1, bias=False),
+            nn.BatchNorm3d(out_channels), nn.ReLU(True))
+        self.knn_enc = nn.Sequential(nn.Linear(in_channels * knum, out_channels), nn.ReLU())
+
+    def forward(self, img_voxel_feats, pts_voxel_feats):
+        dims = tuple(img_voxel_feats.shape[2:])
+        cat = CF.gsfusion_concat(img_voxel_feats, pts_voxel_feats, self.knn_enc[0].weight,
+                                 self.knn_enc[0].bias, self.knum, self.fix_k1_fps)
+        y, _ = conv_bn_act(cat, dims, self.con_enc[0], self.con_enc[1])
+        y, _ = conv_bn_act(y, dims, self.con_enc[3], self.con_enc[4])
+        return CF.to_5d(y, dims)
+
+
+# ----------------------------------------------------------------------------------------
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, in_planes, planes, stride=1, downsample=None, norm_cfg=None):
+        super().__init__()
+        self.conv1 = nn.Conv3d(in_planes, planes, 3, stride, 1, bias=False)
+        self.bn1 = _norm_layer(norm_cfg, planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv3d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = _norm_layer(norm_cfg, planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward2d(self, x, dims):
+        out, odims = conv_bn_act(x, dims, self.conv1, self.bn1)
+        out, _ = conv_bn_act(out, odims, self.conv2, self.bn2, relu=False)
+        if self.downsample is not None:
+            idn, _ = conv_bn_act(x, dims, self.downsample[0], self.downsample[1], relu=False)
+        else:
+            idn = x
+        return F.relu(out + idn), odims
+
+
+@BACKBONES.register_module(force=True)
+class CustomResNet3D(nn.Module):
+    def __init__(self, depth, block_inplanes=[64, 128, 256, 512], block_strides=[1, 2, 2, 2],
+                 out_indices=(0, 1, 2, 3), n_input_channels=3, shortcut_type='B',
+                 norm_cfg=dict(type='BN3d', requires_grad=True), widen_factor=1.0):
+        super().__init__()
+        metas = {10: [1, 1, 1, 1], 18: [2, 2, 2, 2], 34: [3, 4, 6, 3]}
+        if depth not in metas:
+            raise NotImplementedError("hot path covers the BasicBlock depths (10/18/34); configs use 18")
+        if shortcut_type != 'B':
+            raise NotImplementedError("shortcut_type 'B' (conv1x1x1 + norm) only")
+        planes = [int(x * widen_factor) for x in block_inplanes]
+        self.in_planes = planes[0]
+        self.out_indices = out_indices
+        self.input_proj = nn.Sequential(nn.Conv3d(n_input_channels, self.in_planes, 1, 1, bias=False),
+                                        _norm_layer(norm_cfg, self.in_planes), nn.ReLU(inplace=True))
+        self.layers = nn.ModuleList()
+        for i in range(len(planes)):
+            self.layers.append(self._make_layer(planes[i], metas[depth][i], block_strides[i], norm_cfg))
+        for m in self.modules():            # resnet3d.py:150-158
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+            elif isinstance(m, nn.BatchNorm3d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def _make_layer(self, planes, blocks, stride, norm_cfg):
+        downsample = None
+        if stride != 1 or self.in_planes != planes:
+            downsample = nn.Sequential(nn.Conv3d(self.in_planes, planes, 1, stride, bias=False),
+                                       _norm_layer(norm_cfg, planes))
+        layers = [BasicBlock(self.in_planes, planes, stride, downsample, norm_cfg)]
+        self.in_planes = planes
+        for _ in range(1, blocks):
+            layers.append(BasicBlock(planes, planes, norm_cfg=norm_cfg))
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x2d, dims = CF.to_cl2d(x)
+        x2d, dims = conv_bn_act(x2d, dims, self.input_proj[0], self.input_proj[1])
+        res = []
+        for index, layer in enumerate(self.layers):
+            for blk in layer:
+                x2d, dims = blk.forward2d(x2d, dims)
+            if index in self.out_indices:
+                res.append(CF.to_5d(x2d, dims))
+        return res
+
+
+# ----------------------------------------------------------------------------------------
+class _ConvModule(nn.Module):
+    """Parameter container with mmcv ConvModule's child names (`conv`, `bn`)."""
+
+    def __init__(self, cin, cout, k, norm_cfg):
+        super().__init__()
+        self.conv = nn.Conv3d(cin, cout, k, 1, k // 2, bias=False)
+        self.bn = _norm_layer(norm_cfg, cout)
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode="fan_out", nonlinearity="relu")
+
+
+@NECKS.register_module(force=True)
+class FPN3D(nn.Module):
+    def __init__(self, in_channels=[80, 160, 320, 640], out_channels=256,
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True), conv_cfg=dict(type='Conv3d'),
+                 act_cfg=dict(type='ReLU'), with_cp=False, upsample_cfg=dict(mode='trilinear'), init_cfg=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.with_cp = with_cp      # activation checkpointing is a memory policy, not arithmetic
+        self.upsample_cfg = upsample_cfg
+        self.num_out = len(in_channels)
+        self.lateral_convs = nn.ModuleList()
+        self.fpn_convs = nn.ModuleList()
+        for i in range(self.num_out):
+            self.lateral_convs.append(nn.Sequential(_ConvModule(in_channels[i], out_channels, 1, norm_cfg)))
+            self.fpn_convs.append(nn.Sequential(_ConvModule(out_channels, out_channels, 3, norm_cfg)))
+
+    def forward(self, inputs):
+        assert len(inputs) == len(self.in_channels)
+        lat, dims = [], []
+        for i, x in enumerate(inputs):
+            x2d, d = CF.to_cl2d(x)
+            m = self.lateral_convs[i][0]
+            y, _ = conv_bn_act(x2d, d, m.conv, m.bn)
+            lat.append(y)
+            dims.append(d)
+        for i in range(self.num_out - 1, 0, -1):
+            lat[i - 1] = lat[i - 1] + resize_trilinear(lat[i], dims[i], dims[i - 1])
+        outs = []
+        for i in range(self.num_out):
+            m = self.fpn_convs[i][0]
+            y, _ = conv_bn_act(lat[i], dims[i], m.conv, m.bn)
+            outs.append(CF.to_5d(y, dims[i]))
+        return outs
+
+
+# ----------------------------------------------------------------------------------------
+@HEADS.register_module(force=True)
+class OccHead(nn.Module):
+    def __init__(self, in_channels, out_channel, num_level=1, num_img_level=1, soft_weights=False,
+                 loss_weight_cfg=None, conv_cfg=dict(type='Conv3d', bias=False),
+                 norm_cfg=dict(type='GN', num_groups=32, requires_grad=True), fine_topk=20000,
+                 point_cloud_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], final_occ_size=[256, 256, 20],
+                 empty_idx=0, visible_loss=False, balance_cls_weight=True, cascade_ratio=1,
+                 sample_from_voxel=False, sample_from_img=False, train_cfg=None, test_cfg=None,
+                 padding_mode='border', data_type='nus'):
+        super().__init__()
+        if not isinstance(in_channels, list):
+            in_channels = [in_channels]
+        self.in_channels, self.out_channel, self.num_level = in_channels, out_channel, num_level
+        self.soft_weights = soft_weights
+        self.cascade_ratio = cascade_ratio
+        self.sample_from_voxel, self.sample_from_img = sample_from_voxel, sample_from_img
+        self.empty_idx = empty_idx
+        self.final_occ_size = final_occ_size
+        self.fine_topk = fine_topk
+        bias = dict(conv_cfg).get("bias", True)
+        self.occ_convs = nn.ModuleList()
+        for i in range(num_level):
+            mid = in_channels[i] // 2
+            self.occ_convs.append(nn.Sequential(nn.Conv3d(in_channels[i], mid, 3, 1, 1, bias=bias),
+                                                _norm_layer(norm_cfg, mid), nn.ReLU(inplace=True)))
+        self.occ_pred_conv = nn.Sequential(nn.Conv3d(mid, mid // 2, 1, bias=bias), _norm_layer(norm_cfg, mid // 2),
+                                           nn.ReLU(inplace=True), nn.Conv3d(mid // 2, out_channel, 1, bias=bias))
+        self.num_point_sampling_feat = num_level
+        if soft_weights:
+            self.voxel_soft_weights = nn.Sequential(
+                nn.Conv3d(mid, mid // 2, 1, bias=bias), _norm_layer(norm_cfg, mid // 2), nn.ReLU(inplace=True),
+                nn.Conv3d(mid // 2, num_level, 1, bias=bias))
+
+    def forward_coarse_voxel(self, voxel_feats):
+        occs, dims = [], []
+        for f, m in zip(voxel_feats, self.occ_convs):
+            x2d, d = CF.to_cl2d(f)
+            y, _ = conv_bn_act(x2d, d, m[0], m[1])
+            occs.append(y)
+            dims.append(d)
+        d0 = dims[0]
+        if self.soft_weights:
+            w, _ = conv_bn_act(occs[0], d0, self.voxel_soft_weights[0], self.voxel_soft_weights[1])
+            w, _ = conv_bn_act(w, d0, self.voxel_soft_weights[3], None, relu=False)
+            w = torch.softmax(w, dim=1)
+        else:
+            w = torch.full((1, self.num_level), 1.0 / self.num_level, device=occs[0].device)
+        feats = 0
+        for i, f in enumerate(occs):
+            feats = feats + resize_trilinear(f, dims[i], d0) * w[:, i:i + 1]
+        y, _ = conv_bn_act(feats, d0, self.occ_pred_conv[0], self.occ_pred_conv[1])
+        occ, _ = conv_bn_act(y, d0, self.occ_pred_conv[3], None, relu=False)
+        return {"out_voxel_feats": [CF.to_5d(feats, d0)], "occ": [CF.to_5d(occ, d0)]}
+
+    def forward(self, voxel_feats, img_feats=None, img_metas=None, pts_feats=None, target_points=None,
+                transform=None, **kwargs):
+        assert type(voxel_feats) is list and len(voxel_feats) == self.num_level
+        out = self.forward_coarse_voxel(voxel_feats)
+        if self.cascade_ratio != 1 and (self.sample_from_img or self.sample_from_voxel):
+            raise NotImplementedError("OccHead fine/cascade stage is outside the hot path (SURVEY §8f rank 1)")
+        return {"output_voxels": out["occ"], "output_voxels_fine": None, "output_coords_fine": None,
+                "output_points": None}
+
+
+# ----------------------------------------------------------------------------------------
+class _Scales(nn.Module):
+    """`posi_encoder.scales` buffer the reference MLP registers but never uses."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("scales", torch.tensor([2 ** i for i in range(0, 10)]))
+
+
+class MLP(nn.Module):
+    """nerf_mlp.MLP restricted to what coocc_ray.py:112-113 builds (skip_layer=None, ReLU hidden
+    activations, identity output, xavier-uniform weights, zero biases)."""
+
+    def __init__(self, input_dim, output_dim=None, net_depth=8, net_width=256, skip_layer=None, **kw):
+        super().__init__()
+        if skip_layer is not None:
+            raise NotImplementedError("render heads are built with skip_layer=None")
+        self.input_dim, self.output_dim, self.net_depth, self.net_width = input_dim, output_dim, net_depth, net_width
+        self.hidden_layers = nn.ModuleList()
+        self.posi_encoder = _Scales()
+        cin = input_dim
+        for _ in range(net_depth):
+            self.hidden_layers.append(nn.Linear(cin, net_width))
+            cin = net_width
+        self.output_layer = nn.Linear(cin, output_dim)
+        for m in list(self.hidden_layers) + [self.output_layer]:
+            nn.init.xavier_uniform_(m.weight)
+            nn.init.zeros_(m.bias)
+
+    def forward_rows(self, x2d, relu_out=False):
+        for lin in self.hidden_layers:
+            x2d = CF.linear(x2d, lin.weight, lin.bias, relu=True)
+        return CF.linear(x2d, self.output_layer.weight, self.output_layer.bias, relu=relu_out)
+
+    def forward(self, x):
+        shp = x.shape
+        return self.forward_rows(x.reshape(-1, shp[-1])).reshape(*shp[:-1], self.output_dim)
+
+
+def render_fn(voxel_feats, gemo, sigma_head, rgb_head, gt_depth, gt_img):
+    """The inline render block of COOCC_Ray.forward_train (coocc_ray.py:358-433).
+
+    voxel_feats [1,C,X,Y,Z] (fuser output), gemo [1,N,D,H,W,3], gt_depth = img_inputs[7] [1,N,16H,16W],
+    gt_img = img_inputs[0] [1,N,3,16H,16W].  Returns (rgbs [N,16H,16W,3], depths [N,16H,16W], losses dict).
+    The heads run once per voxel of the render box, not once per sample (identical values).
+    """
+    B, N, D, H, W, _ = gemo.shape
+    assert B == 1
+    x2d, dims = CF.to_cl2d(voxel_feats)
+    rows = CF.box_rows(x2d, dims)
+    rgb_raw = rgb_head.forward_rows(rows)                       # [T,3]
+    sigma = sigma_head.forward_rows(rows, relu_out=True)        # [T,1] = relu(sigma_head(f))
+    tab = torch.cat([rgb_raw, sigma], dim=1)                    # [T,4]
+    rgb_map, depth_map = CF.composite(tab, gemo[0], dims)
+    losses2, rgbs, depths = CF.upsample_losses(rgb_map, depth_map, gt_img[0], gt_depth[0], D)
+    return rgbs, depths, {"loss_depth_render": losses2[0], "loss_rgb": losses2[1]}

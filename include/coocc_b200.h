@@ -67,6 +67,88 @@ int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, 
 /* dw[co][tap][ci] += ... (fp32; caller zero-fills dw; split-K partial sums are added atomically). */
 int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * GSFusion index pipeline (csrc/gsf_index.cu), integer-exact.
+ * Replaces P/coocc/fuser/bifuser_n.py:38-125 (fps_NN_fast), :129-135 (nonzero + channels-last
+ * gather) and the CUDA ops furthest_point_sample / ball_query it calls
+ * (mmdet3d/ops/furthest_point_sample/src/furthest_point_sample.cpp:35-46,
+ *  mmdet3d/ops/ball_query/src/ball_query.cpp:32-45).
+ * "list" = occupied voxel ids in ascending order (= torch.nonzero row order), "rank" = inverse
+ * table voxel -> position in list or -1; counts live on the device.
+ * ------------------------------------------------------------------------------------------ */
+/* strided [C,X,Y,Z] fp32 (element strides sC,sX,sY,sZ) -> dst[v*ldo + c]; flags[v] = (sum_c != 0) */
+int coocc_gsf_pack(const float* src, long long sC, long long sX, long long sY, long long sZ, int C, int X,
+                   int Y, int Z, float* dst, long long ldo, unsigned char* flags, void* stream);
+long long coocc_gsf_compact_workspace(int V);
+int coocc_gsf_compact(const unsigned char* flags, int V, int* list, int* rank, int* count, void* workspace,
+                      void* stream);
+/* furthest point sampling of `m` points, start index 0, the reference kernel's tie order
+ * (max distance, then bit-reversed (k mod 1024), then k).  One or two problems per launch
+ * (list1 may be NULL); n_max bounds both counts.  out[j] = position in list. */
+int coocc_gsf_fps(const int* list0, const int* count0, int* out0, const int* list1, const int* count1,
+                  int* out1, int n_max, int m, int Y, int Z, void* stream);
+/* K nearest keys (d2 <= 176 <=> dist < 13.3) of each representative, order (d2 asc, key asc);
+ * out_idx = position in the key list or -1, out_d2 = squared distance or -1. */
+int coocc_gsf_rep_topk(const int* rep_idx, int nrep, const int* qlist, const int* key_rank, int X, int Y,
+                       int Z, int K, int* out_idx, int* out_d2, void* stream);
+/* ball query (first `nsample` queries in index order with d2 < radius^2) + assignment:
+ * winner[k*nq_stride + q] = max representative position r with topk_idx[r][k] valid and q in
+ * ball(r) (caller initialises winner to -1).  group_out (optional, [nrep][nsample]) receives
+ * the ball_query result itself. */
+int coocc_gsf_ball_assign(const int* rep_idx, int nrep, const int* qlist, const int* q_rank,
+                          const int* topk_idx, int X, int Y, int Z, int K, int radius, int nsample,
+                          int nq_stride, int* winner, int* group_out, void* stream);
+/* K == 1, N_q <= 2048 branch (bifuser_n.py:55-60): nearest key of every query or -1 */
+int coocc_gsf_direct_nn(const int* qlist, const int* qcount, int nq_max, const int* key_rank, int X, int Y,
+                        int Z, int* nn, void* stream);
+int coocc_gsf_direct_winner(const int* nn, const int* qcount, int* winner, int nq_max, void* stream);
+int coocc_iota(int* p, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GSFusion feature path (csrc/gsf_feat.cu): bifuser_n.py:138-172 forward and its backward.
+ * rows / P / dP / dF are [K][nrep+1][C]; row nrep is the "index -1 -> last key" row (Q3).
+ * ------------------------------------------------------------------------------------------ */
+int coocc_gsf_gather_rows(const float* grid, long long ld, const int* lookup, const int* lookup_count,
+                          const int* topk_idx, int nrep, int K, int C, float* rows, int* err, void* stream);
+/* C[i][j] (+)= sum_k A[i*sAi + k*sAk] * B[k*sBk + j*sBj]   (small fp32 SIMT GEMM) */
+int coocc_sgemm(int M, int N, int Kd, const float* A, long long sAi, long long sAk, const float* B,
+                long long sBk, long long sBj, float* C, long long ldc, int accumulate, void* stream);
+int coocc_gsf_modulate_fwd(const float* P, const float* bias, const int* winner, int nq_stride,
+                           const int* qlist, const int* qcount, int nq_max, int nrep, int K, int C,
+                           const float* own, long long ld_own, float* dst, long long ld_dst, void* stream);
+int coocc_gsf_modulate_bwd(const float* P, const float* bias, const int* winner, int nq_stride,
+                           const int* qlist, const int* qcount, int nq_max, int nrep, int K, int C,
+                           const float* own, long long ld_own, const float* g, long long ld_g, float* d_own,
+                           long long ld_down, float* dP, float* dbias, void* stream);
+int coocc_gsf_scatter_rows(const float* dF, const int* lookup, const int* lookup_count, const int* topk_idx,
+                           int nrep, int K, int C, float* d_grid, long long ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Volume-render regulariser (csrc/render.cu): coocc_ray.py:358-433.
+ * tab[T][4] = (rgb_raw[3], relu(sigma)) per voxel of the render box (the reference's hard-coded
+ * 100x100x8 grid clipped to the feature grid), t = (x*by + y)*bz + z.
+ * ------------------------------------------------------------------------------------------ */
+int coocc_render_box(int X, int Y, int Z, int* bx, int* by, int* bz);
+int coocc_render_box_gather(const float* grid, long long ld, int X, int Y, int Z, int C, float* rows,
+                            void* stream);
+int coocc_render_box_scatter_add(const float* rows, int C, int X, int Y, int Z, float* grid, long long ld,
+                                 void* stream);
+/* geom [ncam][D][H][W][3] fp32 ego metres -> rgb_map [ncam][H][W][3], depth_map [ncam][H][W];
+ * err[0] = 1 if an in-box sample falls outside the feature grid (the reference raises). */
+int coocc_render_composite_fwd(const float* geom, int ncam, int D, int H, int W, const float* tab, int X,
+                               int Y, int Z, float* rgb_map, float* depth_map, int* err, void* stream);
+int coocc_render_composite_bwd(const float* geom, int ncam, int D, int H, int W, const float* tab, int X,
+                               int Y, int Z, const float* g_rgb_map, const float* g_depth_map, float* d_tab,
+                               void* stream);
+/* x16 bilinear upsample + losses; acc3 = scratch float[3]; losses2 = (loss_depth_render, loss_rgb) */
+int coocc_render_upsample_loss_fwd(const float* rgb_map, const float* depth_map, int ncam, int H, int W,
+                                   int D, const float* gt_img, const float* gt_depth, float* rgbs,
+                                   float* depths, float* acc3, float* losses2, void* stream);
+int coocc_render_upsample_loss_bwd(const float* rgbs, const float* depths, int ncam, int H, int W, int D,
+                                   const float* gt_img, const float* gt_depth, const float* acc3,
+                                   const float* g_losses2, float* g_rgb_map, float* g_depth_map,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif
