@@ -63,6 +63,7 @@ struct TcParams {
   long long ldc;
   const float* bias;
   int relu;
+  int accum;          // epilogue adds the previous contents of out (multi-pass precision split)
   float* stats;        // [2][N] sum / sum of squares over rows, or nullptr
   // wgrad
   int nvb;             // number of voxel (K) blocks
@@ -290,6 +291,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         }
         const int col0 = nt * p.BN + c0;
         if (!wgrad) {
+          float* o = p.out + (long long)row * p.ldc + col0;
+          const bool vec = (col0 + 32 <= p.N) && ((p.ldc & 3) == 0);
+          if (p.accum && row_ok) {
+            // out += acc : second / third pass of the 3xTF32 split
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 f = *reinterpret_cast<const float4*>(o + i);
+                v[i] = __float_as_uint(__uint_as_float(v[i]) + f.x);
+                v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + f.y);
+                v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + f.z);
+                v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + f.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) v[i] = __float_as_uint(__uint_as_float(v[i]) + o[i]);
+            }
+          }
           if (p.stats != nullptr) {
             // per-column sum / sum of squares over the rows of this warp (raw accumulators):
             // butterfly transpose-reduce, lane l ends with the totals of column c0 + l
@@ -313,7 +333,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 ss[i] = (up ? ss[i + off] : ss[i]) + recv_q;
               }
             }
-            // after the butterfly lane l holds column index bitwise == l (bit `off` set <-> upper half)
             const int col = col0 + lane;
             if (col < p.N) {
               atomicAdd(&p.stats[col], s[0]);
@@ -321,8 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             }
           }
           if (row_ok) {
-            float* o = p.out + (long long)row * p.ldc + col0;
-            if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+            if (vec) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 float4 f;
@@ -511,7 +529,7 @@ static int check_desc(const coocc_conv_desc* d) {
   if (!d) return COOCC_ERR_ARG;
   if (d->ksize != 1 && d->ksize != 3) return COOCC_ERR_ARG;
   if (d->stride != 1 && d->stride != 2) return COOCC_ERR_ARG;
-  if (d->dtype != COOCC_DTYPE_TF32 && d->dtype != COOCC_DTYPE_BF16) return COOCC_ERR_ARG;
+  if (d->dtype != COOCC_DTYPE_TF32 && d->dtype != COOCC_DTYPE_BF16) return COOCC_ERR_ARG;   // X3 is expanded by the callers
   if (d->X < 1 || d->Y < 1 || d->Z < 1 || d->Cin < 1 || d->Cout < 1) return COOCC_ERR_ARG;
   const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
   if (((long long)d->ldx * es) % 16 || ((long long)d->ldy * es) % 16) return COOCC_ERR_ALIGN;
@@ -520,9 +538,8 @@ static int check_desc(const coocc_conv_desc* d) {
   return 0;
 }
 
-extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, float* y,
-                                long long ldo, const float* bias, int relu, float* stats,
-                                void* stream) {
+static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, float* y, long long ldo,
+                    const float* bias, int relu, float* stats, int accum, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   if ((rc = init_driver_api())) return rc;
@@ -542,7 +559,7 @@ extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const v
   p.oX = oX; p.oY = oY; p.oZ = oZ;
   p.cstride = d->stride;
   p.lo = -(d->ksize / 2);
-  p.out = y; p.ldc = ldo; p.bias = bias; p.relu = relu; p.stats = stats;
+  p.out = y; p.ldc = ldo; p.bias = bias; p.relu = relu; p.stats = stats; p.accum = accum;
   p.ksplit = 1;
   const int bke = 128 / es;
   const bool plain = (d->ksize == 1 && d->stride == 1);
@@ -564,8 +581,8 @@ extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const v
 
 // dX[v, ci] = sum_{tap,co} dY[v - tap + pad, co] W[co, tap, ci]; stride-1 convolutions only
 // (for stride 2 the caller scatters dY onto the input lattice first, see conv3d_dgrad docs).
-extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, float* dx,
-                                  long long ldo, void* stream) {
+static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, float* dx, long long ldo,
+                      int accum, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   if (d->stride != 1) return COOCC_ERR_ARG;
@@ -591,7 +608,7 @@ extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, cons
   p.oX = d->X; p.oY = d->Y; p.oZ = d->Z;
   p.cstride = 1;
   p.lo = -(d->ksize / 2);
-  p.out = dx; p.ldc = ldo; p.bias = nullptr; p.relu = 0; p.stats = nullptr;
+  p.out = dx; p.ldc = ldo; p.bias = nullptr; p.relu = 0; p.stats = nullptr; p.accum = accum;
   p.ksplit = 1;
   const bool plain = (d->ksize == 1);
   p.a_im2col = plain ? 0 : 1;
@@ -610,8 +627,7 @@ extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, cons
 }
 
 // dW[co, tap, ci] += sum_v dY[v, co] X[v*s + tap - pad, ci]   (dw must be zero-filled by the caller)
-extern "C" int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const void* dy, float* dw,
-                                  void* stream) {
+static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   if ((rc = init_driver_api())) return rc;
@@ -659,4 +675,120 @@ extern "C" int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const
   if (rc) return rc;
   const int ntiles = base_tiles * ks;
   return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// COOCC_DTYPE_TF32X3: fp32-accurate mode.  Every fp32 operand is split as x = hi + lo with
+// hi = round-to-nearest tf32(x) and lo = x - hi (exact in fp32); the product is evaluated as
+// hi*hi + hi*lo + lo*hi in three tensor-core passes accumulating in fp32 (the dropped lo*lo term
+// is ~2^-22 relative).  Used for the 1e-3 parity runs; the fast modes are single-pass.
+// ------------------------------------------------------------------------------------------
+namespace coocc {
+__global__ void split_tf32_kernel(const float* __restrict__ x, long long ldx, long long rows, int cols,
+                                  float* __restrict__ hi, float* __restrict__ lo, long long ldo) {
+  const long long n = rows * ldo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ldo;
+    const int c = (int)(i % ldo);
+    float v = 0.f;
+    if (c < cols) v = x[r * ldx + c];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hf = __uint_as_float(h);
+    hi[i] = hf;
+    lo[i] = v - hf;
+  }
+}
+
+struct SplitBuf {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  long long ld = 0;
+};
+
+static int split_rows(const void* x, long long ldx, long long rows, int cols, SplitBuf* out, cudaStream_t st) {
+  const long long ld = ((long long)cols + 3) / 4 * 4;
+  const size_t bytes = (size_t)rows * ld * sizeof(float);
+  float* base = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&base), 2 * bytes, st) != cudaSuccess) return COOCC_ERR_CUDA;
+  out->hi = base;
+  out->lo = base + rows * ld;
+  out->ld = ld;
+  const long long n = rows * ld;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split_tf32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), ldx, rows, cols, out->hi, out->lo, ld);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+static void split_free(SplitBuf* b, cudaStream_t st) {
+  if (b->hi) cudaFreeAsync(b->hi, st);
+  b->hi = b->lo = nullptr;
+}
+}  // namespace coocc
+
+extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, float* y,
+                                long long ldo, const float* bias, int relu, float* stats,
+                                void* stream) {
+  if (!d) return COOCC_ERR_ARG;
+  if (d->dtype != COOCC_DTYPE_TF32X3) return fwd_impl(d, x, w, y, ldo, bias, relu, stats, 0, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = d->ksize == 3 ? 27 : 1;
+  SplitBuf xs, ws;
+  int rc = split_rows(x, d->ldx, (long long)d->X * d->Y * d->Z, d->Cin, &xs, st);
+  if (!rc) rc = split_rows(w, (long long)taps * d->Cin, d->Cout, taps * d->Cin, &ws, st);
+  coocc_conv_desc t = *d;
+  t.dtype = COOCC_DTYPE_TF32;
+  t.ldx = xs.ld;
+  if (!rc) rc = fwd_impl(&t, xs.hi, ws.hi, y, ldo, nullptr, 0, nullptr, 0, stream);
+  if (!rc) rc = fwd_impl(&t, xs.hi, ws.lo, y, ldo, nullptr, 0, nullptr, 1, stream);
+  if (!rc) rc = fwd_impl(&t, xs.lo, ws.hi, y, ldo, bias, relu, stats, 1, stream);
+  split_free(&xs, st);
+  split_free(&ws, st);
+  return rc;
+}
+
+extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, float* dx,
+                                  long long ldo, void* stream) {
+  if (!d) return COOCC_ERR_ARG;
+  if (d->dtype != COOCC_DTYPE_TF32X3) return dgrad_impl(d, dy, w, dx, ldo, 0, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = d->ksize == 3 ? 27 : 1;
+  SplitBuf gs, ws;
+  int rc = split_rows(dy, d->ldy, (long long)d->X * d->Y * d->Z, d->Cout, &gs, st);
+  if (!rc) rc = split_rows(w, (long long)taps * d->Cin, d->Cout, taps * d->Cin, &ws, st);
+  coocc_conv_desc t = *d;
+  t.dtype = COOCC_DTYPE_TF32;
+  t.ldy = gs.ld;
+  if (!rc) rc = dgrad_impl(&t, gs.hi, ws.hi, dx, ldo, 0, stream);
+  if (!rc) rc = dgrad_impl(&t, gs.hi, ws.lo, dx, ldo, 1, stream);
+  if (!rc) rc = dgrad_impl(&t, gs.lo, ws.hi, dx, ldo, 1, stream);
+  split_free(&gs, st);
+  split_free(&ws, st);
+  return rc;
+}
+
+extern "C" int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const void* dy, float* dw,
+                                  void* stream) {
+  if (!d) return COOCC_ERR_ARG;
+  if (d->dtype != COOCC_DTYPE_TF32X3) return wgrad_impl(d, x, dy, dw, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int pad = d->ksize / 2;
+  const long long Vo = (long long)((d->X + 2 * pad - d->ksize) / d->stride + 1) *
+                       ((d->Y + 2 * pad - d->ksize) / d->stride + 1) *
+                       ((d->Z + 2 * pad - d->ksize) / d->stride + 1);
+  SplitBuf xs, gs;
+  int rc = split_rows(x, d->ldx, (long long)d->X * d->Y * d->Z, d->Cin, &xs, st);
+  if (!rc) rc = split_rows(dy, d->ldy, Vo, d->Cout, &gs, st);
+  coocc_conv_desc t = *d;
+  t.dtype = COOCC_DTYPE_TF32;
+  t.ldx = xs.ld;
+  t.ldy = gs.ld;
+  if (!rc) rc = wgrad_impl(&t, xs.hi, gs.hi, dw, stream);
+  if (!rc) rc = wgrad_impl(&t, xs.hi, gs.lo, dw, stream);
+  if (!rc) rc = wgrad_impl(&t, xs.lo, gs.hi, dw, stream);
+  split_free(&xs, st);
+  split_free(&gs, st);
+  return rc;
 }

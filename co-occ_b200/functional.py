@@ -14,7 +14,24 @@ FPS_NUM = 2048        # P/coocc/fuser/bifuser_n.py:137
 BALL_RADIUS = 6
 BALL_SAMPLES = 200
 
-DT_TF32, DT_BF16 = 0, 1
+DT_TF32, DT_BF16, DT_TF32X3 = 0, 1, 2
+
+# Arithmetic of the tensor-core convolutions / linears:
+#   "fp32" : COOCC_DTYPE_TF32X3, 3-pass hi/lo split, fp32-accurate (parity runs)
+#   "tf32" : single-pass TF32 (what the reference's cuDNN/cuBLAS do by default on Ampere+)
+#   "bf16" : bf16 operands, fp32 accumulation
+_PRECISION = {"mode": "tf32"}
+_DT = {"fp32": DT_TF32X3, "tf32": DT_TF32, "bf16": DT_BF16}
+
+
+def set_precision(mode):
+    if mode not in _DT:
+        raise ValueError("precision must be one of %s" % sorted(_DT))
+    _PRECISION["mode"] = mode
+
+
+def get_precision():
+    return _PRECISION["mode"]
 
 
 def _p(t):
@@ -85,19 +102,37 @@ def out_dim(n, k, s):
 # ----------------------------------------------------------------------------------------
 # convolution / linear on tcgen05
 # ----------------------------------------------------------------------------------------
-def _conv_desc(dims, cin, cout, k, s, ldx, ldy, dtype=DT_TF32):
+def _conv_desc(dims, cin, cout, k, s, ldx, ldy, dtype=None):
     X, Y, Z = dims
+    if dtype is None:
+        dtype = _DT[_PRECISION["mode"]]
     return _lib.ConvDesc(X, Y, Z, cin, cout, k, s, dtype, ldx, ldy)
 
 
-def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=None, out=None):
+def _operand(t, dtype):
+    """operand in the storage type of `dtype` (bf16 mode converts; fp32 modes pass through)."""
+    if dtype != DT_BF16:
+        return t
+    R, C = t.shape
+    ld = (C + 7) // 8 * 8
+    if ld == C:
+        return t.to(torch.bfloat16)
+    buf = torch.zeros(R, ld, device=t.device, dtype=torch.bfloat16)
+    buf[:, :C] = t
+    return buf[:, :C]
+
+
+def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=None, out=None, dtype=None):
     L = _lib.lib()
+    if dtype is None:
+        dtype = _DT[_PRECISION["mode"]]
     odims = tuple(out_dim(n, k, s) for n in dims)
     vo = odims[0] * odims[1] * odims[2]
     ldo = (cout + 3) // 4 * 4
     if out is None:
         out = torch.empty(vo, ldo, device=x2d.device, dtype=torch.float32)
-    d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), ldo)
+    x2d, w2d = _operand(x2d, dtype), _operand(w2d, dtype)
+    d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), ldo, dtype)
     rc = L.coocc_conv3d_fwd(ctypes.byref(d), _p(x2d), _p(w2d), _p(out), out.stride(0), _p(bias),
                             1 if relu else 0, _p(stats), _stream())
     _lib.check(rc, "conv3d_fwd")
@@ -113,26 +148,29 @@ class _Conv3dFn(torch.autograd.Function):
         x2d = _as_rows(x2d)
         w2d = weight_rows(w5d)
         cout, cin = w5d.shape[0], w5d.shape[1]
-        y, odims = conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias, relu)
+        dtype = _DT[_PRECISION["mode"]]
+        y, odims = conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias, relu, dtype=dtype)
         ctx.save_for_backward(x2d, w5d, y if relu else None)
-        ctx.meta = (dims, odims, k, s, relu, bias is not None)
+        ctx.meta = (dims, odims, k, s, relu, bias is not None, dtype)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x2d, w5d, y = ctx.saved_tensors
-        dims, odims, k, s, relu, has_bias = ctx.meta
+        dims, odims, k, s, relu, has_bias, dtype = ctx.meta
         L = _lib.lib()
         cout, cin = w5d.shape[0], w5d.shape[1]
         if relu:
             dy = dy * (y > 0)
         dy = _as_rows(dy)
-        w2d = weight_rows(w5d)
-        dx = dw = db = None
+        db = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
+        w2d = _operand(weight_rows(w5d), dtype)
+        dx = dw = None
         if ctx.needs_input_grad[1]:
             dw2d = torch.zeros(cout, k ** 3 * cin, device=dy.device, dtype=torch.float32)
-            d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), dy.stride(0))
-            _lib.check(L.coocc_conv3d_wgrad(ctypes.byref(d), _p(x2d), _p(dy), _p(dw2d), _stream()), "conv3d_wgrad")
+            xo, dyo = _operand(x2d, dtype), _operand(dy, dtype)
+            d = _conv_desc(dims, cin, cout, k, s, xo.stride(0), dyo.stride(0), dtype)
+            _lib.check(L.coocc_conv3d_wgrad(ctypes.byref(d), _p(xo), _p(dyo), _p(dw2d), _stream()), "conv3d_wgrad")
             # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
             dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
         if ctx.needs_input_grad[0]:
@@ -146,12 +184,11 @@ class _Conv3dFn(torch.autograd.Function):
                 dy_in = dy
             ldo = (cin + 3) // 4 * 4
             dxb = torch.empty(dims[0] * dims[1] * dims[2], ldo, device=dy.device, dtype=torch.float32)
-            d = _conv_desc(dims, cin, cout, k, 1, ldo, dy_in.stride(0))
+            dy_in = _operand(dy_in, dtype)
+            d = _conv_desc(dims, cin, cout, k, 1, ldo, dy_in.stride(0), dtype)
             _lib.check(L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(w2d), _p(dxb), dxb.stride(0), _stream()),
                        "conv3d_dgrad")
             dx = dxb[:, :cin]
-        if has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(0)
         return dx, dw, db, None, None, None, None
 
 

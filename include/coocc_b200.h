@@ -31,6 +31,7 @@ extern "C" {
 
 #define COOCC_DTYPE_TF32 0 /* fp32 storage, tf32 tensor-core math (TMA rounds to nearest), fp32 accumulate */
 #define COOCC_DTYPE_BF16 1 /* bf16 storage and math, fp32 accumulate */
+#define COOCC_DTYPE_TF32X3 2 /* fp32 storage, fp32-accurate: 3-pass hi/lo tf32 split (parity mode) */
 
 int coocc_version(void);
 
