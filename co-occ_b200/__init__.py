@@ -12,3 +12,4 @@ from . import synthetic  # noqa: F401
 from . import _lib  # noqa: F401
 from .functional import get_precision, set_precision  # noqa: F401
 from .modules import BiFuser_N, CustomResNet3D, FPN3D, MLP, OccHead, render_fn  # noqa: F401
+from .hotpath import HotPath, model_cfg  # noqa: F401

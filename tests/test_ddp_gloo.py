@@ -1,0 +1,54 @@
+"""world_size-2 gloo test of the data-parallel gradient reducer (host logic of the N>1 path)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from coocc_b200.ddp import GradReducer
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv3d(4, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv3d(8, 2, 1))
+    # one parameter in channels_last_3d, like the conv weights of the hot path
+    net[0].weight.data = net[0].weight.data.contiguous(memory_format=torch.channels_last_3d)
+    # reference first (no hooks installed yet): average of the per-rank gradients
+    ref = [torch.zeros_like(p) for p in net.parameters()]
+    for r in range(world):
+        net.zero_grad()
+        xr = torch.randn(1, 4, 5, 5, 3, generator=torch.Generator().manual_seed(100 + r))
+        net(xr).square().mean().backward()
+        for acc, p in zip(ref, net.parameters()):
+            acc += p.grad / world
+    net.zero_grad()
+    red = GradReducer(net.parameters(), bucket_bytes=64)
+    assert len(red.buckets) >= 2
+    x = torch.randn(1, 4, 5, 5, 3, generator=torch.Generator().manual_seed(100 + rank))
+    net(x).square().mean().backward()
+    nbytes = red.finish()
+    grads = [p.grad.clone() for p in net.parameters()]
+    ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(grads, ref))
+    q.put((rank, ok, nbytes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(nb > 0 for _, _, nb in res)
