@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward voxels/sec of the Co-Occ fused-voxel hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload northstar|r50|r101|openocc] [--precision tf32|bf16|fp32]
+
+One "step" = one training pass of the hot path over one synthetic scene per GPU:
+GSFusion (BiFuser_N) -> CustomResNet3D-18 -> FPN3D -> OccHead coarse logits + cross-entropy,
+the volume-render regulariser with its two losses, backward through all of it, the data-parallel
+gradient all-reduce (N > 1) and the AdamW update.  `value` = X*Y*Z voxels of the working grid x
+scenes per step / time, summed over ranks (weak scaling, one scene per GPU like samples_per_gpu=1).
+
+--impl reference times the reference's own algorithm on the host CPUs (the oracle restatement,
+oracle/oracle.py, which is bit-identical to the unmodified reference Python -- see
+tests/test_oracle_vs_reference.py) on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "voxels/sec fwd+bwd (fused-voxel hot path: GSFusion + 3D conv decoder/head + volume render)"
+UNIT = "voxels/s"
+CPU_SAMPLE_GRID = (40, 40, 8)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="northstar")
+    ap.add_argument("--precision", default=os.environ.get("COOCC_PRECISION", "tf32"), choices=["tf32", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (oracle = the checker, used here only as the timed CPU baseline / reference arm)
+# ------------------------------------------------------------------------------------------
+def cpu_sample_inputs(cfg, seed=0):
+    from coocc_b200 import synthetic as S
+    grid = CPU_SAMPLE_GRID
+    img, pts = S.make_voxel_feats(grid, cfg["C"], 0.6, 0.25, seed)
+    inp = dict(img_voxel_feats=img, pts_voxel_feats=pts,
+               geom=S.make_geom(grid, cfg["cams"], cfg["fH"], cfg["fW"], cfg["D"], seed))
+    inp["gt_img"], inp["gt_depth"] = S.make_render_targets(cfg["cams"], cfg["fH"], cfg["fW"], seed)
+    g = torch.Generator().manual_seed(seed + 5)
+    occ = torch.randint(1, 17, (1,) + grid, generator=g)
+    occ[torch.rand((1,) + grid, generator=g) < 0.9] = 0
+    inp["gt_occ"] = occ
+    return inp, grid
+
+
+def cpu_step_fn(cfg, seed=0):
+    """fwd+bwd of the reference algorithm (oracle restatement) on the bounded sample."""
+    import torch.nn.functional as F
+    from coocc_b200 import synthetic as S
+    from oracle import oracle as O
+    inp, grid = cpu_sample_inputs(cfg, seed)
+    C, K = cfg["C"], cfg["K"]
+    planes = [C, 2 * C, 4 * C, 8 * C]
+    P = dict(occ_fuser=S.fuser_params(C, K), semantic_encoder=S.resnet3d_params(C, planes),
+             semantic_neck=S.fpn3d_params(planes, 2 * C), pts_bbox_head=S.occhead_params([2 * C] * 4),
+             render=S.render_params(C))
+    P = {m: {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in p.items()} for m, p in P.items()}
+    leaves = [v for p in P.values() for v in p.values() if v.requires_grad]
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def step():
+        for v in leaves:
+            v.grad = None
+        img = inp["img_voxel_feats"].clone().requires_grad_(True)
+        pts = inp["pts_voxel_feats"].clone().requires_grad_(True)
+        out = O.hot_path_forward(P, dict(inp, img_voxel_feats=img, pts_voxel_feats=pts), K, tie="canonical")
+        loss = F.cross_entropy(out["occ"], inp["gt_occ"], ignore_index=255) + out["loss_depth_render"] + out["loss_rgb"]
+        loss.backward()
+        return loss.item()
+
+    return step, grid[0] * grid[1] * grid[2]
+
+
+def cpu_baseline(cfg, warm=1, steps=2):
+    step, nvox = cpu_step_fn(cfg)
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=nvox / dt, unit=UNIT, cores=os.cpu_count() or 1, kind="port",
+                sample="oracle restatement of the reference (PyTorch CPU fp32, %d threads), fwd+bwd on a %dx%dx%d x C=%d grid, "
+                       "K=%d, %d cams x %d rays x %d samples, %d timed steps of %.2f s"
+                       % (os.cpu_count() or 1, *CPU_SAMPLE_GRID, cfg["C"], cfg["K"], cfg["cams"], cfg["fH"] * cfg["fW"],
+                          cfg["D"], steps, dt),
+                seconds_per_step=dt)
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, nvox = cpu_step_fn(cfg)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = nvox / dt
+    line = dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=workload_config(args, cfg),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=os.cpu_count() or 1, kind="port",
+                                  sample="each step = fwd+bwd of the reference algorithm on a %dx%dx%d x C=%d sample grid "
+                                         "of the workload (%.2f s/step)" % (*CPU_SAMPLE_GRID, cfg["C"], dt)),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg):
+    X, Y, Z = cfg["grid"]
+    return dict(workload="%s: %dx%dx%d working grid, C=%d, K=%d, %d cams x %d rays x %d samples, 1 scene/GPU"
+                         % (args.workload, X, Y, Z, cfg["C"], cfg["K"], cfg["cams"], cfg["fH"] * cfg["fW"], cfg["D"]),
+                step="GSFusion + ResNet3D-18 + FPN3D + OccHead(coarse)+CE + render losses, backward, grad all-reduce, AdamW",
+                l2="inputs (%.0f MB/step) exceed the 126 MB L2" % (2 * X * Y * Z * cfg["C"] * 4 / 1e6),
+                parallelism="dp%d (replicas only)" % args.gpus, precision=args.precision)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch.distributed as dist
+    import coocc_b200
+    from coocc_b200 import functional as CF
+    from coocc_b200 import synthetic as S
+    from coocc_b200 import _lib
+    from coocc_b200.ddp import GradReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    coocc_b200.set_precision(args.precision)
+    C, K = cfg["C"], cfg["K"]
+    X, Y, Z = cfg["grid"]
+    nvox = X * Y * Z
+
+    torch.manual_seed(0)                      # reference initialisers, same weights on every rank
+    model = coocc_b200.HotPath(coocc_b200.model_cfg(C, K), C).to(dev)
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    reducer = GradReducer(params)
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
+
+    # ---- synthetic scene of this rank in pinned host memory (upstream memory layouts) ------
+    seed = rank
+    img_v, pts_v = S.make_voxel_feats(cfg["grid"], C, cfg["p_img"], cfg["p_pts"], seed)
+    host = dict(img=img_v.permute(0, 1, 4, 2, 3).contiguous().pin_memory(),     # stored [1,C,Z,X,Y]
+                pts=pts_v.permute(0, 1, 4, 3, 2).contiguous().pin_memory(),     # stored [1,C,Z,Y,X]
+                geom=S.make_geom(cfg["grid"], cfg["cams"], cfg["fH"], cfg["fW"], cfg["D"], seed).pin_memory())
+    gi, gd = S.make_render_targets(cfg["cams"], cfg["fH"], cfg["fW"], seed)
+    host["gt_img"], host["gt_depth"] = gi.pin_memory(), gd.pin_memory()
+    g = torch.Generator().manual_seed(seed + 5)
+    occ = torch.randint(1, 17, (1, X, Y, Z), generator=g)
+    occ[torch.rand(1, X, Y, Z, generator=g) < 0.9] = 0
+    host["gt_occ"] = occ.pin_memory()
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+
+    def to_device():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        d["img"] = d["img"].permute(0, 1, 3, 4, 2)      # logical [1,C,X,Y,Z], upstream strides
+        d["pts"] = d["pts"].permute(0, 1, 4, 3, 2)
+        return d
+
+    def step(d):
+        opt.zero_grad(set_to_none=True)
+        losses, _, _ = model.forward_train(d["img"], d["pts"], d["geom"], d["gt_depth"], d["gt_img"], d["gt_occ"])
+        loss = losses["loss_voxel_ce_c_0"] + losses["loss_depth_render"] + losses["loss_rgb"]
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    resident = to_device()
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _lib.CALLS["n"] = 0
+    ms = timed(lambda: step(resident), args.steps)
+    launches = _lib.CALLS["n"]
+    # end-to-end: host (pinned) inputs in, loss out, every step
+    last = {}
+
+    def e2e_step():
+        last["loss"] = float(step(to_device()).item())
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (tc_conv_kernel), measured live with CUDA events ---
+    CF.PROFILE = []
+    step(resident)
+    torch.cuda.synchronize()
+    prof = CF.PROFILE
+    CF.PROFILE = None
+    t_conv = sum(a.elapsed_time(b) for a, b, _, _ in prof) / 1e3
+    f_conv = sum(f for _, _, f, _ in prof)
+    n_conv = len(prof)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = peaks.get("bf16_tflops_sustained")
+    peak_src = "measured bf16 sustained (MEASURED_PEAKS.json)"
+    if peak is None:
+        peak, peak_src = 1400.0, "fallback sustained bf16 (B200_PROFILING.md)"
+    achieved = f_conv / t_conv / 1e12 if t_conv > 0 else 0.0
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    value = nvox * world * args.steps / (ms / 1e3)
+    e2e_val = nvox * world * args.steps / (ms_e2e / 1e3)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype={"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.precision], data="synthetic",
+                config=workload_config(args, cfg), clocks=clk,
+                e2e=dict(value=e2e_val, unit=UNIT, ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d_bytes,
+                         d2h_bytes_per_step=4, loss=last.get("loss")),
+                gpu_launches=launches,
+                roofline=dict(bound="tensor", kernel="tc_conv_kernel (all conv/linear launches of one step)",
+                              achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                              launches_per_step=n_conv, algorithmic_flops_per_step=f_conv,
+                              kernel_ms_per_step=t_conv * 1e3, share_of_step=t_conv * 1e3 / (ms / args.steps),
+                              peak_source=peak_src,
+                              note="tf32 math has half the nominal bf16 rate" if args.precision == "tf32" else ""))
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from coocc_b200 import synthetic as S
+    cfg = S.CONFIGS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

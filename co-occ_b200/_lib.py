@@ -83,6 +83,10 @@ def exported_symbols():
     return list(_SIGS.keys())
 
 
+CALLS = {"n": 0}      # number of kernel-launching C-ABI calls made (bench.py reports it)
+
+
 def check(rc, what):
+    CALLS["n"] += 1
     if rc != 0:
         raise RuntimeError("coocc_b200.%s failed: %s (%d)" % (what, ERRORS.get(rc, "unknown"), rc))

@@ -34,6 +34,20 @@ def get_precision():
     return _PRECISION["mode"]
 
 
+PROFILE = None     # bench.py sets this to a list to time every conv launch with CUDA events
+
+
+def _timed(tag, flops, fn):
+    if PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn()
+    e1.record()
+    PROFILE.append((e0, e1, flops, tag))
+    return rc
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -133,8 +147,9 @@ def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=N
         out = torch.empty(vo, ldo, device=x2d.device, dtype=torch.float32)
     x2d, w2d = _operand(x2d, dtype), _operand(w2d, dtype)
     d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), ldo, dtype)
-    rc = L.coocc_conv3d_fwd(ctypes.byref(d), _p(x2d), _p(w2d), _p(out), out.stride(0), _p(bias),
-                            1 if relu else 0, _p(stats), _stream())
+    flops = 2.0 * vo * (k ** 3) * cin * cout
+    rc = _timed("fwd", flops, lambda: L.coocc_conv3d_fwd(ctypes.byref(d), _p(x2d), _p(w2d), _p(out), out.stride(0),
+                                                         _p(bias), 1 if relu else 0, _p(stats), _stream()))
     _lib.check(rc, "conv3d_fwd")
     return out[:, :cout], odims
 
@@ -170,7 +185,9 @@ class _Conv3dFn(torch.autograd.Function):
             dw2d = torch.zeros(cout, k ** 3 * cin, device=dy.device, dtype=torch.float32)
             xo, dyo = _operand(x2d, dtype), _operand(dy, dtype)
             d = _conv_desc(dims, cin, cout, k, s, xo.stride(0), dyo.stride(0), dtype)
-            _lib.check(L.coocc_conv3d_wgrad(ctypes.byref(d), _p(xo), _p(dyo), _p(dw2d), _stream()), "conv3d_wgrad")
+            flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
+            _lib.check(_timed("wgrad", flops, lambda: L.coocc_conv3d_wgrad(ctypes.byref(d), _p(xo), _p(dyo), _p(dw2d),
+                                                                          _stream())), "conv3d_wgrad")
             # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
             dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
         if ctx.needs_input_grad[0]:
@@ -186,8 +203,9 @@ class _Conv3dFn(torch.autograd.Function):
             dxb = torch.empty(dims[0] * dims[1] * dims[2], ldo, device=dy.device, dtype=torch.float32)
             dy_in = _operand(dy_in, dtype)
             d = _conv_desc(dims, cin, cout, k, 1, ldo, dy_in.stride(0), dtype)
-            _lib.check(L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(w2d), _p(dxb), dxb.stride(0), _stream()),
-                       "conv3d_dgrad")
+            flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
+            _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(w2d), _p(dxb),
+                                                                          dxb.stride(0), _stream())), "conv3d_dgrad")
             dx = dxb[:, :cin]
         return dx, dw, db, None, None, None, None
 
