@@ -1,0 +1,258 @@
+// elementwise.cu -- HBM-bound companions of the tensor-core convolutions:
+//   BatchNorm3d (training mode) fused with ReLU and the residual add, forward and backward,
+//   fed by the per-channel sums the conv epilogue already produced (no extra statistics pass);
+//   x2 zero-insertion for the strided-conv data gradient.
+//
+// Reference semantics: torch.nn.BatchNorm3d / SyncBatchNorm (world size 1) as used at
+// P/coocc/fuser/bifuser_n.py:25,28, P/coocc/backbones/resnet3d.py:41,45,54-60,
+// P/coocc/necks/fpn3d.py:48-67 (ConvModule), P/coocc/dense_heads/occ_head.py:102-132:
+//   y = (x - mean_batch) / sqrt(var_biased + eps) * gamma + beta ; running stats with momentum,
+//   running_var from the unbiased variance.
+// All tensors are [V, C] row-major (NDHWC); one thread owns 4 consecutive channels of a row, a
+// warp covers 128 contiguous channels (512 B) -> fully coalesced float4 traffic.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/coocc_b200.h"
+
+namespace coocc {
+
+// mean / invstd from the conv epilogue sums; updates the running statistics in place
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, double count, float eps,
+                                   float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ mean_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = (double)stats[c] / count;
+  double var = (double)stats[C + c] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean_invstd[c] = (float)m;
+  mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// out = relu?( (x - mean) * invstd * gamma + beta (+ residual) )
+template <typename OutT>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ x, long long ldx,
+                                                         long long V, int C,
+                                                         const float* __restrict__ mean_invstd,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta,
+                                                         const float* __restrict__ residual, long long ldr,
+                                                         int relu, OutT* __restrict__ out, long long ldo) {
+  const int c4 = C >> 2;
+  const long long total = V * c4;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long r = i / c4;
+    const int c = (int)(i % c4) * 4;
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float4 m = *reinterpret_cast<const float4*>(mean_invstd + c);
+    const float4 is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    float4 y;
+    y.x = (xv.x - m.x) * is.x * g.x + b.x;
+    y.y = (xv.y - m.y) * is.y * g.y + b.y;
+    y.z = (xv.z - m.z) * is.z * g.z + b.z;
+    y.w = (xv.w - m.w) * is.w * g.w + b.w;
+    if (residual != nullptr) {
+      const float4 rv = *reinterpret_cast<const float4*>(residual + r * ldr + c);
+      y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
+    }
+    if (relu) {
+      y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+    }
+    store4(out + r * ldo + c, y);
+  }
+}
+
+// sums[c] = sum_r dz, sums[C + c] = sum_r dz * xhat, dz = dout * [out > 0] (relu) or dout
+// block = 32 x 8: threadIdx.x -> channel group (4 channels), threadIdx.y -> row lane.
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
+    const float* __restrict__ dout, long long ldd, const float* __restrict__ out, long long ldo,
+    const float* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
+    int relu, int rows_per_block, float* __restrict__ sums) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  if (c < C) {
+    const float4 m = *reinterpret_cast<const float4*>(mean_invstd + c);
+    const float4 is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(V, r0 + rows_per_block);
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      float4 d = *reinterpret_cast<const float4*>(dout + r * ldd + c);
+      if (relu) {
+        const float4 o = *reinterpret_cast<const float4*>(out + r * ldo + c);
+        d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
+        d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+      }
+      const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+      s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+      s2.x += d.x * (xv.x - m.x) * is.x; s2.y += d.y * (xv.y - m.y) * is.y;
+      s2.z += d.z * (xv.z - m.z) * is.z; s2.w += d.w * (xv.w - m.w) * is.w;
+    }
+  }
+  __shared__ float4 sh1[8][32], sh2[8][32];
+  sh1[threadIdx.y][threadIdx.x] = s1;
+  sh2[threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) {
+      const float4 a = sh1[j][threadIdx.x], b = sh2[j][threadIdx.x];
+      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+      s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+    }
+    atomicAdd(&sums[c + 0], s1.x); atomicAdd(&sums[c + 1], s1.y);
+    atomicAdd(&sums[c + 2], s1.z); atomicAdd(&sums[c + 3], s1.w);
+    atomicAdd(&sums[C + c + 0], s2.x); atomicAdd(&sums[C + c + 1], s2.y);
+    atomicAdd(&sums[C + c + 2], s2.z); atomicAdd(&sums[C + c + 3], s2.w);
+  }
+}
+
+// dx = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  dres = dz (optional)
+template <typename OutT>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
+    const float* __restrict__ dout, long long ldd, const float* __restrict__ out, long long ldo,
+    const float* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
+    const float* __restrict__ gamma, const float* __restrict__ sums, int relu, OutT* __restrict__ dx,
+    long long lddx, float* __restrict__ dres, long long lddr) {
+  const int c4 = C >> 2;
+  const long long total = V * c4;
+  const float inv_n = 1.f / (float)V;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long r = i / c4;
+    const int c = (int)(i % c4) * 4;
+    float4 d = *reinterpret_cast<const float4*>(dout + r * ldd + c);
+    if (relu) {
+      const float4 o = *reinterpret_cast<const float4*>(out + r * ldo + c);
+      d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
+      d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+    }
+    if (dres != nullptr) *reinterpret_cast<float4*>(dres + r * lddr + c) = d;
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float4 m = *reinterpret_cast<const float4*>(mean_invstd + c);
+    const float4 is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 a = *reinterpret_cast<const float4*>(sums + c);
+    const float4 b = *reinterpret_cast<const float4*>(sums + C + c);
+    float4 y;
+    y.x = g.x * is.x * (d.x - a.x * inv_n - (xv.x - m.x) * is.x * b.x * inv_n);
+    y.y = g.y * is.y * (d.y - a.y * inv_n - (xv.y - m.y) * is.y * b.y * inv_n);
+    y.z = g.z * is.z * (d.z - a.z * inv_n - (xv.z - m.z) * is.z * b.z * inv_n);
+    y.w = g.w * is.w * (d.w - a.w * inv_n - (xv.w - m.w) * is.w * b.w * inv_n);
+    store4(dx + r * lddx + c, y);
+  }
+}
+
+// up[(2x,2y,2z), :] = src[(x,y,z), :], zeros elsewhere: the data gradient of a stride-2 conv is the
+// stride-1 data gradient of the zero-inserted output gradient.
+template <typename T>
+__global__ void __launch_bounds__(256) dilate2_kernel(const T* __restrict__ src, long long lds, int oX,
+                                                      int oY, int oZ, int C, T* __restrict__ dst,
+                                                      long long ldd, int X, int Y, int Z) {
+  const int cv = C / (16 / (int)sizeof(T));           // 16-byte vectors per row
+  const long long total = (long long)X * Y * Z * cv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long v = i / cv;
+    const int c = (int)(i % cv);
+    const int z = v % Z, y = (v / Z) % Y, x = v / ((long long)Z * Y);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (!(x & 1) && !(y & 1) && !(z & 1) && (x >> 1) < oX && (y >> 1) < oY && (z >> 1) < oZ) {
+      const long long sv = ((long long)(x >> 1) * oY + (y >> 1)) * oZ + (z >> 1);
+      val = *reinterpret_cast<const uint4*>(src + sv * lds + (long long)c * (16 / sizeof(T)));
+    }
+    *reinterpret_cast<uint4*>(dst + v * ldd + (long long)c * (16 / sizeof(T))) = val;
+  }
+}
+
+static int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  if (b > 148LL * 32) b = 148LL * 32;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace coocc
+
+using namespace coocc;
+#define CK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA)
+
+extern "C" int coocc_bn_finalize(const float* stats, int C, long long count, float eps, float momentum,
+                                 float* running_mean, float* running_var, float* mean_invstd, void* stream) {
+  if (!stats || !mean_invstd || C < 1 || count < 1) return COOCC_ERR_ARG;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, C, (double)count, eps, momentum,
+                                                                       running_mean, running_var, mean_invstd);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_bn_act_fwd(const float* x, long long ldx, long long V, int C, const float* mean_invstd,
+                                const float* gamma, const float* beta, const float* residual, long long ldr,
+                                int relu, void* out, long long ldo, int out_bf16, void* stream) {
+  if (!x || !mean_invstd || !gamma || !beta || !out || (C & 3) || (ldx & 3) || (ldo & 3)) return COOCC_ERR_ARG;
+  if (residual && (ldr & 3)) return COOCC_ERR_ARG;
+  const int g = grid_for(V * (C >> 2));
+  if (out_bf16)
+    bn_act_fwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, V, C, mean_invstd, gamma, beta, residual,
+                                                                        ldr, relu, (__nv_bfloat16*)out, ldo);
+  else
+    bn_act_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, V, C, mean_invstd, gamma, beta, residual, ldr,
+                                                                relu, (float*)out, ldo);
+  return CK_LAUNCH();
+}
+
+// sums: float[2*C], zeroed by the caller.  dgamma = sums[C:], dbeta = sums[:C].
+extern "C" int coocc_bn_act_bwd(const float* dout, long long ldd, const float* out, long long ldo, const float* x,
+                                long long ldx, long long V, int C, const float* mean_invstd, const float* gamma,
+                                int relu, float* sums, void* dx, long long lddx, int dx_bf16, float* dres,
+                                long long lddr, void* stream) {
+  if (!dout || !x || !mean_invstd || !gamma || !sums || !dx || (C & 3) || (ldd & 3) || (ldx & 3) || (lddx & 3))
+    return COOCC_ERR_ARG;
+  if (relu && (!out || (ldo & 3))) return COOCC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cgroups = (C / 4 + 31) / 32;
+  int rows_per_block = 256;
+  long long nby = (V + rows_per_block - 1) / rows_per_block;
+  while (nby * cgroups > 148LL * 16) {
+    rows_per_block *= 2;
+    nby = (V + rows_per_block - 1) / rows_per_block;
+  }
+  bn_act_bwd_reduce_kernel<<<dim3(cgroups, (unsigned)nby), dim3(32, 8), 0, st>>>(dout, ldd, out, ldo, x, ldx, V, C,
+                                                                               mean_invstd, relu, rows_per_block, sums);
+  const int g = grid_for(V * (C >> 2));
+  if (dx_bf16)
+    bn_act_bwd_apply_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(dout, ldd, out, ldo, x, ldx, V, C, mean_invstd, gamma, sums,
+                                                             relu, (__nv_bfloat16*)dx, lddx, dres, lddr);
+  else
+    bn_act_bwd_apply_kernel<float><<<g, 256, 0, st>>>(dout, ldd, out, ldo, x, ldx, V, C, mean_invstd, gamma, sums, relu,
+                                                     (float*)dx, lddx, dres, lddr);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_dilate2(const void* src, long long lds, int oX, int oY, int oZ, int C, void* dst, long long ldd,
+                             int X, int Y, int Z, int is_bf16, void* stream) {
+  if (!src || !dst) return COOCC_ERR_ARG;
+  const int es = is_bf16 ? 2 : 4;
+  if ((C * es) % 16 || (lds * es) % 16 || (ldd * es) % 16) return COOCC_ERR_ALIGN;
+  const long long total = (long long)X * Y * Z * (C * es / 16);
+  if (is_bf16)
+    dilate2_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, lds, oX, oY, oZ, C, (__nv_bfloat16*)dst, ldd, X, Y, Z);
+  else
+    dilate2_kernel<float><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const float*)src, lds, oX, oY, oZ, C,
+                                                                            (float*)dst, ldd, X, Y, Z);
+  return CK_LAUNCH();
+}

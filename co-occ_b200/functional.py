@@ -146,7 +146,7 @@ def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=N
     if out is None:
         out = torch.empty(vo, ldo, device=x2d.device, dtype=torch.float32)
     x2d, w2d = _operand(x2d, dtype), _operand(w2d, dtype)
-    d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), ldo, dtype)
+    d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), (cout + 7) // 8 * 8, dtype)
     flops = 2.0 * vo * (k ** 3) * cin * cout
     rc = _timed("fwd", flops, lambda: L.coocc_conv3d_fwd(ctypes.byref(d), _p(x2d), _p(w2d), _p(out), out.stride(0),
                                                          _p(bias), 1 if relu else 0, _p(stats), _stream()))
