@@ -54,6 +54,10 @@ _SIGS = {
     "coocc_gsf_modulate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p]),
     "coocc_gsf_modulate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
     "coocc_gsf_scatter_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_bn_finalize": (c_int, [c_void_p, c_int, c_ll, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "coocc_bn_act_fwd": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p]),
+    "coocc_bn_act_bwd": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_dilate2": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "coocc_render_box": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "coocc_render_box_gather": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "coocc_render_box_scatter_add": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),

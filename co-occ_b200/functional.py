@@ -158,19 +158,23 @@ class _Conv3dFn(torch.autograd.Function):
     """y[Vout,Cout] = conv3d(x[V,Cin], w[Cout,Cin,k,k,k]) (+bias)(relu), padding k//2."""
 
     @staticmethod
-    def forward(ctx, x2d, w5d, bias, dims, k, s, relu):
+    def forward(ctx, x2d, w5d, bias, dims, k, s, relu, want_stats=False):
         _require_cuda(x2d, w5d)
         x2d = _as_rows(x2d)
         w2d = weight_rows(w5d)
         cout, cin = w5d.shape[0], w5d.shape[1]
         dtype = _DT[_PRECISION["mode"]]
-        y, odims = conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias, relu, dtype=dtype)
+        stats = torch.zeros(2, cout, device=x2d.device, dtype=torch.float32) if want_stats else None
+        y, odims = conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias, relu, stats=stats, dtype=dtype)
         ctx.save_for_backward(x2d, w5d, y if relu else None)
         ctx.meta = (dims, odims, k, s, relu, bias is not None, dtype)
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         x2d, w5d, y = ctx.saved_tensors
         dims, odims, k, s, relu, has_bias, dtype = ctx.meta
         L = _lib.lib()
@@ -194,9 +198,10 @@ class _Conv3dFn(torch.autograd.Function):
             if s != 1:
                 # scatter dy onto the input lattice (even positions), then a stride-1 dgrad
                 X, Y, Z = dims
-                up = torch.zeros(X, Y, Z, dy.shape[1], device=dy.device, dtype=torch.float32)
-                up[::2, ::2, ::2][:odims[0], :odims[1], :odims[2]] = dy.reshape(*odims, dy.shape[1])
-                dy_in = up.reshape(X * Y * Z, dy.shape[1])
+                dy_in = torch.empty(X * Y * Z, dy.stride(0), device=dy.device, dtype=torch.float32)
+                _lib.check(L.coocc_dilate2(_p(dy), dy.stride(0), odims[0], odims[1], odims[2], dy.stride(0),
+                                           _p(dy_in), dy_in.stride(0), X, Y, Z, 0, _stream()), "dilate2")
+                dy_in = dy_in[:, :dy.shape[1]]
             else:
                 dy_in = dy
             ldo = (cin + 3) // 4 * 4
@@ -207,11 +212,53 @@ class _Conv3dFn(torch.autograd.Function):
             _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(w2d), _p(dxb),
                                                                           dxb.stride(0), _stream())), "conv3d_dgrad")
             dx = dxb[:, :cin]
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def conv3d(x2d, w5d, dims, k, s=1, bias=None, relu=False):
-    return _Conv3dFn.apply(x2d, w5d, bias, dims, k, s, relu)
+def conv3d(x2d, w5d, dims, k, s=1, bias=None, relu=False, want_stats=False):
+    return _Conv3dFn.apply(x2d, w5d, bias, dims, k, s, relu, want_stats)
+
+
+class _BNActFn(torch.autograd.Function):
+    """out = relu?(batchnorm_train(x) (+ residual)) from the conv-epilogue statistics."""
+
+    @staticmethod
+    def forward(ctx, x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var):
+        L = _lib.lib()
+        V, C = x.shape
+        dev = x.device
+        mi = torch.empty(2, C, device=dev, dtype=torch.float32)
+        _lib.check(L.coocc_bn_finalize(_p(stats), C, V, float(eps), float(momentum), _p(running_mean),
+                                       _p(running_var), _p(mi), _stream()), "bn_finalize")
+        out = torch.empty(V, C, device=dev, dtype=torch.float32)
+        if residual is not None:
+            residual = _as_rows(residual)
+        _lib.check(L.coocc_bn_act_fwd(_p(x), x.stride(0), V, C, _p(mi), _p(gamma), _p(beta), _p(residual),
+                                      residual.stride(0) if residual is not None else 0, 1 if relu else 0,
+                                      _p(out), out.stride(0), 0, _stream()), "bn_act_fwd")
+        ctx.save_for_backward(x, out if relu else None, mi, gamma)
+        ctx.meta = (relu, residual is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        x, out, mi, gamma = ctx.saved_tensors
+        relu, has_res = ctx.meta
+        V, C = x.shape
+        dout = _as_rows(dout)
+        sums = torch.zeros(2, C, device=x.device, dtype=torch.float32)
+        dx = torch.empty(V, C, device=x.device, dtype=torch.float32)
+        dres = torch.empty(V, C, device=x.device, dtype=torch.float32) if has_res else None
+        _lib.check(L.coocc_bn_act_bwd(_p(dout), dout.stride(0), _p(out), out.stride(0) if out is not None else 0,
+                                      _p(x), x.stride(0), V, C, _p(mi), _p(gamma), 1 if relu else 0, _p(sums), _p(dx),
+                                      dx.stride(0), 0, _p(dres), C if has_res else 0, _stream()), "bn_act_bwd")
+        return dx, None, sums[1], sums[0], dres, None, None, None, None, None
+
+
+def bn_act(x, stats, gamma, beta, residual=None, relu=True, eps=1e-5, momentum=0.1, running_mean=None,
+           running_var=None):
+    return _BNActFn.apply(x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var)
 
 
 def linear(x2d, weight, bias=None, relu=False):

@@ -47,13 +47,26 @@ def batch_norm2d(x2d, bn):
                         bn.weight, bn.bias, use_batch, mom, bn.eps)
 
 
-def conv_bn_act(x2d, dims, conv, bn=None, relu=True):
+def conv_bn_act(x2d, dims, conv, bn=None, relu=True, residual=None):
+    """conv -> BatchNorm (batch statistics from the conv epilogue) -> (+ residual) -> ReLU."""
     k = conv.kernel_size[0]
     s = conv.stride[0]
-    y = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, bias=conv.bias)
     odims = tuple(CF.out_dim(n, k, s) for n in dims)
+    fused = (bn is not None and bn.training and conv.bias is None and conv.out_channels % 4 == 0
+             and bn.momentum is not None)
+    if fused:
+        y, stats = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, want_stats=True)
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        track = bn.track_running_stats
+        y = CF.bn_act(y, stats, bn.weight, bn.bias, residual, relu, bn.eps, bn.momentum,
+                      bn.running_mean if track else None, bn.running_var if track else None)
+        return y, odims
+    y = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, bias=conv.bias)
     if bn is not None:
         y = batch_norm2d(y, bn)
+    if residual is not None:
+        y = y + residual
     if relu:
         y = F.relu(y)
     return y, odims
@@ -108,12 +121,12 @@ class BasicBlock(nn.Module):
 
     def forward2d(self, x, dims):
         out, odims = conv_bn_act(x, dims, self.conv1, self.bn1)
-        out, _ = conv_bn_act(out, odims, self.conv2, self.bn2, relu=False)
         if self.downsample is not None:
             idn, _ = conv_bn_act(x, dims, self.downsample[0], self.downsample[1], relu=False)
         else:
             idn = x
-        return F.relu(out + idn), odims
+        out, _ = conv_bn_act(out, odims, self.conv2, self.bn2, relu=True, residual=idn)   # resnet3d.py:53-60
+        return out, odims
 
 
 @BACKBONES.register_module(force=True)

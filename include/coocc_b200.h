@@ -150,6 +150,31 @@ int coocc_render_upsample_loss_bwd(const float* rgbs, const float* depths, int n
                                    const float* g_losses2, float* g_rgb_map, float* g_depth_map,
                                    void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm3d (training mode) + ReLU + residual, and x2 zero insertion (csrc/elementwise.cu).
+ * Replaces torch.nn.BatchNorm3d / SyncBatchNorm + nn.ReLU (+ `out += residual`) at
+ * P/coocc/fuser/bifuser_n.py:25-29, P/coocc/backbones/resnet3d.py:46-62, P/coocc/necks/fpn3d.py:48-67,
+ * P/coocc/dense_heads/occ_head.py:102-132.  Tensors are [V, C] row-major, C % 4 == 0.
+ * ------------------------------------------------------------------------------------------ */
+/* stats = float[2*C] (sum, sum of squares) from coocc_conv3d_fwd; writes mean_invstd = float[2*C] and
+ * updates running_mean / running_var (may be NULL) with `momentum` (unbiased variance). */
+int coocc_bn_finalize(const float* stats, int C, long long count, float eps, float momentum,
+                      float* running_mean, float* running_var, float* mean_invstd, void* stream);
+/* out = relu?((x - mean) * invstd * gamma + beta (+ residual)); out is fp32 or bf16 */
+int coocc_bn_act_fwd(const float* x, long long ldx, long long V, int C, const float* mean_invstd,
+                     const float* gamma, const float* beta, const float* residual, long long ldr, int relu,
+                     void* out, long long ldo, int out_bf16, void* stream);
+/* backward of the above.  sums = float[2*C] zeroed by the caller; on return sums[0:C] = dbeta,
+ * sums[C:2C] = dgamma.  dx (fp32 or bf16) = gradient w.r.t. x; dres (optional) = gradient w.r.t.
+ * the residual input. */
+int coocc_bn_act_bwd(const float* dout, long long ldd, const float* out, long long ldo, const float* x,
+                     long long ldx, long long V, int C, const float* mean_invstd, const float* gamma, int relu,
+                     float* sums, void* dx, long long lddx, int dx_bf16, float* dres, long long lddr,
+                     void* stream);
+/* dst[(2x,2y,2z)] = src[(x,y,z)], zero elsewhere (dst extent X,Y,Z; src extent oX,oY,oZ) */
+int coocc_dilate2(const void* src, long long lds, int oX, int oY, int oZ, int C, void* dst, long long ldd,
+                  int X, int Y, int Z, int is_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

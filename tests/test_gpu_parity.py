@@ -243,3 +243,51 @@ def test_conv3d_op_forward_backward(case, precision):
     _report("conv%s[%s]" % (str(case), precision), **e)
     bound = 2e-5 if precision == "fp32" else 2e-3
     assert max(e.values()) < bound
+
+
+# ------------------------------------------------------------------------------- fused BN
+@pytest.mark.parametrize("res", [False, True])
+def test_conv_bn_relu_fused(res, precision):
+    """conv -> BatchNorm3d(train) -> (+residual) -> ReLU through the fused kernels
+    (conv-epilogue statistics + bn_act fwd/bwd) against torch CPU modules."""
+    import torch.nn as nn
+    from coocc_b200 import modules as M
+    gen = torch.Generator().manual_seed(7)
+    Cin, Cout, dims = 32, 64, (11, 9, 4)
+    conv = nn.Conv3d(Cin, Cout, 3, 1, 1, bias=False)
+    bn = nn.BatchNorm3d(Cout)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) * 0.05)
+        bn.weight.copy_(torch.rand(Cout, generator=gen) + 0.5)
+        bn.bias.copy_(torch.randn(Cout, generator=gen) * 0.1)
+    x0 = torch.randn(1, Cin, *dims, generator=gen)
+    r0 = torch.randn(1, Cout, *dims, generator=gen)
+    import copy
+    conv_g, bn_g = copy.deepcopy(conv).to(DEV), copy.deepcopy(bn).to(DEV)
+    # CPU reference
+    xr, rr = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+    y = bn(conv(xr))
+    if res:
+        y = y + rr
+    y = torch.relu(y)
+    gy = torch.randn(y.shape, generator=gen)
+    y.backward(gy)
+    # fused CUDA path
+    x = x0.to(DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    r = r0.to(DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    x2d, d = CF.to_cl2d(x)
+    r2d = CF.to_cl2d(r)[0] if res else None
+    o2d, _ = M.conv_bn_act(x2d, d, conv_g, bn_g, relu=True, residual=r2d)
+    o = CF.to_5d(o2d, d)
+    o.backward(gy.to(DEV))
+    torch.cuda.synchronize()
+    e = dict(y=rel_err(o, y), dx=rel_l2(x.grad, xr.grad), dw=rel_l2(conv_g.weight.grad, conv.weight.grad),
+             dgamma=rel_l2(bn_g.weight.grad, bn.weight.grad), dbeta=rel_l2(bn_g.bias.grad, bn.bias.grad),
+             rmean=rel_err(bn_g.running_mean, bn.running_mean), rvar=rel_err(bn_g.running_var, bn.running_var))
+    if res:
+        e["dres"] = rel_l2(r.grad, rr.grad)
+    _report("conv_bn_relu[res=%s,%s]" % (res, precision), **e)
+    fwd_b, bwd_b = (2e-5, 2e-3) if precision == "fp32" else (3e-3, 5e-2)
+    assert e["y"] < fwd_b and e["rmean"] < fwd_b and e["rvar"] < fwd_b
+    assert max(v for k, v in e.items() if k.startswith("d")) < bwd_b
+    assert int(bn_g.num_batches_tracked) == 1
