@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   // ---- tile bookkeeping (identical in every role) ---------------------------------------
   const int ntn = (p.N + p.BN - 1) / p.BN;
   const int ntm = (p.M + kBM - 1) / kBM;
-  const int ntiles = wgrad ? ntm * ntn * p.taps * p.ksplit : ntm * ntn;
+  const int ntiles = wgrad ? ntm * ntn * p.taps * p.ksplit : ntm * ntn * p.ksplit;
   const int kb_per_tap = (p.Kc + E::BKE - 1) / E::BKE;
 
   if (threadIdx.x == 0) {
@@ -146,27 +146,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int mt, nt, tap0, tap1, kb0, kb1;
+        int mt, nt, it0, it1;          // it = flattened (tap, k-block) iteration
+        int wg_tap = 0;
         if (!wgrad) {
-          nt = tile % ntn;
-          mt = tile / ntn;
-          tap0 = 0; tap1 = p.taps; kb0 = 0; kb1 = kb_per_tap;
+          int t = tile;
+          const int sp = t % p.ksplit; t /= p.ksplit;
+          nt = t % ntn;
+          mt = t / ntn;
+          const int nk_total = p.taps * kb_per_tap;
+          it0 = (int)((long long)nk_total * sp / p.ksplit);
+          it1 = (int)((long long)nk_total * (sp + 1) / p.ksplit);
         } else {
           int t = tile;
           const int sp = t % p.ksplit; t /= p.ksplit;
           nt = t % ntn; t /= ntn;
           mt = t % ntm; t /= ntm;
-          tap0 = t; tap1 = t + 1;
-          kb0 = (int)((long long)p.nvb * sp / p.ksplit);
-          kb1 = (int)((long long)p.nvb * (sp + 1) / p.ksplit);
+          wg_tap = t;
+          it0 = (int)((long long)p.nvb * sp / p.ksplit);
+          it1 = (int)((long long)p.nvb * (sp + 1) / p.ksplit);
         }
-        for (int tap = tap0; tap < tap1; ++tap) {
+        for (int it = it0; it < it1; ++it) {
+          const int tap = wgrad ? wg_tap : it / kb_per_tap;
+          const int kb = wgrad ? it : it % kb_per_tap;
           // filter offsets of this tap in the im2col operand (W<->z, H<->y, D<->x)
           const int kx = (p.taps == 1) ? 0 : tap / 9, ky = (p.taps == 1) ? 0 : (tap / 3) % 3,
                     kz = (p.taps == 1) ? 0 : tap % 3;
           // dgrad walks the mirrored tap of the weight tensor
           const int wtap = (p.mode == MODE_DGRAD) ? (p.taps - 1 - tap) : tap;
-          for (int kb = kb0; kb < kb1; ++kb) {
+          {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * kStageBytes;
             uint8_t* sb = sa + kABytes;
@@ -224,11 +231,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int nk;
-        if (!wgrad) {
-          nk = p.taps * kb_per_tap;
-        } else {
+        {
           const int sp = tile % p.ksplit;
-          nk = (int)((long long)p.nvb * (sp + 1) / p.ksplit) - (int)((long long)p.nvb * sp / p.ksplit);
+          const int tot = wgrad ? p.nvb : p.taps * kb_per_tap;
+          nk = (int)((long long)tot * (sp + 1) / p.ksplit) - (int)((long long)tot * sp / p.ksplit);
         }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -265,8 +271,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int mt, nt, tap = 0, nk = 1;
       if (!wgrad) {
-        nt = tile % ntn;
-        mt = tile / ntn;
+        int t = tile;
+        const int sp = t % p.ksplit; t /= p.ksplit;
+        nt = t % ntn;
+        mt = t / ntn;
+        const int tot = p.taps * kb_per_tap;
+        nk = (int)((long long)tot * (sp + 1) / p.ksplit) - (int)((long long)tot * sp / p.ksplit);
       } else {
         int t = tile;
         const int sp = t % p.ksplit; t /= p.ksplit;
@@ -290,7 +300,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
         const int col0 = nt * p.BN + c0;
-        if (!wgrad) {
+        if (!wgrad && p.ksplit > 1) {
+          // split-K partial of an under-filled layer: accumulate atomically into the zeroed output
+          if (row_ok && nk > 0) {
+            float* o = p.out + (long long)row * p.ldc + col0;
+            if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i),
+                             "f"(__uint_as_float(v[i])), "f"(__uint_as_float(v[i + 1])),
+                             "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                             : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) atomicAdd(o + i, __uint_as_float(v[i]));
+            }
+          }
+        } else if (!wgrad) {
           float* o = p.out + (long long)row * p.ldc + col0;
           const bool vec = (col0 + 32 <= p.N) && ((p.ldc & 3) == 0);
           if (p.accum && row_ok) {
@@ -512,6 +540,48 @@ static int launch(const TcParams& p, int ntiles, cudaStream_t st) {
   return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
 }
 
+// column sums / sums of squares of a small [M, N] matrix (BN statistics of split-K layers)
+__global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ y, long long ld, int M, int N,
+                                                       float* __restrict__ stats) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  float s = 0.f, q = 0.f;
+  if (c < N)
+    for (int r = blockIdx.y * 8 + (threadIdx.x >> 5); r < M; r += gridDim.y * 8) {
+      const float v = y[(long long)r * ld + c];
+      s += v;
+      q += v * v;
+    }
+  __shared__ float sh[2][8][32];
+  sh[0][threadIdx.x >> 5][threadIdx.x & 31] = s;
+  sh[1][threadIdx.x >> 5][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (threadIdx.x < 32 && c < N) {
+    for (int j = 1; j < 8; ++j) { s += sh[0][j][threadIdx.x]; q += sh[1][j][threadIdx.x]; }
+    atomicAdd(&stats[c], s);
+    atomicAdd(&stats[N + c], q);
+  }
+}
+
+// split the reduction of an under-filled fprop/dgrad launch over several CTAs
+static int pick_ksplit(int ntiles, int nk_total) {
+  if (ntiles * 2 > g_num_sms || nk_total < 8) return 1;
+  int ks = g_num_sms / ntiles;
+  if (ks > nk_total / 4) ks = nk_total / 4;
+  return ks < 1 ? 1 : ks;
+}
+
+static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
+  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN);
+  p.ksplit = 1;
+  if (p.bias == nullptr && !p.relu) p.ksplit = pick_ksplit(ntiles, nk_total);
+  if (p.ksplit > 1 && !p.accum) {
+    if (cudaMemset2DAsync(p.out, (size_t)p.ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), (size_t)p.M, st) !=
+        cudaSuccess)
+      return COOCC_ERR_CUDA;
+  }
+  return 0;
+}
+
 static int pick_bn(int n) {
   int bn = ((n + 15) / 16) * 16;
   if (bn <= kMaxBN) return bn;
@@ -575,8 +645,17 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
   rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, bke,
                   p.BN, false);
   if (rc) return rc;
-  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN);
-  return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+  float* stats_after = nullptr;
+  if ((rc = prepare_split(p, taps * ((d->Cin + bke - 1) / bke), (cudaStream_t)stream))) return rc;
+  if (p.ksplit > 1 && p.stats) { stats_after = p.stats; p.stats = nullptr; }
+  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
+  rc = es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+  if (!rc && stats_after) {
+    dim3 grid((p.N + 31) / 32, p.M >= 4096 ? 64 : (p.M + 63) / 64);
+    colstats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p.out, p.ldc, p.M, p.N, stats_after);
+    rc = cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+  }
+  return rc;
 }
 
 // dX[v, ci] = sum_{tap,co} dY[v - tap + pad, co] W[co, tap, ci]; stride-1 convolutions only
@@ -622,7 +701,8 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, f
   if (rc) return rc;
   rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, ch, ch, true);
   if (rc) return rc;
-  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN);
+  if ((rc = prepare_split(p, taps * ((d->Cout + ch - 1) / ch), (cudaStream_t)stream))) return rc;
+  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
   return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
 }
 
