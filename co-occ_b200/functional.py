@@ -125,7 +125,7 @@ def _conv_desc(dims, cin, cout, k, s, ldx, ldy, dtype=None):
 
 def _operand(t, dtype):
     """operand in the storage type of `dtype` (bf16 mode converts; fp32 modes pass through)."""
-    if dtype != DT_BF16:
+    if dtype != DT_BF16 or t.dtype == torch.bfloat16:
         return t
     R, C = t.shape
     ld = (C + 7) // 8 * 8
@@ -145,7 +145,7 @@ def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=N
     ldo = (cout + 3) // 4 * 4
     if out is None:
         out = torch.empty(vo, ldo, device=x2d.device, dtype=torch.float32)
-    x2d, w2d = _operand(x2d, dtype), _operand(w2d, dtype)
+    x2d, w2d = _operand(x2d, dtype), _operand(w2d, dtype)      # no-ops when already converted
     d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), (cout + 7) // 8 * 8, dtype)
     flops = 2.0 * vo * (k ** 3) * cin * cout
     rc = _timed("fwd", flops, lambda: L.coocc_conv3d_fwd(ctypes.byref(d), _p(x2d), _p(w2d), _p(out), out.stride(0),
@@ -160,14 +160,15 @@ class _Conv3dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2d, w5d, bias, dims, k, s, relu, want_stats=False):
         _require_cuda(x2d, w5d)
-        x2d = _as_rows(x2d)
-        w2d = weight_rows(w5d)
         cout, cin = w5d.shape[0], w5d.shape[1]
         dtype = _DT[_PRECISION["mode"]]
+        # operands in their storage type (bf16 mode: converted once here and kept for backward)
+        xo = _operand(_as_rows(x2d), dtype)
+        wo = _operand(weight_rows(w5d), dtype)
         stats = torch.zeros(2, cout, device=x2d.device, dtype=torch.float32) if want_stats else None
-        y, odims = conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias, relu, stats=stats, dtype=dtype)
-        ctx.save_for_backward(x2d, w5d, y if relu else None)
-        ctx.meta = (dims, odims, k, s, relu, bias is not None, dtype)
+        y, odims = conv_fwd_raw(xo, wo, dims, cin, cout, k, s, bias, relu, stats=stats, dtype=dtype)
+        ctx.save_for_backward(xo, wo, y if relu else None)
+        ctx.meta = (dims, odims, k, s, relu, bias is not None, dtype, cin, cout)
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -175,19 +176,17 @@ class _Conv3dFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats=None):
-        x2d, w5d, y = ctx.saved_tensors
-        dims, odims, k, s, relu, has_bias, dtype = ctx.meta
+        xo, wo, y = ctx.saved_tensors
+        dims, odims, k, s, relu, has_bias, dtype, cin, cout = ctx.meta
         L = _lib.lib()
-        cout, cin = w5d.shape[0], w5d.shape[1]
         if relu:
             dy = dy * (y > 0)
         dy = _as_rows(dy)
         db = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
-        w2d = _operand(weight_rows(w5d), dtype)
+        dyo = _operand(dy, dtype)
         dx = dw = None
         if ctx.needs_input_grad[1]:
             dw2d = torch.zeros(cout, k ** 3 * cin, device=dy.device, dtype=torch.float32)
-            xo, dyo = _operand(x2d, dtype), _operand(dy, dtype)
             d = _conv_desc(dims, cin, cout, k, s, xo.stride(0), dyo.stride(0), dtype)
             flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
             _lib.check(_timed("wgrad", flops, lambda: L.coocc_conv3d_wgrad(ctypes.byref(d), _p(xo), _p(dyo), _p(dw2d),
@@ -198,18 +197,18 @@ class _Conv3dFn(torch.autograd.Function):
             if s != 1:
                 # scatter dy onto the input lattice (even positions), then a stride-1 dgrad
                 X, Y, Z = dims
-                dy_in = torch.empty(X * Y * Z, dy.stride(0), device=dy.device, dtype=torch.float32)
-                _lib.check(L.coocc_dilate2(_p(dy), dy.stride(0), odims[0], odims[1], odims[2], dy.stride(0),
-                                           _p(dy_in), dy_in.stride(0), X, Y, Z, 0, _stream()), "dilate2")
-                dy_in = dy_in[:, :dy.shape[1]]
+                dy_in = torch.empty(X * Y * Z, dyo.stride(0), device=dy.device, dtype=dyo.dtype)
+                _lib.check(L.coocc_dilate2(_p(dyo), dyo.stride(0), odims[0], odims[1], odims[2], dyo.stride(0),
+                                           _p(dy_in), dy_in.stride(0), X, Y, Z, 1 if dtype == DT_BF16 else 0,
+                                           _stream()), "dilate2")
+                dy_in = dy_in[:, :cout]
             else:
-                dy_in = dy
+                dy_in = dyo
             ldo = (cin + 3) // 4 * 4
             dxb = torch.empty(dims[0] * dims[1] * dims[2], ldo, device=dy.device, dtype=torch.float32)
-            dy_in = _operand(dy_in, dtype)
             d = _conv_desc(dims, cin, cout, k, 1, ldo, dy_in.stride(0), dtype)
             flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
-            _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(w2d), _p(dxb),
+            _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(wo), _p(dxb),
                                                                           dxb.stride(0), _stream())), "conv3d_dgrad")
             dx = dxb[:, :cin]
         return dx, dw, db, None, None, None, None, None
@@ -265,6 +264,54 @@ def linear(x2d, weight, bias=None, relu=False):
     """nn.Linear on the tensor cores: a 1x1x1 convolution over `rows` voxels."""
     w5d = weight.reshape(weight.shape[0], weight.shape[1], 1, 1, 1)
     return _Conv3dFn.apply(x2d, w5d, bias, (x2d.shape[0], 1, 1), 1, 1, relu)
+
+
+class _ResizeAddFn(torch.autograd.Function):
+    """out = base (opt.) + wts[:, col] (opt.) * trilinear_resize(src)   on [V,C] rows."""
+
+    @staticmethod
+    def forward(ctx, src, sdims, odims, base, wts, col):
+        L = _lib.lib()
+        src = _as_rows(src)
+        C = src.shape[1]
+        Vo = odims[0] * odims[1] * odims[2]
+        out = torch.empty(Vo, C, device=src.device, dtype=torch.float32)
+        if base is not None:
+            base = _as_rows(base)
+        wptr, ldw = None, 0
+        if wts is not None:
+            wts = wts.contiguous()
+            wptr, ldw = _pb(wts, 4 * col), wts.stride(0)
+        _lib.check(L.coocc_trilinear_fwd(_p(src), src.stride(0), sdims[0], sdims[1], sdims[2], C, _p(base),
+                                         base.stride(0) if base is not None else 0, wptr, ldw, _p(out), C,
+                                         odims[0], odims[1], odims[2], _stream()), "trilinear_fwd")
+        ctx.save_for_backward(src, wts)
+        ctx.meta = (sdims, odims, col, base is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        src, wts = ctx.saved_tensors
+        sdims, odims, col, has_base = ctx.meta
+        dout = _as_rows(dout)
+        C = src.shape[1]
+        dsrc = dwts = None
+        wptr, ldw = (None, 0) if wts is None else (_pb(wts, 4 * col), wts.stride(0))
+        if ctx.needs_input_grad[0]:
+            dsrc = torch.empty(src.shape[0], C, device=src.device, dtype=torch.float32)
+            _lib.check(L.coocc_trilinear_bwd(_p(dout), dout.stride(0), odims[0], odims[1], odims[2], C, wptr, ldw,
+                                             _p(dsrc), C, sdims[0], sdims[1], sdims[2], _stream()), "trilinear_bwd")
+        if wts is not None and ctx.needs_input_grad[4]:
+            dwts = torch.zeros_like(wts)
+            _lib.check(L.coocc_trilinear_wgrad(_p(dout), dout.stride(0), _p(src), src.stride(0), sdims[0], sdims[1],
+                                               sdims[2], odims[0], odims[1], odims[2], C, _pb(dwts, 4 * col),
+                                               dwts.stride(0), _stream()), "trilinear_wgrad")
+        return dsrc, None, None, (dout if has_base else None), dwts, None
+
+
+def resize_add(src, sdims, odims, base=None, wts=None, col=0):
+    return _ResizeAddFn.apply(src, tuple(sdims), tuple(odims), base, wts, col)
 
 
 # ----------------------------------------------------------------------------------------

@@ -214,8 +214,8 @@ class FPN3D(nn.Module):
             y, _ = conv_bn_act(x2d, d, m.conv, m.bn)
             lat.append(y)
             dims.append(d)
-        for i in range(self.num_out - 1, 0, -1):
-            lat[i - 1] = lat[i - 1] + resize_trilinear(lat[i], dims[i], dims[i - 1])
+        for i in range(self.num_out - 1, 0, -1):       # fpn3d.py:91-94, resize fused with the add
+            lat[i - 1] = CF.resize_add(lat[i], dims[i], dims[i - 1], base=lat[i - 1])
         outs = []
         for i in range(self.num_out):
             m = self.fpn_convs[i][0]
@@ -272,9 +272,15 @@ class OccHead(nn.Module):
             w = torch.softmax(w, dim=1)
         else:
             w = torch.full((1, self.num_level), 1.0 / self.num_level, device=occs[0].device)
-        feats = 0
-        for i, f in enumerate(occs):
-            feats = feats + resize_trilinear(f, dims[i], d0) * w[:, i:i + 1]
+        feats = None
+        if self.soft_weights:
+            for i, f in enumerate(occs):               # occ_head.py:161-165, resize * weight + add fused
+                feats = CF.resize_add(f, dims[i], d0, base=feats, wts=w, col=i)
+        else:
+            for i, f in enumerate(occs):
+                r = CF.resize_add(f, dims[i], d0, base=feats)
+                feats = r
+            feats = feats * (1.0 / self.num_level)
         y, _ = conv_bn_act(feats, d0, self.occ_pred_conv[0], self.occ_pred_conv[1])
         occ, _ = conv_bn_act(y, d0, self.occ_pred_conv[3], None, relu=False)
         return {"out_voxel_feats": [CF.to_5d(feats, d0)], "occ": [CF.to_5d(occ, d0)]}

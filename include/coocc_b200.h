@@ -175,6 +175,22 @@ int coocc_bn_act_bwd(const float* dout, long long ldd, const float* out, long lo
 int coocc_dilate2(const void* src, long long lds, int oX, int oY, int oZ, int C, void* dst, long long ldd,
                   int X, int Y, int Z, int is_bf16, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Trilinear resize (align_corners=False, explicit size) on NDHWC rows, fused with the add /
+ * per-voxel weight that follows it (csrc/trilinear.cu).  Replaces F.interpolate at
+ * P/coocc/necks/fpn3d.py:91-94 and P/coocc/dense_heads/occ_head.py:161-165.
+ *   out[v,:] = base[v,:] (optional) + wts[v*ldw] (optional) * interp(src)[v,:]
+ * ------------------------------------------------------------------------------------------ */
+int coocc_trilinear_fwd(const float* src, long long lds, int sX, int sY, int sZ, int C, const float* base,
+                        long long ldb, const float* wts, long long ldw, float* out, long long ldo, int oX,
+                        int oY, int oZ, void* stream);
+/* dsrc = transpose(interp) applied to (wts * dout) */
+int coocc_trilinear_bwd(const float* dout, long long ldd, int oX, int oY, int oZ, int C, const float* wts,
+                        long long ldw, float* dsrc, long long lds, int sX, int sY, int sZ, void* stream);
+/* dw[v*lddw] = sum_c dout[v,c] * interp(src)[v,c] */
+int coocc_trilinear_wgrad(const float* dout, long long ldd, const float* src, long long lds, int sX, int sY,
+                          int sZ, int oX, int oY, int oZ, int C, float* dw, long long lddw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
