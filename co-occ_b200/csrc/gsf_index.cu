@@ -258,14 +258,34 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
   }
   const uint32_t bsmask = (1u << log2bs) - 1u;
 
+  // Each warp owns a *contiguous* chunk of 32*PPT list entries.  The list is sorted by voxel id,
+  // so a chunk is a compact slab of the grid; its bounding box lets the warp skip a round whose new
+  // sample cannot lower any of its running distances (tie keys carry the reference's order, so the
+  // point -> thread mapping is free).
+  const int gw = rank * (kFpsThreads / 32) + warp;
+  const int kbase = gw * (32 * PPT) + lane;
   uint32_t dist[PPT];
-  const int stride = CS * kFpsThreads;
+  int xlo = 1 << 30, ylo = 1 << 30, zlo = 1 << 30, xhi = -1, yhi = -1, zhi = -1;
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
-    const int k = i * stride + rank * kFpsThreads + tid;
-    coords[i * kFpsThreads + tid] = k < n ? pack_xyz(job.list[k], Y, Z) : 0u;
+    const int k = kbase + i * 32;
+    uint32_t c = 0u;
+    if (k < n) {
+      c = pack_xyz(job.list[k], Y, Z);
+      const int x = c & 1023u, y = (c >> 10) & 1023u, z = c >> 20;
+      xlo = min(xlo, x); xhi = max(xhi, x);
+      ylo = min(ylo, y); yhi = max(yhi, y);
+      zlo = min(zlo, z); zhi = max(zhi, z);
+    }
+    coords[i * kFpsThreads + tid] = c;
     dist[i] = kInfDist;
   }
+  xlo = __reduce_min_sync(0xffffffffu, xlo); xhi = __reduce_max_sync(0xffffffffu, xhi);
+  ylo = __reduce_min_sync(0xffffffffu, ylo); yhi = __reduce_max_sync(0xffffffffu, yhi);
+  zlo = __reduce_min_sync(0xffffffffu, zlo); zhi = __reduce_max_sync(0xffffffffu, zhi);
+  const bool warp_has_points = xhi >= 0;
+  uint32_t wd = warp_has_points ? kInfDist : 0u, wt = 0xffffffffu, wc = 0u;   // cached warp best
+
   uint32_t cur = pack_xyz(job.list[0], Y, Z);          // start index 0 (furthest_point_sample.py)
   if (rank == 0 && tid == 0 && m > 0) job.out[0] = 0;
   __syncthreads();
@@ -273,28 +293,38 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
 
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
-    uint32_t bd = 0, bt = 0xffffffffu, bc = 0;
-    bool have = false;
+    bool update = warp_has_points;
+    if (update && wd != kInfDist) {
+      const int px = cur & 1023u, py = (cur >> 10) & 1023u, pz = cur >> 20;
+      const int ddx = max(0, max(xlo - px, px - xhi));
+      const int ddy = max(0, max(ylo - py, py - yhi));
+      const int ddz = max(0, max(zlo - pz, pz - zhi));
+      update = (uint32_t)(ddx * ddx + ddy * ddy + ddz * ddz) < wd;
+    }
+    if (update) {
+      uint32_t bd = 0, bt = 0xffffffffu, bc = 0;
 #pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-      const int k = i * stride + rank * kFpsThreads + tid;
-      if (k < n) {
-        const uint32_t c = coords[i * kFpsThreads + tid];
-        const uint32_t d = min((uint32_t)d2_packed(c, cur), dist[i]);
-        dist[i] = d;
-        const uint32_t t = (__brev((uint32_t)k & bsmask) >> (32 - log2bs) << 22) | ((uint32_t)k >> log2bs);
-        if (!have || d > bd || (d == bd && t < bt)) {
-          bd = d; bt = t; bc = c; have = true;
+      for (int i = 0; i < PPT; ++i) {
+        const int k = kbase + i * 32;
+        if (k < n) {
+          const uint32_t c = coords[i * kFpsThreads + tid];
+          const uint32_t d = min((uint32_t)d2_packed(c, cur), dist[i]);
+          dist[i] = d;
+          const uint32_t t = (__brev((uint32_t)k & bsmask) >> (32 - log2bs) << 22) | ((uint32_t)k >> log2bs);
+          if (d > bd || (d == bd && t < bt)) {
+            bd = d; bt = t; bc = c;
+          }
         }
       }
+      warp_best(bd, bt, bc);
+      wd = bd; wt = bt; wc = bc;
     }
-    if (!have) { bd = 0; bt = 0xffffffffu; }
-    warp_best(bd, bt, bc);
     if (lane == 0) {
-      wbest[par][warp].d = bd; wbest[par][warp].t = bt; wbest[par][warp].c = bc;
+      wbest[par][warp].d = wd; wbest[par][warp].t = wt; wbest[par][warp].c = wc;
     }
     __syncthreads();
     // every warp reduces the per-warp candidates redundantly (no second block barrier)
+    uint32_t bd, bt, bc;
     {
       const bool ok = lane < kFpsThreads / 32;
       bd = ok ? wbest[par][lane].d : 0u;
@@ -552,8 +582,9 @@ extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, con
   if (Y > 1023 || Z > 1023) return COOCC_ERR_CAPACITY;
   const int njobs = list1 ? 2 : 1;
   FpsJob j0{list0, count0, out0}, j1{list1 ? list1 : list0, list1 ? count1 : count0, list1 ? out1 : out0};
+  // few CTAs = cheap per-round cluster barrier; the bounding-box skip keeps per-round compute low
   int cs = 1;
-  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 8) cs *= 2;
+  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 32) cs *= 2;
   const int ppt = (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads);
   cudaStream_t st = (cudaStream_t)stream;
   if (ppt <= 4) return launch_fps<4>(j0, j1, njobs, m, Y, Z, cs, -1, st);
