@@ -236,6 +236,46 @@ struct FpsJob {
   int* out;          // [m] sampled indices into list
 };
 
+// --- one-hop cluster exchange -------------------------------------------------------------
+// Every warp sends its candidate straight into the inbox of every CTA of the cluster with
+// st.async (remote shared-memory store that completes bytes on the *receiver's* mbarrier); a
+// round is then a single wait on the local mbarrier -- no __syncthreads, no barrier.cluster.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remote_mbar, uint32_t a, uint32_t b,
+                                            uint32_t c, uint32_t d) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+          remote_addr),
+      "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_mbar)
+      : "memory");
+}
+__device__ __forceinline__ void fps_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void fps_mbar_arm(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "FPS_WAIT:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra FPS_DONE;\n\t"
+      "bra FPS_WAIT;\n\t"
+      "FPS_DONE:\n\t}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+constexpr int kFpsWarps = kFpsThreads / 32;
+
 template <int PPT>
 __global__ void __launch_bounds__(kFpsThreads, 1)
 fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
@@ -244,10 +284,11 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
   const unsigned rank = cluster.block_rank();
   const FpsJob job = (blockIdx.y == 0) ? job0 : job1;
   const int n = *job.count;
-  extern __shared__ uint32_t coords[];                // [PPT * kFpsThreads]
-  __shared__ FpsCand wbest[2][kFpsThreads / 32];
-  __shared__ FpsCand cbest[2][16];
+  extern __shared__ uint32_t coords[];                          // [PPT * kFpsThreads]
+  __shared__ __align__(16) FpsCand inbox[2][16 * kFpsWarps];    // [parity][sender cta * warps + warp]
+  __shared__ __align__(8) uint64_t mbar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t nmsg = CS * kFpsWarps;                         // messages per round per CTA
 
   // block-size rule of the reference launcher (opt_n_threads): 2^floor(log2 n), capped at 1024
   int log2bs = 0;
@@ -262,7 +303,7 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
   // so a chunk is a compact slab of the grid; its bounding box lets the warp skip a round whose new
   // sample cannot lower any of its running distances (tie keys carry the reference's order, so the
   // point -> thread mapping is free).
-  const int gw = rank * (kFpsThreads / 32) + warp;
+  const int gw = rank * kFpsWarps + warp;
   const int kbase = gw * (32 * PPT) + lane;
   uint32_t dist[PPT];
   int xlo = 1 << 30, ylo = 1 << 30, zlo = 1 << 30, xhi = -1, yhi = -1, zhi = -1;
@@ -287,9 +328,24 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
   uint32_t wd = warp_has_points ? kInfDist : 0u, wt = 0xffffffffu, wc = 0u;   // cached warp best
 
   uint32_t cur = pack_xyz(job.list[0], Y, Z);          // start index 0 (furthest_point_sample.py)
-  if (rank == 0 && tid == 0 && m > 0) job.out[0] = 0;
+  if (tid == 0) {
+    if (rank == 0 && m > 0) job.out[0] = 0;
+    fps_mbar_init(&mbar[0], 1);
+    fps_mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fps_mbar_arm(&mbar[1], nmsg * 16);                 // round 1
+    fps_mbar_arm(&mbar[0], nmsg * 16);                 // round 2
+  }
+  // remote addresses of this warp's inbox slot / mbarrier in the CTA `lane` of the cluster
+  uint32_t r_slot[2] = {0, 0}, r_bar[2] = {0, 0};
+  if (lane < CS) {
+    for (int p2 = 0; p2 < 2; ++p2) {
+      r_slot[p2] = mapa_u32((uint32_t)__cvta_generic_to_shared(&inbox[p2][rank * kFpsWarps + warp]), lane);
+      r_bar[p2] = mapa_u32((uint32_t)__cvta_generic_to_shared(&mbar[p2]), lane);
+    }
+  }
   __syncthreads();
-  if (CS > 1) cluster.sync();
+  cluster.sync();
 
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
@@ -319,38 +375,28 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
       warp_best(bd, bt, bc);
       wd = bd; wt = bt; wc = bc;
     }
-    if (lane == 0) {
-      wbest[par][warp].d = wd; wbest[par][warp].t = wt; wbest[par][warp].c = wc;
+    // lane i -> CTA i: this warp's candidate, completing 16 bytes on the receiver's mbarrier
+    if (lane < CS) st_async_v4(r_slot[par], r_bar[par], wd, wt, wc, 0u);
+    // the (j >> 1) & 1 parity of the round's mbarrier: mbar[par] is used every second round
+    fps_mbar_wait(&mbar[par], ((j - 1) >> 1) & 1);
+    uint32_t bd = 0u, bt = 0xffffffffu, bc = 0u;
+    for (uint32_t e = lane; e < nmsg; e += 32) {
+      const FpsCand cnd = inbox[par][e];
+      if (cnd.d > bd || (cnd.d == bd && cnd.t < bt)) { bd = cnd.d; bt = cnd.t; bc = cnd.c; }
     }
-    __syncthreads();
-    // every warp reduces the per-warp candidates redundantly (no second block barrier)
-    uint32_t bd, bt, bc;
-    {
-      const bool ok = lane < kFpsThreads / 32;
-      bd = ok ? wbest[par][lane].d : 0u;
-      bt = ok ? wbest[par][lane].t : 0xffffffffu;
-      bc = ok ? wbest[par][lane].c : 0u;
-      warp_best(bd, bt, bc);
-    }
-    if (CS > 1) {
-      if (warp == 0 && lane < CS) {
-        FpsCand* remote = cluster.map_shared_rank(&cbest[par][rank], lane);
-        remote->d = bd; remote->t = bt; remote->c = bc;
-      }
-      cluster.sync();
-      const bool ok = lane < CS;
-      bd = ok ? cbest[par][lane].d : 0u;
-      bt = ok ? cbest[par][lane].t : 0xffffffffu;
-      bc = ok ? cbest[par][lane].c : 0u;
-      warp_best(bd, bt, bc);
-    }
+    warp_best(bd, bt, bc);
     cur = bc;
-    if (rank == 0 && tid == 0) {
-      const uint32_t kmod = __brev(bt >> 22) >> (32 - log2bs);
-      job.out[j] = (int)(((bt & 0x3fffffu) << log2bs) | kmod);
+    // all warps of this CTA must have read inbox[par] before it is re-armed for round j + 2
+    __syncthreads();
+    if (tid == 0) {
+      if (j + 2 < m) fps_mbar_arm(&mbar[par], nmsg * 16);
+      if (rank == 0) {
+        const uint32_t kmod = __brev(bt >> 22) >> (32 - log2bs);
+        job.out[j] = (int)(((bt & 0x3fffffu) << log2bs) | kmod);
+      }
     }
   }
-  if (CS > 1) cluster.sync();
+  cluster.sync();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -584,7 +630,7 @@ extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, con
   FpsJob j0{list0, count0, out0}, j1{list1 ? list1 : list0, list1 ? count1 : count0, list1 ? out1 : out0};
   // few CTAs = cheap per-round cluster barrier; the bounding-box skip keeps per-round compute low
   int cs = 1;
-  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 32) cs *= 2;
+  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 8) cs *= 2;
   const int ppt = (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads);
   cudaStream_t st = (cudaStream_t)stream;
   if (ppt <= 4) return launch_fps<4>(j0, j1, njobs, m, Y, Z, cs, -1, st);
