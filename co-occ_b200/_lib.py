@@ -44,6 +44,7 @@ _SIGS = {
     "coocc_gsf_compact_workspace": (c_ll, [c_int]),
     "coocc_gsf_compact": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "coocc_gsf_fps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "coocc_gsf_fps_tune": (c_int, [c_int, c_int]),
     "coocc_gsf_rep_topk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "coocc_gsf_ball_assign": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "coocc_gsf_direct_nn": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

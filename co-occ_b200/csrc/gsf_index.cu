@@ -278,7 +278,7 @@ constexpr int kFpsWarps = kFpsThreads / 32;
 
 template <int PPT>
 __global__ void __launch_bounds__(kFpsThreads, 1)
-fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
+fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, int flags) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned CS = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
@@ -378,7 +378,12 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
     // lane i -> CTA i: this warp's candidate, completing 16 bytes on the receiver's mbarrier
     if (lane < CS) st_async_v4(r_slot[par], r_bar[par], wd, wt, wc, 0u);
     // the (j >> 1) & 1 parity of the round's mbarrier: mbar[par] is used every second round
-    fps_mbar_wait(&mbar[par], ((j - 1) >> 1) & 1);
+    if (flags & 1) {
+      if (lane == 0) fps_mbar_wait(&mbar[par], ((j - 1) >> 1) & 1);     // one poller per warp
+      __syncwarp();
+    } else {
+      fps_mbar_wait(&mbar[par], ((j - 1) >> 1) & 1);
+    }
     uint32_t bd = 0u, bt = 0xffffffffu, bc = 0u;
     for (uint32_t e = lane; e < nmsg; e += 32) {
       const FpsCand cnd = inbox[par][e];
@@ -386,8 +391,12 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override) {
     }
     warp_best(bd, bt, bc);
     cur = bc;
-    // all warps of this CTA must have read inbox[par] before it is re-armed for round j + 2
-    __syncthreads();
+    // No block barrier: inbox[par] is only overwritten by round j+2 messages, and a sender can reach
+    // round j+2 only after it received *every* warp's round j+1 message, which each warp of this CTA
+    // sends after the reads above (program order).  Re-arming for round j+2 happens here, before this
+    // thread's own round j+1 message, hence before any round j+2 byte can arrive; slower local warps
+    // still waiting on the completed phase are unaffected (parity wait).
+    if (!(flags & 2)) __syncthreads();
     if (tid == 0) {
       if (j + 2 < m) fps_mbar_arm(&mbar[par], nmsg * 16);
       if (rank == 0) {
@@ -591,6 +600,8 @@ extern "C" int coocc_gsf_compact(const unsigned char* flags, int V, int* list, i
   return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
 }
 
+static int g_fps_cs = 0, g_fps_flags = 2;   // flags 2: all-lane poll, no block barrier (fastest measured)
+
 template <int PPT>
 static int launch_fps(FpsJob j0, FpsJob j1, int njobs, int m, int Y, int Z, int cs, int log2bs,
                       cudaStream_t st) {
@@ -614,7 +625,7 @@ static int launch_fps(FpsJob j0, FpsJob j1, int njobs, int m, int Y, int Z, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, fps_kernel<PPT>, j0, j1, m, Y, Z, log2bs);
+  e = cudaLaunchKernelEx(&cfg, fps_kernel<PPT>, j0, j1, m, Y, Z, log2bs, g_fps_flags);
   return e == cudaSuccess ? 0 : COOCC_ERR_CUDA;
 }
 
@@ -631,6 +642,7 @@ extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, con
   // few CTAs = cheap per-round cluster barrier; the bounding-box skip keeps per-round compute low
   int cs = 1;
   while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 8) cs *= 2;
+  if (g_fps_cs > 0) cs = g_fps_cs;
   const int ppt = (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads);
   cudaStream_t st = (cudaStream_t)stream;
   if (ppt <= 4) return launch_fps<4>(j0, j1, njobs, m, Y, Z, cs, -1, st);
@@ -639,6 +651,13 @@ extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, con
   if (ppt <= 32) return launch_fps<32>(j0, j1, njobs, m, Y, Z, cs, -1, st);
   if (ppt <= 64) return launch_fps<64>(j0, j1, njobs, m, Y, Z, cs, -1, st);
   return COOCC_ERR_CAPACITY;
+}
+
+// tuning hook (benchmarks only): force the cluster size (0 = automatic) and exchange variant flags
+extern "C" int coocc_gsf_fps_tune(int cluster_size, int flags) {
+  g_fps_cs = cluster_size;
+  g_fps_flags = flags;
+  return 0;
 }
 
 extern "C" int coocc_gsf_rep_topk(const int* rep_idx, int nrep, const int* qlist, const int* key_rank,

@@ -88,6 +88,8 @@ int coocc_gsf_compact(const unsigned char* flags, int V, int* list, int* rank, i
  * (list1 may be NULL); n_max bounds both counts.  out[j] = position in list. */
 int coocc_gsf_fps(const int* list0, const int* count0, int* out0, const int* list1, const int* count1,
                   int* out1, int n_max, int m, int Y, int Z, void* stream);
+/* benchmark hook: force the FPS cluster size (0 = automatic) and exchange-variant flags */
+int coocc_gsf_fps_tune(int cluster_size, int flags);
 /* K nearest keys (d2 <= 176 <=> dist < 13.3) of each representative, order (d2 asc, key asc);
  * out_idx = position in the key list or -1, out_d2 = squared distance or -1. */
 int coocc_gsf_rep_topk(const int* rep_idx, int nrep, const int* qlist, const int* key_rank, int X, int Y,
