@@ -37,14 +37,14 @@ def get_precision():
 PROFILE = None     # bench.py sets this to a list to time every conv launch with CUDA events
 
 
-def _timed(tag, flops, fn):
+def _timed(tag, flops, fn, info=""):
     if PROFILE is None:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = fn()
     e1.record()
-    PROFILE.append((e0, e1, flops, tag))
+    PROFILE.append((e0, e1, flops, tag + info))
     return rc
 
 
@@ -149,7 +149,8 @@ def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=N
     d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), (cout + 7) // 8 * 8, dtype)
     flops = 2.0 * vo * (k ** 3) * cin * cout
     rc = _timed("fwd", flops, lambda: L.coocc_conv3d_fwd(ctypes.byref(d), _p(x2d), _p(w2d), _p(out), out.stride(0),
-                                                         _p(bias), 1 if relu else 0, _p(stats), _stream()))
+                                                         _p(bias), 1 if relu else 0, _p(stats), _stream()),
+                " %s %d->%d k%d s%d" % (dims, cin, cout, k, s))
     _lib.check(rc, "conv3d_fwd")
     return out[:, :cout], odims
 
@@ -190,7 +191,8 @@ class _Conv3dFn(torch.autograd.Function):
             d = _conv_desc(dims, cin, cout, k, s, xo.stride(0), dyo.stride(0), dtype)
             flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
             _lib.check(_timed("wgrad", flops, lambda: L.coocc_conv3d_wgrad(ctypes.byref(d), _p(xo), _p(dyo), _p(dw2d),
-                                                                          _stream())), "conv3d_wgrad")
+                                                                          _stream()),
+                              " %s %d->%d k%d s%d" % (dims, cin, cout, k, s)), "conv3d_wgrad")
             # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
             dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
         if ctx.needs_input_grad[0]:
@@ -209,7 +211,8 @@ class _Conv3dFn(torch.autograd.Function):
             d = _conv_desc(dims, cin, cout, k, 1, ldo, dy_in.stride(0), dtype)
             flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
             _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(wo), _p(dxb),
-                                                                          dxb.stride(0), _stream())), "conv3d_dgrad")
+                                                                          dxb.stride(0), _stream()),
+                              " %s %d->%d k%d s%d" % (dims, cin, cout, k, s)), "conv3d_dgrad")
             dx = dxb[:, :cin]
         return dx, dw, db, None, None, None, None, None
 

@@ -29,10 +29,12 @@ NC = dict(type="SyncBN", requires_grad=True)
 TOL = {
     "fp32": dict(fused=1e-3, fused_grad=1e-2, occ=1e-3, stack_grad=2e-2, render=1e-3, render_grad=1e-2),
     "tf32": dict(fused=3e-3, fused_grad=3e-1, occ=2e-2, stack_grad=5e-1, render=2e-3, render_grad=5e-1),
+    # bf16 operands (8-bit mantissa), fp32 accumulation: per-layer ~3e-3, reported separately
+    "bf16": dict(fused=2e-2, fused_grad=8e-1, occ=1e-1, stack_grad=1.0, render=2e-2, render_grad=1.0),
 }
 
 
-@pytest.fixture(params=["fp32", "tf32"])
+@pytest.fixture(params=["fp32", "tf32", "bf16"])
 def precision(request):
     old = coocc_b200.get_precision()
     coocc_b200.set_precision(request.param)
@@ -241,7 +243,7 @@ def test_conv3d_op_forward_backward(case, precision):
     torch.cuda.synchronize()
     e = dict(y=rel_err(y, yr), dx=rel_err(x.grad, xr.grad), dw=rel_err(w.grad, wr.grad))
     _report("conv%s[%s]" % (str(case), precision), **e)
-    bound = 2e-5 if precision == "fp32" else 2e-3
+    bound = {"fp32": 2e-5, "tf32": 2e-3, "bf16": 2e-2}[precision]
     assert max(e.values()) < bound
 
 
@@ -287,7 +289,7 @@ def test_conv_bn_relu_fused(res, precision):
     if res:
         e["dres"] = rel_l2(r.grad, rr.grad)
     _report("conv_bn_relu[res=%s,%s]" % (res, precision), **e)
-    fwd_b, bwd_b = (2e-5, 2e-3) if precision == "fp32" else (3e-3, 5e-2)
+    fwd_b, bwd_b = {"fp32": (2e-5, 2e-3), "tf32": (3e-3, 5e-2), "bf16": (3e-2, 3e-1)}[precision]
     assert e["y"] < fwd_b and e["rmean"] < fwd_b and e["rvar"] < fwd_b
     assert max(v for k, v in e.items() if k.startswith("d")) < bwd_b
     assert int(bn_g.num_batches_tracked) == 1

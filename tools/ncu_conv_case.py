@@ -1,0 +1,22 @@
+"""Small driver for `ncu --set full`: a few launches of the dominant kernel on real layer shapes."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import coocc_b200
+from coocc_b200 import _lib
+L = _lib.lib(); dev = "cuda"
+st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+dtype = 1  # bf16
+for (X, Y, Z, Cin, Cout) in ((200, 200, 16, 512, 256), (200, 200, 16, 128, 128)):
+    xc = torch.randn(X * Y * Z, Cin, device=dev).to(torch.bfloat16)
+    wc = (torch.randn(Cout, 27 * Cin, device=dev) * 0.01).to(torch.bfloat16)
+    gy = torch.randn(X * Y * Z, Cout, device=dev).to(torch.bfloat16)
+    y = torch.empty(X * Y * Z, Cout, device=dev); dx = torch.empty(X * Y * Z, Cin, device=dev)
+    dw = torch.zeros(Cout, 27 * Cin, device=dev); stats = torch.zeros(2, Cout, device=dev)
+    d = _lib.ConvDesc(X, Y, Z, Cin, Cout, 3, 1, dtype, Cin, Cout)
+    for _ in range(2):
+        L.coocc_conv3d_fwd(ctypes.byref(d), xc.data_ptr(), wc.data_ptr(), y.data_ptr(), Cout, None, 0, stats.data_ptr(), st())
+        L.coocc_conv3d_dgrad(ctypes.byref(d), gy.data_ptr(), wc.data_ptr(), dx.data_ptr(), Cin, st())
+        L.coocc_conv3d_wgrad(ctypes.byref(d), xc.data_ptr(), gy.data_ptr(), dw.data_ptr(), st())
+    torch.cuda.synchronize()
+print("done")
