@@ -50,6 +50,7 @@ struct TcParams {
   int mode;
   int M, N;            // output rows / cols (fprop: V_out, Cout; dgrad: V, Cin; wgrad: Cout, Cin)
   int BN;              // N tile (multiple of 16, <= 256)
+  int MT;              // 128-row MMA tiles per CTA tile (2 when BN <= 128: same bytes/MAC as 128x256)
   int taps;            // 1 or 27
   int Kc;              // reduction channels per tap (fprop: Cin, dgrad: Cout); wgrad: unused
   int a_im2col;        // A (fprop/dgrad) or B (wgrad) loaded through im2col
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   // ---- tile bookkeeping (identical in every role) ---------------------------------------
   const int ntn = (p.N + p.BN - 1) / p.BN;
-  const int ntm = (p.M + kBM - 1) / kBM;
+  const int ntm = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
   const int ntiles = wgrad ? ntm * ntn * p.taps * p.ksplit : ntm * ntn * p.ksplit;
   const int kb_per_tap = (p.Kc + E::BKE - 1) / E::BKE;
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t a_bytes = kABytes;
+  const uint32_t a_bytes = kABytes * (uint32_t)p.MT;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
 
   if (warp == 0) {
@@ -176,17 +177,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * kStageBytes;
-            uint8_t* sb = sa + kABytes;
+            uint8_t* sb = sa + a_bytes;
             mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
             if (!wgrad) {
-              // ---- A: [128 pixels x BKE channels], K-major
-              if (p.a_im2col) {
-                int w, h, d;
-                pixel_to_whd(p, mt * kBM, w, h, d);
-                tma_load_im2col_5d(sa, &p.tmA, &full_bar[stage], kb * E::BKE, w, h, d, 0,
-                                   (uint16_t)kz, (uint16_t)ky, (uint16_t)kx);
-              } else {
-                tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * E::BKE, mt * kBM);
+              // ---- A: MT x [128 pixels x BKE channels], K-major
+              for (int hh = 0; hh < p.MT; ++hh) {
+                const int pix = (mt * p.MT + hh) * kBM;
+                if (p.a_im2col) {
+                  int w, h, d;
+                  pixel_to_whd(p, pix, w, h, d);
+                  tma_load_im2col_5d(sa + hh * kABytes, &p.tmA, &full_bar[stage], kb * E::BKE, w, h, d, 0,
+                                     (uint16_t)kz, (uint16_t)ky, (uint16_t)kx);
+                } else {
+                  tma_load_2d(sa + hh * kABytes, &p.tmA, &full_bar[stage], kb * E::BKE, pix);
+                }
               }
               // ---- B
               if (!b_mn) {   // weights rows, K-major: box {BKE, BN}
@@ -243,14 +247,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sb = sa + a_bytes;
+          for (int hh = 0; hh < p.MT; ++hh) {
+            const uint32_t sah = sa + hh * kABytes;
 #pragma unroll
-          for (int j = 0; j < E::NUK; ++j) {
-            const uint64_t ad = a_mn ? make_smem_desc(sa + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
-                                     : make_smem_desc(sa + j * 32, 16, 1024, 2);
-            const uint64_t bd = b_mn ? make_smem_desc(sb + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
-                                     : make_smem_desc(sb + j * 32, 16, 1024, 2);
-            umma<E::TF32>(d_tmem, ad, bd, idesc, (k | j) ? 1u : 0u);
+            for (int j = 0; j < E::NUK; ++j) {
+              const uint64_t ad = a_mn ? make_smem_desc(sah + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
+                                       : make_smem_desc(sah + j * 32, 16, 1024, 2);
+              const uint64_t bd = b_mn ? make_smem_desc(sb + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
+                                       : make_smem_desc(sb + j * 32, 16, 1024, 2);
+              umma<E::TF32>(d_tmem + (uint32_t)(hh * p.BN), ad, bd, idesc, (k | j) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -287,9 +294,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = mt * kBM + q * 32 + lane;
+      for (int hh = 0; hh < p.MT; ++hh) {
+      const int row = (mt * p.MT + hh) * kBM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(hh * p.BN) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         if (nk > 0) {
@@ -413,6 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
               if (col0 + i < p.N) atomicAdd(o + i, __uint_as_float(v[i]));
           }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -571,7 +580,10 @@ static int pick_ksplit(int ntiles, int nk_total) {
 }
 
 static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
-  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN);
+  // two 128-row MMA tiles per CTA when the N tile is narrow and there is enough work to fill the GPU
+  p.MT = 1;
+  if (p.BN <= 128 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + p.BN - 1) / p.BN) >= g_num_sms) p.MT = 2;
+  const int ntiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN);
   p.ksplit = 1;
   if (p.bias == nullptr && !p.relu) p.ksplit = pick_ksplit(ntiles, nk_total);
   if (p.ksplit > 1 && !p.accum) {
@@ -648,7 +660,7 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
   float* stats_after = nullptr;
   if ((rc = prepare_split(p, taps * ((d->Cin + bke - 1) / bke), (cudaStream_t)stream))) return rc;
   if (p.ksplit > 1 && p.stats) { stats_after = p.stats; p.stats = nullptr; }
-  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
+  const int ntiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
   rc = es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
   if (!rc && stats_after) {
     dim3 grid((p.N + 31) / 32, p.M >= 4096 ? 64 : (p.M + 63) / 64);
@@ -702,7 +714,7 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, f
   rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, ch, ch, true);
   if (rc) return rc;
   if ((rc = prepare_split(p, taps * ((d->Cout + ch - 1) / ch), (cudaStream_t)stream))) return rc;
-  const int ntiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
+  const int ntiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
   return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
 }
 
@@ -720,6 +732,7 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.mode = MODE_WGRAD;
+  p.MT = 1;
   p.M = d->Cout;
   p.N = d->Cin;
   p.BN = ((d->Cin + ch - 1) / ch) * ch;

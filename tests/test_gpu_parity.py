@@ -217,6 +217,7 @@ CONV_CASES = [
     # X, Y, Z, Cin, Cout, k, stride
     (12, 10, 4, 32, 32, 1, 1), (12, 10, 4, 64, 40, 3, 1), (13, 11, 4, 32, 64, 3, 2), (13, 13, 1, 64, 128, 3, 2),
     (12, 10, 4, 64, 96, 1, 2), (10, 10, 8, 128, 17, 1, 1), (9, 9, 2, 256, 3, 1, 1), (25, 25, 2, 96, 32, 3, 1),
+    (64, 60, 10, 32, 64, 3, 1),      # > 148 double tiles: exercises the 256-row CTA tile (MT = 2) and its ragged tail
 ]
 
 
