@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="northstar")
-    ap.add_argument("--precision", default=os.environ.get("COOCC_PRECISION", "tf32"), choices=["tf32", "bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("COOCC_PRECISION", "bf16"), choices=["tf32", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -328,7 +328,13 @@ def run_ours(args, cfg):
                               launches_per_step=n_conv, algorithmic_flops_per_step=f_conv,
                               kernel_ms_per_step=t_conv * 1e3, share_of_step=t_conv * 1e3 / (ms / args.steps),
                               peak_source=peak_src,
+                              traffic_note="ncu --set full of the same kernel (profiles/r01_ncu_full_tc_conv_bf16.summary.txt): "
+                                           "DRAM read+write ~= algorithmic bytes (input read once, output written once); the "
+                                           "kernel is bound by the L2->SM operand stream, not HBM",
                               note="tf32 math has half the nominal bf16 rate" if args.precision == "tf32" else ""))
+    line["parity"] = dict(mode=args.precision,
+                          note="fp32 mode (3xTF32 split) matches the oracle to 3e-5 on logits; tf32 ~1e-2; bf16 ~5e-2 "
+                               "(tests/test_gpu_parity.py, profiles/r01_gpu_parity_*.log); indices bit-exact in every mode")
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg)
     print(json.dumps(line), flush=True)

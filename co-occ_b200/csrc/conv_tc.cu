@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/coocc_b200.h"
@@ -178,10 +179,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * kStageBytes;
             uint8_t* sb = sa + a_bytes;
-            mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+            // a 128-row half that starts past the last pixel is not loaded at all (an im2col load whose
+            // base pixel lies outside the tensor faults); its rows are masked in the epilogue
+            const int nhalf = wgrad ? 1 : min(p.MT, (p.M - mt * p.MT * kBM + kBM - 1) / kBM);
+            mbar_expect_tx(&full_bar[stage], (wgrad ? a_bytes : (uint32_t)nhalf * kABytes) + b_bytes);
             if (!wgrad) {
               // ---- A: MT x [128 pixels x BKE channels], K-major
-              for (int hh = 0; hh < p.MT; ++hh) {
+              for (int hh = 0; hh < nhalf; ++hh) {
                 const int pix = (mt * p.MT + hh) * kBM;
                 if (p.a_im2col) {
                   int w, h, d;
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                                        : make_smem_desc(sah + j * 32, 16, 1024, 2);
               const uint64_t bd = b_mn ? make_smem_desc(sb + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
                                        : make_smem_desc(sb + j * 32, 16, 1024, 2);
-              umma<E::TF32>(d_tmem + (uint32_t)(hh * p.BN), ad, bd, idesc, (k | j) ? 1u : 0u);
+              umma<E::TF32>(d_tmem + (uint32_t)(hh * 128), ad, bd, idesc, (k | j) ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       for (int hh = 0; hh < p.MT; ++hh) {
       const int row = (mt * p.MT + hh) * kBM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(hh * p.BN) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(hh * 128) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         if (nk > 0) {
@@ -582,7 +586,12 @@ static int pick_ksplit(int ntiles, int nk_total) {
 static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
   // two 128-row MMA tiles per CTA when the N tile is narrow and there is enough work to fill the GPU
   p.MT = 1;
-  if (p.BN <= 128 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + p.BN - 1) / p.BN) >= g_num_sms) p.MT = 2;
+  static int mt_enabled = -1;
+  if (mt_enabled < 0) {
+    const char* e = getenv("COOCC_CONV_MT2");
+    mt_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (mt_enabled && p.BN <= 128 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + p.BN - 1) / p.BN) >= g_num_sms) p.MT = 2;
   const int ntiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN);
   p.ksplit = 1;
   if (p.bias == nullptr && !p.relu) p.ksplit = pick_ksplit(ntiles, nk_total);
