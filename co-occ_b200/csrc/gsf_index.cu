@@ -276,19 +276,35 @@ __device__ __forceinline__ void fps_mbar_wait(uint64_t* bar, uint32_t parity) {
 
 constexpr int kFpsWarps = kFpsThreads / 32;
 
-template <int PPT>
+// Points are dealt to the warps of a CTA in groups ("slots") of 32 consecutive list entries, round
+// robin: slot s of warp w holds entries base + (s*16 + w)*32 + lane.  The list is sorted by voxel id,
+// so a slot is a short run of a grid row with a tight bounding box.  Per round a warp
+//   1. tests the new sample against the bounding box of each of its slots (lane-parallel),
+//   2. updates only the slots the sample can reach (one point per lane) and refreshes their cached
+//      maxima,
+//   3. reduces its slot maxima to the warp candidate and sends it to every CTA (one hop).
+// A sample only reaches slots within sqrt(current max-min distance), so after the first rounds a
+// warp touches 0-2 slots per round however many points it owns: the round latency no longer grows
+// with N.  Running distances and coordinates live in shared memory.
 __global__ void __launch_bounds__(kFpsThreads, 1)
-fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, int flags) {
+fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, int S) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned CS = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
   const FpsJob job = (blockIdx.y == 0) ? job0 : job1;
   const int n = *job.count;
-  extern __shared__ uint32_t coords[];                          // [PPT * kFpsThreads]
+  extern __shared__ uint32_t dyn[];
+  uint32_t* dist = dyn;                                  // [S * 512]
+  uint32_t* coords = dist + (size_t)S * kFpsThreads;     // [S * 512]
+  uint32_t* blo = coords + (size_t)S * kFpsThreads;      // [16][S] slot bounding box (packed min)
+  uint32_t* bhi = blo + kFpsWarps * S;                   // [16][S] packed max
+  uint32_t* sd = bhi + kFpsWarps * S;                    // [16][S] slot best distance
+  uint32_t* stie = sd + kFpsWarps * S;                   // [16][S] slot best tie key
+  uint32_t* sc = stie + kFpsWarps * S;                   // [16][S] slot best coordinate
   __shared__ __align__(16) FpsCand inbox[2][16 * kFpsWarps];    // [parity][sender cta * warps + warp]
   __shared__ __align__(8) uint64_t mbar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t nmsg = CS * kFpsWarps;                         // messages per round per CTA
+  const uint32_t nmsg = CS * kFpsWarps;
 
   // block-size rule of the reference launcher (opt_n_threads): 2^floor(log2 n), capped at 1024
   int log2bs = 0;
@@ -298,45 +314,42 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
     while ((2 << log2bs) <= n && log2bs < 10) ++log2bs;
   }
   const uint32_t bsmask = (1u << log2bs) - 1u;
+  const int cta_base = rank * (S * kFpsThreads);
 
-  // Each warp owns a *contiguous* chunk of 32*PPT list entries.  The list is sorted by voxel id,
-  // so a chunk is a compact slab of the grid; its bounding box lets the warp skip a round whose new
-  // sample cannot lower any of its running distances (tie keys carry the reference's order, so the
-  // point -> thread mapping is free).
-  const int gw = rank * kFpsWarps + warp;
-  const int kbase = gw * (32 * PPT) + lane;
-  uint32_t dist[PPT];
-  int xlo = 1 << 30, ylo = 1 << 30, zlo = 1 << 30, xhi = -1, yhi = -1, zhi = -1;
-#pragma unroll
-  for (int i = 0; i < PPT; ++i) {
-    const int k = kbase + i * 32;
+  // ---- load points, build slot bounding boxes ---------------------------------------------
+  for (int sl = 0; sl < S; ++sl) {
+    const int k = cta_base + (sl * kFpsWarps + warp) * 32 + lane;
     uint32_t c = 0u;
+    int xl = 1 << 20, yl = 1 << 20, zl = 1 << 20, xh = -1, yh = -1, zh = -1;
     if (k < n) {
       c = pack_xyz(job.list[k], Y, Z);
-      const int x = c & 1023u, y = (c >> 10) & 1023u, z = c >> 20;
-      xlo = min(xlo, x); xhi = max(xhi, x);
-      ylo = min(ylo, y); yhi = max(yhi, y);
-      zlo = min(zlo, z); zhi = max(zhi, z);
+      xl = xh = c & 1023u; yl = yh = (c >> 10) & 1023u; zl = zh = c >> 20;
     }
-    coords[i * kFpsThreads + tid] = c;
-    dist[i] = kInfDist;
+    coords[sl * kFpsThreads + tid] = c;
+    dist[sl * kFpsThreads + tid] = kInfDist;
+    xl = __reduce_min_sync(0xffffffffu, xl); xh = __reduce_max_sync(0xffffffffu, xh);
+    yl = __reduce_min_sync(0xffffffffu, yl); yh = __reduce_max_sync(0xffffffffu, yh);
+    zl = __reduce_min_sync(0xffffffffu, zl); zh = __reduce_max_sync(0xffffffffu, zh);
+    if (lane == 0) {
+      const bool has = xh >= 0;
+      blo[warp * S + sl] = has ? ((uint32_t)xl | ((uint32_t)yl << 10) | ((uint32_t)zl << 20)) : 0xffffffffu;
+      bhi[warp * S + sl] = has ? ((uint32_t)xh | ((uint32_t)yh << 10) | ((uint32_t)zh << 20)) : 0u;
+      sd[warp * S + sl] = has ? kInfDist : 0u;          // INF forces the first update
+      stie[warp * S + sl] = 0xffffffffu;
+      sc[warp * S + sl] = 0u;
+    }
   }
-  xlo = __reduce_min_sync(0xffffffffu, xlo); xhi = __reduce_max_sync(0xffffffffu, xhi);
-  ylo = __reduce_min_sync(0xffffffffu, ylo); yhi = __reduce_max_sync(0xffffffffu, yhi);
-  zlo = __reduce_min_sync(0xffffffffu, zlo); zhi = __reduce_max_sync(0xffffffffu, zhi);
-  const bool warp_has_points = xhi >= 0;
-  uint32_t wd = warp_has_points ? kInfDist : 0u, wt = 0xffffffffu, wc = 0u;   // cached warp best
+  uint32_t wd = 0u, wt = 0xffffffffu, wc = 0u;           // cached warp candidate
 
-  uint32_t cur = pack_xyz(job.list[0], Y, Z);          // start index 0 (furthest_point_sample.py)
+  uint32_t cur = pack_xyz(job.list[0], Y, Z);            // start index 0 (furthest_point_sample.py)
   if (tid == 0) {
     if (rank == 0 && m > 0) job.out[0] = 0;
     fps_mbar_init(&mbar[0], 1);
     fps_mbar_init(&mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    fps_mbar_arm(&mbar[1], nmsg * 16);                 // round 1
-    fps_mbar_arm(&mbar[0], nmsg * 16);                 // round 2
+    fps_mbar_arm(&mbar[1], nmsg * 16);                   // round 1
+    fps_mbar_arm(&mbar[0], nmsg * 16);                   // round 2
   }
-  // remote addresses of this warp's inbox slot / mbarrier in the CTA `lane` of the cluster
   uint32_t r_slot[2] = {0, 0}, r_bar[2] = {0, 0};
   if (lane < CS) {
     for (int p2 = 0; p2 < 2; ++p2) {
@@ -349,41 +362,57 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
 
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
-    bool update = warp_has_points;
-    if (update && wd != kInfDist) {
-      const int px = cur & 1023u, py = (cur >> 10) & 1023u, pz = cur >> 20;
-      const int ddx = max(0, max(xlo - px, px - xhi));
-      const int ddy = max(0, max(ylo - py, py - yhi));
-      const int ddz = max(0, max(zlo - pz, pz - zhi));
-      update = (uint32_t)(ddx * ddx + ddy * ddy + ddz * ddz) < wd;
-    }
-    if (update) {
-      uint32_t bd = 0, bt = 0xffffffffu, bc = 0;
-#pragma unroll
-      for (int i = 0; i < PPT; ++i) {
-        const int k = kbase + i * 32;
-        if (k < n) {
-          const uint32_t c = coords[i * kFpsThreads + tid];
-          const uint32_t d = min((uint32_t)d2_packed(c, cur), dist[i]);
-          dist[i] = d;
-          const uint32_t t = (__brev((uint32_t)k & bsmask) >> (32 - log2bs) << 22) | ((uint32_t)k >> log2bs);
-          if (d > bd || (d == bd && t < bt)) {
-            bd = d; bt = t; bc = c;
-          }
+    const int px = cur & 1023u, py = (cur >> 10) & 1023u, pz = cur >> 20;
+    bool changed = false;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      // 1. which of this warp's slots can the new sample reach?
+      const int sl = s0 + lane;
+      bool need = false;
+      if (sl < S) {
+        const uint32_t lo = blo[warp * S + sl], hi = bhi[warp * S + sl];
+        if (lo != 0xffffffffu) {
+          const int ddx = max(0, max((int)(lo & 1023u) - px, px - (int)(hi & 1023u)));
+          const int ddy = max(0, max((int)((lo >> 10) & 1023u) - py, py - (int)((hi >> 10) & 1023u)));
+          const int ddz = max(0, max((int)(lo >> 20) - pz, pz - (int)(hi >> 20)));
+          need = (uint32_t)(ddx * ddx + ddy * ddy + ddz * ddz) < sd[warp * S + sl];
         }
+      }
+      uint32_t todo = __ballot_sync(0xffffffffu, need);
+      // 2. update those slots, one point per lane
+      while (todo) {
+        const int u = s0 + __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int k = cta_base + (u * kFpsWarps + warp) * 32 + lane;
+        uint32_t bd = 0u, bt = 0xffffffffu, bc = 0u;
+        if (k < n) {
+          const uint32_t c = coords[u * kFpsThreads + tid];
+          const uint32_t d = min((uint32_t)d2_packed(c, cur), dist[u * kFpsThreads + tid]);
+          dist[u * kFpsThreads + tid] = d;
+          bd = d;
+          bt = (__brev((uint32_t)k & bsmask) >> (32 - log2bs) << 22) | ((uint32_t)k >> log2bs);
+          bc = c;
+        }
+        warp_best(bd, bt, bc);
+        if (lane == 0) {
+          sd[warp * S + u] = bd; stie[warp * S + u] = bt; sc[warp * S + u] = bc;
+        }
+        changed = true;
+      }
+    }
+    // 3. warp candidate = best slot maximum (only when a slot changed)
+    if (changed) {
+      __syncwarp();
+      uint32_t bd = 0u, bt = 0xffffffffu, bc = 0u;
+      for (int sl = lane; sl < S; sl += 32) {
+        const uint32_t d = sd[warp * S + sl], t = stie[warp * S + sl];
+        if (d > bd || (d == bd && t < bt)) { bd = d; bt = t; bc = sc[warp * S + sl]; }
       }
       warp_best(bd, bt, bc);
       wd = bd; wt = bt; wc = bc;
     }
     // lane i -> CTA i: this warp's candidate, completing 16 bytes on the receiver's mbarrier
     if (lane < CS) st_async_v4(r_slot[par], r_bar[par], wd, wt, wc, 0u);
-    // the (j >> 1) & 1 parity of the round's mbarrier: mbar[par] is used every second round
-    if (flags & 1) {
-      if (lane == 0) fps_mbar_wait(&mbar[par], ((j - 1) >> 1) & 1);     // one poller per warp
-      __syncwarp();
-    } else {
-      fps_mbar_wait(&mbar[par], ((j - 1) >> 1) & 1);
-    }
+    fps_mbar_wait(&mbar[par], ((j - 1) >> 1) & 1);
     uint32_t bd = 0u, bt = 0xffffffffu, bc = 0u;
     for (uint32_t e = lane; e < nmsg; e += 32) {
       const FpsCand cnd = inbox[par][e];
@@ -396,7 +425,6 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
     // sends after the reads above (program order).  Re-arming for round j+2 happens here, before this
     // thread's own round j+1 message, hence before any round j+2 byte can arrive; slower local warps
     // still waiting on the completed phase are unaffected (parity wait).
-    if (!(flags & 2)) __syncthreads();
     if (tid == 0) {
       if (j + 2 < m) fps_mbar_arm(&mbar[par], nmsg * 16);
       if (rank == 0) {
@@ -600,16 +628,35 @@ extern "C" int coocc_gsf_compact(const unsigned char* flags, int V, int* list, i
   return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
 }
 
-static int g_fps_cs = 0, g_fps_flags = 2;   // flags 2: all-lane poll, no block barrier (fastest measured)
+static int g_fps_cs = 0, g_fps_flags = 0;
 
-template <int PPT>
-static int launch_fps(FpsJob j0, FpsJob j1, int njobs, int m, int Y, int Z, int cs, int log2bs,
-                      cudaStream_t st) {
-  const size_t smem = (size_t)PPT * kFpsThreads * sizeof(uint32_t);
-  cudaError_t e = cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static size_t fps_smem_bytes(int S) {
+  return ((size_t)2 * S * kFpsThreads + (size_t)5 * kFpsWarps * S) * sizeof(uint32_t);
+}
+
+// Runs one or two independent FPS problems (both GSFusion directions) in one launch, one cluster
+// each.  n_max = upper bound of the point counts (sizes the cluster); the exact counts are read
+// on the device from count0/count1.
+extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, const int* list1,
+                             const int* count1, int* out1, int n_max, int m, int Y, int Z,
+                             void* stream) {
+  if (!list0 || !count0 || !out0 || n_max < 1 || m < 1) return COOCC_ERR_ARG;
+  if (Y > 1023 || Z > 1023) return COOCC_ERR_CAPACITY;
+  const int njobs = list1 ? 2 : 1;
+  FpsJob j0{list0, count0, out0}, j1{list1 ? list1 : list0, list1 ? count1 : count0, list1 ? out1 : out0};
+  // smallest cluster whose shared memory holds the points (<= ~8 slots per warp preferred: the
+  // first round touches every slot)
+  int cs = 1;
+  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 8) cs *= 2;
+  if (g_fps_cs > 0) cs = g_fps_cs;
+  const int S = (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads);
+  const size_t smem = fps_smem_bytes(S);
+  if (smem > 217 * 1024) return COOCC_ERR_CAPACITY;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return COOCC_ERR_CUDA;
   if (cs > 8) {
-    e = cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    e = cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return COOCC_ERR_CUDA;
   }
   cudaLaunchConfig_t cfg;
@@ -625,32 +672,8 @@ static int launch_fps(FpsJob j0, FpsJob j1, int njobs, int m, int Y, int Z, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, fps_kernel<PPT>, j0, j1, m, Y, Z, log2bs, g_fps_flags);
+  e = cudaLaunchKernelEx(&cfg, fps_kernel, j0, j1, m, Y, Z, -1, S);
   return e == cudaSuccess ? 0 : COOCC_ERR_CUDA;
-}
-
-// Runs one or two independent FPS problems (both GSFusion directions) in one launch, one cluster
-// each.  n_max = upper bound of the point counts (sizes the cluster); the exact counts are read
-// on the device from count0/count1.
-extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, const int* list1,
-                             const int* count1, int* out1, int n_max, int m, int Y, int Z,
-                             void* stream) {
-  if (!list0 || !count0 || !out0 || n_max < 1 || m < 1) return COOCC_ERR_ARG;
-  if (Y > 1023 || Z > 1023) return COOCC_ERR_CAPACITY;
-  const int njobs = list1 ? 2 : 1;
-  FpsJob j0{list0, count0, out0}, j1{list1 ? list1 : list0, list1 ? count1 : count0, list1 ? out1 : out0};
-  // few CTAs = cheap per-round cluster barrier; the bounding-box skip keeps per-round compute low
-  int cs = 1;
-  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 8) cs *= 2;
-  if (g_fps_cs > 0) cs = g_fps_cs;
-  const int ppt = (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (ppt <= 4) return launch_fps<4>(j0, j1, njobs, m, Y, Z, cs, -1, st);
-  if (ppt <= 8) return launch_fps<8>(j0, j1, njobs, m, Y, Z, cs, -1, st);
-  if (ppt <= 16) return launch_fps<16>(j0, j1, njobs, m, Y, Z, cs, -1, st);
-  if (ppt <= 32) return launch_fps<32>(j0, j1, njobs, m, Y, Z, cs, -1, st);
-  if (ppt <= 64) return launch_fps<64>(j0, j1, njobs, m, Y, Z, cs, -1, st);
-  return COOCC_ERR_CAPACITY;
 }
 
 // tuning hook (benchmarks only): force the cluster size (0 = automatic) and exchange variant flags
