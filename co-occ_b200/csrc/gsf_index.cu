@@ -644,10 +644,10 @@ extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, con
   if (Y > 1023 || Z > 1023) return COOCC_ERR_CAPACITY;
   const int njobs = list1 ? 2 : 1;
   FpsJob j0{list0, count0, out0}, j1{list1 ? list1 : list0, list1 ? count1 : count0, list1 ? out1 : out0};
-  // smallest cluster whose shared memory holds the points (<= ~8 slots per warp preferred: the
-  // first round touches every slot)
+  // smallest cluster with <= 24 slots per warp (measured on B200: 48k points run fastest on 4 CTAs;
+  // the per-round cost is the one-hop exchange, which grows with the cluster size)
   int cs = 1;
-  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 8) cs *= 2;
+  while (cs < 16 && (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads) > 24) cs *= 2;
   if (g_fps_cs > 0) cs = g_fps_cs;
   const int S = (n_max + cs * kFpsThreads - 1) / (cs * kFpsThreads);
   const size_t smem = fps_smem_bytes(S);
