@@ -52,6 +52,8 @@ struct TcParams {
   int M, N;            // output rows / cols (fprop: V_out, Cout; dgrad: V, Cin; wgrad: Cout, Cin)
   int BN;              // N tile (multiple of 16, <= 256)
   int MT;              // 128-row MMA tiles per CTA tile (2 when BN <= 128: same bytes/MAC as 128x256)
+  int es;              // operand element size in bytes (host bookkeeping)
+  int mc;              // 1: CTA pairs (cluster of 2) on adjacent M tiles share the B tile by TMA multicast
   int taps;            // 1 or 27
   int Kc;              // reduction channels per tap (fprop: Cin, dgrad: Cout); wgrad: unused
   int a_im2col;        // A (fprop/dgrad) or B (wgrad) loaded through im2col
@@ -117,7 +119,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   // ---- tile bookkeeping (identical in every role) ---------------------------------------
   const int ntn = (p.N + p.BN - 1) / p.BN;
   const int ntm = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
-  const int ntiles = wgrad ? ntm * ntn * p.taps * p.ksplit : ntm * ntn * p.ksplit;
+  // with multicast a "tile" of the scheduler is a PAIR of M tiles (one per CTA of the cluster)
+  const int crank = p.mc ? (int)cluster_ctarank() : 0;
+  const int cidx = p.mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int cnum = p.mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int ntm_sched = p.mc ? (ntm + 1) / 2 : ntm;
+  const int ntiles = wgrad ? ntm * ntn * p.taps * p.ksplit : ntm_sched * ntn * p.ksplit;
   const int kb_per_tap = (p.Kc + E::BKE - 1) / E::BKE;
 
   if (threadIdx.x == 0) {
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], p.mc ? 2 : 1);   // multicast: both CTAs' MMAs must release the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -136,6 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (p.mc) cluster_sync_all();       // peer barriers must exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -147,14 +155,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = cidx; tile < ntiles; tile += cnum) {
         int mt, nt, it0, it1;          // it = flattened (tap, k-block) iteration
         int wg_tap = 0;
         if (!wgrad) {
           int t = tile;
           const int sp = t % p.ksplit; t /= p.ksplit;
           nt = t % ntn;
-          mt = t / ntn;
+          mt = p.mc ? 2 * (t / ntn) + crank : t / ntn;
           const int nk_total = p.taps * kb_per_tap;
           it0 = (int)((long long)nk_total * sp / p.ksplit);
           it1 = (int)((long long)nk_total * (sp + 1) / p.ksplit);
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             uint8_t* sb = sa + a_bytes;
             // a 128-row half that starts past the last pixel is not loaded at all (an im2col load whose
             // base pixel lies outside the tensor faults); its rows are masked in the epilogue
-            const int nhalf = wgrad ? 1 : min(p.MT, (p.M - mt * p.MT * kBM + kBM - 1) / kBM);
+            const int nhalf = wgrad ? 1 : max(0, min(p.MT, (p.M - mt * p.MT * kBM + kBM - 1) / kBM));
             mbar_expect_tx(&full_bar[stage], (wgrad ? a_bytes : (uint32_t)nhalf * kABytes) + b_bytes);
             if (!wgrad) {
               // ---- A: MT x [128 pixels x BKE channels], K-major
@@ -196,14 +204,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                   tma_load_2d(sa + hh * kABytes, &p.tmA, &full_bar[stage], kb * E::BKE, pix);
                 }
               }
-              // ---- B
-              if (!b_mn) {   // weights rows, K-major: box {BKE, BN}
-                tma_load_2d(sb, &p.tmB, &full_bar[stage], wtap * p.Cin + kb * E::BKE, nt * p.BN);
+              // ---- B (with multicast each CTA of the pair fetches half of the tile for both)
+              if (!b_mn) {   // weights rows, K-major: box {BKE, BN} (or {BKE, BN/2} per CTA)
+                if (p.mc) {
+                  const int half = p.BN >> 1;
+                  tma_load_2d_mc(sb + crank * half * 128, &p.tmB, &full_bar[stage], wtap * p.Cin + kb * E::BKE,
+                                 nt * p.BN + crank * half, (uint16_t)3);
+                } else {
+                  tma_load_2d(sb, &p.tmB, &full_bar[stage], wtap * p.Cin + kb * E::BKE, nt * p.BN);
+                }
               } else {       // dgrad: W in place, MN-major chunks of CH input channels x KR couts
                 const int nch = p.BN / E::CH;
-                for (int j = 0; j < nch; ++j)
-                  tma_load_2d(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
-                              wtap * p.Cin + nt * p.BN + j * E::CH, kb * E::KR);
+                if (p.mc) {
+                  for (int j = crank * (nch >> 1); j < (crank + 1) * (nch >> 1); ++j)
+                    tma_load_2d_mc(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
+                                   wtap * p.Cin + nt * p.BN + j * E::CH, kb * E::KR, (uint16_t)3);
+                } else {
+                  for (int j = 0; j < nch; ++j)
+                    tma_load_2d(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
+                                wtap * p.Cin + nt * p.BN + j * E::CH, kb * E::KR);
+                }
               }
             } else {
               // ---- A: dY^T tile, MN-major: chunks of CH couts x KR voxels
@@ -237,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = cidx; tile < ntiles; tile += cnum) {
         int nk;
         {
           const int sp = tile % p.ksplit;
@@ -263,7 +283,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
               umma<E::TF32>(d_tmem + (uint32_t)(hh * 128), ad, bd, idesc, (k | j) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+          if (p.mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees the slot in both CTAs
+          else umma_commit(&empty_bar[stage]);     // frees the smem slot when the MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (nk > 0) {
@@ -279,13 +300,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     const int q = warp & 3;                 // TMEM lane quadrant of this warp
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = cidx; tile < ntiles; tile += cnum) {
       int mt, nt, tap = 0, nk = 1;
       if (!wgrad) {
         int t = tile;
         const int sp = t % p.ksplit; t /= p.ksplit;
         nt = t % ntn;
-        mt = t / ntn;
+        mt = p.mc ? 2 * (t / ntn) + crank : t / ntn;
         const int tot = p.taps * kb_per_tap;
         nk = (int)((long long)tot * (sp + 1) / p.ksplit) - (int)((long long)tot * sp / p.ksplit);
       } else {
@@ -436,6 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (p.mc) cluster_sync_all();       // the peer may still multicast into / arrive on this CTA
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -547,10 +569,27 @@ static int launch(const TcParams& p, int ntiles, cudaStream_t st) {
     if (e != cudaSuccess) return COOCC_ERR_CUDA;
     attr_set = true;
   }
-  int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
-  if (grid < 1) return 0;
-  tc_conv_kernel<ES><<<grid, kThreads, kSmemBytes, st>>>(p);
-  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+  if (ntiles < 1) return 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  if (p.mc) {
+    // ntiles counts CTA pairs
+    const int pairs = ntiles < g_num_sms / 2 ? ntiles : g_num_sms / 2;
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(ntiles < g_num_sms ? ntiles : g_num_sms, 1, 1);
+  }
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  return cudaLaunchKernelEx(&cfg, tc_conv_kernel<ES>, p) == cudaSuccess ? 0 : COOCC_ERR_CUDA;
 }
 
 // column sums / sums of squares of a small [M, N] matrix (BN statistics of split-K layers)
@@ -592,7 +631,21 @@ static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
     mt_enabled = (e && e[0] == '0') ? 0 : 1;
   }
   if (mt_enabled && p.BN <= 128 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + p.BN - 1) / p.BN) >= g_num_sms) p.MT = 2;
-  const int ntiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN);
+  const int ntm = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
+  const int ntiles = ntm * ((p.N + p.BN - 1) / p.BN);
+  // CTA pairs sharing the weight tile by TMA multicast (halves the B traffic out of L2 per CTA)
+  static int mc_enabled = -1;
+  if (mc_enabled < 0) {
+    const char* e = getenv("COOCC_CONV_MC");
+    mc_enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int es = p.es;
+  const int ch = 128 / es;
+  p.mc = 0;
+  if (mc_enabled && ntm >= 2) {
+    if (p.mode == MODE_FPROP && ((p.BN / 2) % 8) == 0) p.mc = 1;
+    if (p.mode == MODE_DGRAD && ((p.BN / ch) % 2) == 0) p.mc = 1;
+  }
   p.ksplit = 1;
   if (p.bias == nullptr && !p.relu) p.ksplit = pick_ksplit(ntiles, nk_total);
   if (p.ksplit > 1 && !p.accum) {
@@ -663,13 +716,16 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
                         d->stride, bke, kBM, false);
   }
   if (rc) return rc;
-  rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, bke,
-                  p.BN, false);
-  if (rc) return rc;
   float* stats_after = nullptr;
+  p.es = es;
   if ((rc = prepare_split(p, taps * ((d->Cin + bke - 1) / bke), (cudaStream_t)stream))) return rc;
+  // weight rows; with multicast each CTA of a pair fetches half of the N tile
+  rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, bke,
+                  p.mc ? p.BN / 2 : p.BN, false);
+  if (rc) return rc;
   if (p.ksplit > 1 && p.stats) { stats_after = p.stats; p.stats = nullptr; }
-  const int ntiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
+  const int ntm_ = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
+  const int ntiles = (p.mc ? (ntm_ + 1) / 2 : ntm_) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
   rc = es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
   if (!rc && stats_after) {
     dim3 grid((p.N + 31) / 32, p.M >= 4096 ? 64 : (p.M + 63) / 64);
@@ -722,8 +778,10 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, f
   if (rc) return rc;
   rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, ch, ch, true);
   if (rc) return rc;
+  p.es = es;
   if ((rc = prepare_split(p, taps * ((d->Cout + ch - 1) / ch), (cudaStream_t)stream))) return rc;
-  const int ntiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
+  const int ntm_ = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
+  const int ntiles = (p.mc ? (ntm_ + 1) / 2 : ntm_) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
   return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
 }
 
@@ -742,6 +800,8 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   memset(&p, 0, sizeof(p));
   p.mode = MODE_WGRAD;
   p.MT = 1;
+  p.mc = 0;
+  p.es = es;
   p.M = d->Cout;
   p.N = d->Cin;
   p.BN = ((d->Cin + ch - 1) / ch) * ch;

@@ -64,6 +64,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const void* tmap, uint64
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, multicast: the box lands at the same shared-memory offset in every CTA of `mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* smem, const void* tmap, uint64_t* bar, int c0,
+                                               int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // im2col load of a [pixelsPerColumn x channelsPerPixel] tile of an NDHWC tensor:
 // coords (c, w, h, d, n) of the first *base* pixel, offsets = filter tap (w, h, d).
 __device__ __forceinline__ void tma_load_im2col_5d(void* smem, const void* tmap, uint64_t* bar,
@@ -118,6 +137,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
           smem_u32(bar))
+      : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
       : "memory");
 }
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (row = lane)
