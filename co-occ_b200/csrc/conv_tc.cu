@@ -636,8 +636,10 @@ static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
   // CTA pairs sharing the weight tile by TMA multicast (halves the B traffic out of L2 per CTA)
   static int mc_enabled = -1;
   if (mc_enabled < 0) {
+    // measured on B200 (profiles/): no gain -- the limiter is the per-SM operand ingest, which
+    // multicast does not reduce -- so the pairing is opt-in (COOCC_CONV_MC=1)
     const char* e = getenv("COOCC_CONV_MC");
-    mc_enabled = (e && e[0] == '0') ? 0 : 1;
+    mc_enabled = (e && e[0] == '1') ? 1 : 0;
   }
   const int es = p.es;
   const int ch = 128 / es;
