@@ -63,17 +63,22 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int Kd, const 
   const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < Kd; k0 += 16) {
+  // split-K over blockIdx.z (partials are added atomically; the host zero-fills C when needed)
+  const int ksplit = gridDim.z;
+  const int kchunk = ((Kd + ksplit - 1) / ksplit + 15) / 16 * 16;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(Kd, kbeg + kchunk);
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
     for (int e = threadIdx.x; e < 16 * 64; e += 256) {
       // choose the mapping whose consecutive threads walk the unit-stride axis
       int kk, ii;
       if (sAk == 1) { kk = e % 16; ii = e / 16; } else { ii = e % 64; kk = e / 64; }
       const int gi = i0 + ii, gk = k0 + kk;
-      As[kk][ii] = (gi < M && gk < Kd) ? A[gi * sAi + gk * sAk] : 0.f;
+      As[kk][ii] = (gi < M && gk < kend) ? A[gi * sAi + gk * sAk] : 0.f;
       int kb, jj;
       if (sBk == 1) { kb = e % 16; jj = e / 16; } else { jj = e % 64; kb = e / 64; }
       const int gj = j0 + jj, gk2 = k0 + kb;
-      Bs[kb][jj] = (gj < N && gk2 < Kd) ? B[gk2 * sBk + gj * sBj] : 0.f;
+      Bs[kb][jj] = (gj < N && gk2 < kend) ? B[gk2 * sBk + gj * sBj] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -97,7 +102,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int Kd, const 
       const int gj = j0 + tj * 4 + v;
       if (gj < N) {
         float* o = Cm + gi * ldc + gj;
-        *o = accumulate ? (*o + acc[u][v]) : acc[u][v];
+        if (ksplit > 1) atomicAdd(o, acc[u][v]);
+        else *o = accumulate ? (*o + acc[u][v]) : acc[u][v];
       }
     }
   }
@@ -227,6 +233,20 @@ extern "C" int coocc_sgemm(int M, int N, int Kd, const float* A, long long sAi, 
                            int accumulate, void* stream) {
   if (!A || !B || !Cm || M < 1 || N < 1 || Kd < 1) return COOCC_ERR_ARG;
   dim3 grid((N + 63) / 64, (M + 63) / 64);
+  // few output tiles and a long reduction (dW = dP^T rows): split K so that >= ~128 blocks run
+  int ks = 1;
+  const int tiles = grid.x * grid.y;
+  if (tiles < 64 && Kd >= 256) {
+    ks = 128 / tiles;
+    if (ks > Kd / 64) ks = Kd / 64;
+    if (ks < 1) ks = 1;
+  }
+  if (ks > 1 && !accumulate) {
+    if (cudaMemset2DAsync(Cm, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M,
+                          (cudaStream_t)stream) != cudaSuccess)
+      return COOCC_ERR_CUDA;
+  }
+  grid.z = ks;
   sgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(M, N, Kd, A, sAi, sAk, B, sBk, sBj, Cm, ldc, accumulate);
   return CK_LAUNCH();
 }

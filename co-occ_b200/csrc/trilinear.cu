@@ -72,38 +72,60 @@ __device__ __forceinline__ void tl_range(int i, float scale, int out_size, int& 
   if (hi > out_size - 1) hi = out_size - 1;
 }
 
+// per-axis gather lists: for input index i, the output indices o in [lo, lo+n) and their weights
+constexpr int kTlMax = 24;     // enough for x8 upsampling (<= 2*8 + 3 candidates per axis)
+
+// one warp per input voxel (lanes = channel groups of 4): the three per-axis weight lists are built
+// once per voxel (lane j computes candidate j) in shared memory, the inner loops are pure
+// multiply-adds over coalesced 16-byte loads
 __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const float* __restrict__ dout, long long ldd,
                                                             TlDims d, int C, const float* __restrict__ wts,
                                                             long long ldw, float* __restrict__ dsrc,
                                                             long long lds) {
+  __shared__ float sw[8][3][kTlMax];
+  const int wid = threadIdx.x >> 5;
+  const long long v = blockIdx.x * 8LL + wid;
+  const int lane = threadIdx.x & 31;
+  if (v >= (long long)d.sX * d.sY * d.sZ) return;
+  const int z = v % d.sZ, y = (v / d.sZ) % d.sY, x = v / ((long long)d.sZ * d.sY);
+  int lo[3], n[3];
+  {
+    const int idx[3] = {x, y, z};
+    const float sc[3] = {d.fx, d.fy, d.fz};
+    const int in_sz[3] = {d.sX, d.sY, d.sZ};
+    const int out_sz[3] = {d.oX, d.oY, d.oZ};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      int hi;
+      tl_range(idx[a], sc[a], out_sz[a], lo[a], hi);
+      n[a] = min(hi - lo[a] + 1, kTlMax);
+      if (lane < n[a]) {
+        int a0, a1;
+        float la;
+        tl_src(lo[a] + lane, sc[a], in_sz[a], a0, a1, la);
+        sw[wid][a][lane] = (a0 == idx[a] ? 1.f - la : 0.f) + (a1 == idx[a] ? la : 0.f);
+      }
+    }
+  }
+  __syncwarp();
+  const float* wx = sw[wid][0];
+  const float* wy = sw[wid][1];
+  const float* wz = sw[wid][2];
   const int c4 = C >> 2;
-  const long long total = (long long)d.sX * d.sY * d.sZ * c4;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const long long v = i / c4;
-    const int c = (int)(i % c4) * 4;
-    const int z = v % d.sZ, y = (v / d.sZ) % d.sY, x = v / ((long long)d.sZ * d.sY);
-    int xlo, xhi, ylo, yhi, zlo, zhi;
-    tl_range(x, d.fx, d.oX, xlo, xhi);
-    tl_range(y, d.fy, d.oY, ylo, yhi);
-    tl_range(z, d.fz, d.oZ, zlo, zhi);
+  for (int cg = lane; cg < c4; cg += 32) {
+    const int c = cg * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int ox = xlo; ox <= xhi; ++ox) {
-      int a0, a1; float la;
-      tl_src(ox, d.fx, d.sX, a0, a1, la);
-      const float wx = (a0 == x ? 1.f - la : 0.f) + (a1 == x ? la : 0.f);
-      if (wx == 0.f) continue;
-      for (int oy = ylo; oy <= yhi; ++oy) {
-        int b0, b1; float lb;
-        tl_src(oy, d.fy, d.sY, b0, b1, lb);
-        const float wy = (b0 == y ? 1.f - lb : 0.f) + (b1 == y ? lb : 0.f);
-        if (wy == 0.f) continue;
-        for (int oz = zlo; oz <= zhi; ++oz) {
-          int e0, e1; float le;
-          tl_src(oz, d.fz, d.sZ, e0, e1, le);
-          const float wz = (e0 == z ? 1.f - le : 0.f) + (e1 == z ? le : 0.f);
-          if (wz == 0.f) continue;
-          const long long ov = ((long long)ox * d.oY + oy) * d.oZ + oz;
-          float w = wx * wy * wz;
+    for (int ix = 0; ix < n[0]; ++ix) {
+      const float wxv = wx[ix];
+      if (wxv == 0.f) continue;
+      for (int iy = 0; iy < n[1]; ++iy) {
+        const float wxy = wxv * wy[iy];
+        if (wxy == 0.f) continue;
+        const long long row0 = ((long long)(lo[0] + ix) * d.oY + (lo[1] + iy)) * d.oZ + lo[2];
+        for (int iz = 0; iz < n[2]; ++iz) {
+          float w = wxy * wz[iz];
+          if (w == 0.f) continue;
+          const long long ov = row0 + iz;
           if (wts != nullptr) w *= wts[ov * ldw];
           const float4 g = *reinterpret_cast<const float4*>(dout + ov * ldd + c);
           acc.x += w * g.x; acc.y += w * g.y; acc.z += w * g.z; acc.w += w * g.w;
@@ -178,8 +200,8 @@ extern "C" int coocc_trilinear_bwd(const float* dout, long long ldd, int oX, int
                                    int sZ, void* stream) {
   if (!dout || !dsrc || (C & 3) || (lds & 3) || (ldd & 3)) return COOCC_ERR_ARG;
   const TlDims d = make_dims(sX, sY, sZ, oX, oY, oZ);
-  trilinear_bwd_kernel<<<tl_grid((long long)sX * sY * sZ * (C >> 2)), 256, 0, (cudaStream_t)stream>>>(
-      dout, ldd, d, C, wts, ldw, dsrc, lds);
+  const long long Vs = (long long)sX * sY * sZ;
+  trilinear_bwd_kernel<<<(unsigned)((Vs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dout, ldd, d, C, wts, ldw, dsrc, lds);
   return CK_LAUNCH();
 }
 
