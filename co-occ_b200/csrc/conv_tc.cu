@@ -820,10 +820,21 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   p.out = dw; p.ldc = d->Cin;
   p.nvb = (int)((Vo + ch - 1) / ch);
   const int base_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN) * taps;
-  int ks = (2 * g_num_sms + base_tiles - 1) / base_tiles;      // aim for >= 2 waves of work
-  if (ks < 1) ks = 1;
-  if (ks > p.nvb) ks = p.nvb;
-  if (ks > 64) ks = 64;
+  // split-K factor: tiles are dealt round-robin to the persistent CTAs, so pick the factor whose
+  // tile count fills whole waves (297 tiles on 148 SMs cost 3 waves, 296 cost 2)
+  int ks = 1;
+  {
+    const int max_ks = p.nvb < 48 ? (p.nvb < 1 ? 1 : p.nvb) : 48;
+    double best = -1.0;
+    for (int c = 1; c <= max_ks; ++c) {
+      const long long tiles = (long long)base_tiles * c;
+      const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
+      double eff = (double)tiles / (double)(waves * g_num_sms);
+      if (tiles < g_num_sms) eff *= 0.9;                 // prefer filling the machine at least once
+      eff -= 0.002 * c;                                  // slight preference for fewer atomic passes
+      if (eff > best) { best = eff; ks = c; }
+    }
+  }
   p.ksplit = ks;
   const bool plain = (d->ksize == 1 && d->stride == 1);
   p.a_im2col = plain ? 0 : 1;
