@@ -824,7 +824,10 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   // tile count fills whole waves (297 tiles on 148 SMs cost 3 waves, 296 cost 2)
   int ks = 1;
   {
-    const int max_ks = p.nvb < 48 ? (p.nvb < 1 ? 1 : p.nvb) : 48;
+    // every split keeps >= 8 k-blocks so the pipeline fill / atomic epilogue stay amortised
+    int max_ks = p.nvb / 8;
+    if (max_ks > 48) max_ks = 48;
+    if (max_ks < 1) max_ks = 1;
     double best = -1.0;
     for (int c = 1; c <= max_ks; ++c) {
       const long long tiles = (long long)base_tiles * c;
