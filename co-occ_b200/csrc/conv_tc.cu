@@ -40,7 +40,8 @@ constexpr int kMaxBN = 256;           // MMA N upper bound (TMEM columns per acc
 constexpr int kABytes = kBM * 128;    // 16 KiB per stage
 constexpr int kBBytesMax = kMaxBN * 128;
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kRingBytes = kStages * kStageBytes;       // 192 KiB operand ring, cut into `nstages` stages
+constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kThreads = 256;
 
 enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
@@ -51,7 +52,10 @@ struct TcParams {
   int mode;
   int M, N;            // output rows / cols (fprop: V_out, Cout; dgrad: V, Cin; wgrad: Cout, Cin)
   int BN;              // N tile (multiple of 16, <= 256)
-  int MT;              // 128-row MMA tiles per CTA tile (2 when BN <= 128: same bytes/MAC as 128x256)
+  int MT;              // 128-row MMA tiles per CTA tile (1, 2 or 4; MT*BN <= 512 TMEM columns)
+  int nstages;         // smem ring depth (4, or 3 when a stage is 64 KiB)
+  int nacc;            // TMEM accumulator buffers (2, or 1 when MT*BN > 256: epilogue not overlapped)
+  int hstride;         // TMEM column stride between the MT halves
   int es;              // operand element size in bytes (host bookkeeping)
   int mc;              // 1: CTA pairs (cluster of 2) on adjacent M tiles share the B tile by TMA multicast
   int taps;            // 1 or 27
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRingBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
@@ -149,6 +153,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   const uint32_t a_bytes = kABytes * (uint32_t)p.MT;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = a_bytes + (b_bytes + 1023u) / 1024u * 1024u;
+  const int nstages = p.nstages;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================================
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           const int wtap = (p.mode == MODE_DGRAD) ? (p.taps - 1 - tap) : tap;
           {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * kStageBytes;
+            uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + a_bytes;
             // a 128-row half that starts past the last pixel is not loaded at all (an im2col load whose
             // base pixel lies outside the tensor faults); its rows are masked in the epilogue
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                               nt * p.BN + j * E::CH, kb * E::KR);
               }
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -266,11 +272,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;   // nacc == 1 -> acc stays 0
         for (int k = 0; k < nk; ++k) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
           for (int hh = 0; hh < p.MT; ++hh) {
             const uint32_t sah = sa + hh * kABytes;
@@ -280,19 +286,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                                        : make_smem_desc(sah + j * 32, 16, 1024, 2);
               const uint64_t bd = b_mn ? make_smem_desc(sb + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
                                        : make_smem_desc(sb + j * 32, 16, 1024, 2);
-              umma<E::TF32>(d_tmem + (uint32_t)(hh * 128), ad, bd, idesc, (k | j) ? 1u : 0u);
+              umma<E::TF32>(d_tmem + (uint32_t)(hh * p.hstride), ad, bd, idesc, (k | j) ? 1u : 0u);
             }
           }
           if (p.mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees the slot in both CTAs
           else umma_commit(&empty_bar[stage]);     // frees the smem slot when the MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (nk > 0) {
           umma_commit(&tfull_bar[acc]);            // accumulator complete -> epilogue
         } else {
           mbar_arrive(&tfull_bar[acc]);
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       for (int hh = 0; hh < p.MT; ++hh) {
       const int row = (mt * p.MT + hh) * kBM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(hh * 128) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(hh * p.hstride) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         if (nk > 0) {
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -623,14 +629,28 @@ static int pick_ksplit(int ntiles, int nk_total) {
 }
 
 static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
-  // two 128-row MMA tiles per CTA when the N tile is narrow and there is enough work to fill the GPU
+  // Several 128-row MMA tiles per CTA tile share one B tile: fewer operand bytes per MAC have to
+  // be pulled from L2 into the SM (the measured limiter, profiles/r01_ncu_full_tc_conv_bf16.summary.txt).
+  //   BN <= 128: MT = 2, two TMEM buffers (epilogue overlaps the next tile)
+  //   BN == 256: MT = 2 uses all 512 TMEM columns -> single buffer, only for long reductions where the
+  //              exposed epilogue is a few % of the tile; 64 KiB stages -> 3-deep ring
   p.MT = 1;
   static int mt_enabled = -1;
   if (mt_enabled < 0) {
     const char* e = getenv("COOCC_CONV_MT2");
-    mt_enabled = (e && e[0] == '0') ? 0 : 1;
+    mt_enabled = e ? atoi(e) : 2;       // 0: off, 1: narrow tiles only, 2: also 256-wide tiles
   }
-  if (mt_enabled && p.BN <= 128 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ((p.N + p.BN - 1) / p.BN) >= g_num_sms) p.MT = 2;
+  const int ntn_ = (p.N + p.BN - 1) / p.BN;
+  if (mt_enabled >= 1 && p.BN <= 128 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ntn_ >= g_num_sms) p.MT = 2;
+  if (mt_enabled >= 2 && p.BN > 128 && nk_total >= 32 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ntn_ >= g_num_sms)
+    p.MT = 2;
+  p.hstride = p.BN <= 128 ? 128 : 256;
+  p.nacc = (p.MT * p.hstride <= 256) ? 2 : 1;
+  {
+    const int stage = kABytes * p.MT + (p.BN * 128 + 1023) / 1024 * 1024;
+    p.nstages = kRingBytes / stage;
+    if (p.nstages > kStages) p.nstages = kStages;
+  }
   const int ntm = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
   const int ntiles = ntm * ((p.N + p.BN - 1) / p.BN);
   // CTA pairs sharing the weight tile by TMA multicast (halves the B traffic out of L2 per CTA)
@@ -802,6 +822,9 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   memset(&p, 0, sizeof(p));
   p.mode = MODE_WGRAD;
   p.MT = 1;
+  p.nstages = kStages;
+  p.nacc = 2;
+  p.hstride = 128;
   p.mc = 0;
   p.es = es;
   p.M = d->Cout;
