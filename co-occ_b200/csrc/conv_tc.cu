@@ -53,6 +53,7 @@ struct TcParams {
   int M, N;            // output rows / cols (fprop: V_out, Cout; dgrad: V, Cin; wgrad: Cout, Cin)
   int BN;              // N tile (multiple of 16, <= 256)
   int MT;              // 128-row MMA tiles per CTA tile (1, 2 or 4; MT*BN <= 512 TMEM columns)
+  int NT;              // wgrad: filter taps per CTA tile sharing one dY tile (1 or 3)
   int nstages;         // smem ring depth (4, or 3 when a stage is 64 KiB)
   int nacc;            // TMEM accumulator buffers (2, or 1 when MT*BN > 256: epilogue not overlapped)
   int hstride;         // TMEM column stride between the MT halves
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   const int cidx = p.mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int cnum = p.mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int ntm_sched = p.mc ? (ntm + 1) / 2 : ntm;
-  const int ntiles = wgrad ? ntm * ntn * p.taps * p.ksplit : ntm_sched * ntn * p.ksplit;
+  const int ntg = (p.taps + p.NT - 1) / p.NT;       // wgrad: tap groups
+  const int ntiles = wgrad ? ntm * ntn * ntg * p.ksplit : ntm_sched * ntn * p.ksplit;
   const int kb_per_tap = (p.Kc + E::BKE - 1) / E::BKE;
 
   if (threadIdx.x == 0) {
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   const uint32_t a_bytes = kABytes * (uint32_t)p.MT;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = a_bytes + (b_bytes + 1023u) / 1024u * 1024u;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)p.NT * ((b_bytes + 1023u) / 1024u * 1024u);
   const int nstages = p.nstages;
 
   if (warp == 0) {
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           it1 = (int)((long long)p.nvb * (sp + 1) / p.ksplit);
         }
         for (int it = it0; it < it1; ++it) {
-          const int tap = wgrad ? wg_tap : it / kb_per_tap;
+          const int tap = wgrad ? wg_tap * p.NT : it / kb_per_tap;    // wgrad: first tap of the group
           const int kb = wgrad ? it : it % kb_per_tap;
           // filter offsets of this tap in the im2col operand (W<->z, H<->y, D<->x)
           const int kx = (p.taps == 1) ? 0 : tap / 9, ky = (p.taps == 1) ? 0 : (tap / 3) % 3,
@@ -195,8 +197,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             uint8_t* sb = sa + a_bytes;
             // a 128-row half that starts past the last pixel is not loaded at all (an im2col load whose
             // base pixel lies outside the tensor faults); its rows are masked in the epilogue
-            const int nhalf = wgrad ? 1 : max(0, min(p.MT, (p.M - mt * p.MT * kBM + kBM - 1) / kBM));
-            mbar_expect_tx(&full_bar[stage], (wgrad ? a_bytes : (uint32_t)nhalf * kABytes) + b_bytes);
+            const int nhalf = max(0, min(p.MT, (p.M - mt * p.MT * kBM + kBM - 1) / kBM));
+            const int ntap = wgrad ? min(p.NT, p.taps - tap) : 1;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)nhalf * kABytes + (uint32_t)ntap * b_bytes);
             if (!wgrad) {
               // ---- A: MT x [128 pixels x BKE channels], K-major
               for (int hh = 0; hh < nhalf; ++hh) {
@@ -232,22 +235,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 }
               }
             } else {
-              // ---- A: dY^T tile, MN-major: chunks of CH couts x KR voxels
-              for (int j = 0; j < kBM / E::CH; ++j)
-                tma_load_2d(sa + j * E::MN_CHUNK, &p.tmA, &full_bar[stage],
-                            mt * kBM + j * E::CH, kb * E::KR);
-              // ---- B: X tile (shifted by tap), MN-major: chunks of CH cins x KR pixels
+              // ---- A: MT dY^T tiles, MN-major: chunks of CH couts x KR voxels
+              for (int hh = 0; hh < nhalf; ++hh)
+                for (int j = 0; j < kBM / E::CH; ++j)
+                  tma_load_2d(sa + hh * kABytes + j * E::MN_CHUNK, &p.tmA, &full_bar[stage],
+                              (mt * p.MT + hh) * kBM + j * E::CH, kb * E::KR);
+              // ---- B: NT X tiles (one per tap of the group), MN-major: chunks of CH cins x KR pixels
               const int nch = p.BN / E::CH;
+              const uint32_t b_stride = (b_bytes + 1023u) / 1024u * 1024u;
               int w = 0, h = 0, d = 0;
               if (p.a_im2col) pixel_to_whd(p, kb * E::KR, w, h, d);
-              for (int j = 0; j < nch; ++j) {
-                if (p.a_im2col)
-                  tma_load_im2col_5d(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
-                                     nt * p.BN + j * E::CH, w, h, d, 0, (uint16_t)kz, (uint16_t)ky,
-                                     (uint16_t)kx);
-                else
-                  tma_load_2d(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
-                              nt * p.BN + j * E::CH, kb * E::KR);
+              for (int tt = 0; tt < ntap; ++tt) {
+                const int tp = tap + tt;
+                const int tx = (p.taps == 1) ? 0 : tp / 9, ty = (p.taps == 1) ? 0 : (tp / 3) % 3,
+                          tz = (p.taps == 1) ? 0 : tp % 3;
+                for (int j = 0; j < nch; ++j) {
+                  if (p.a_im2col)
+                    tma_load_im2col_5d(sb + tt * b_stride + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
+                                       nt * p.BN + j * E::CH, w, h, d, 0, (uint16_t)tz, (uint16_t)ty,
+                                       (uint16_t)tx);
+                  else
+                    tma_load_2d(sb + tt * b_stride + j * E::MN_CHUNK, &p.tmB, &full_bar[stage],
+                                nt * p.BN + j * E::CH, kb * E::KR);
+                }
               }
             }
             if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -264,11 +274,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cidx; tile < ntiles; tile += cnum) {
-        int nk;
+        int nk, ntap = 1;
         {
           const int sp = tile % p.ksplit;
           const int tot = wgrad ? p.nvb : p.taps * kb_per_tap;
           nk = (int)((long long)tot * (sp + 1) / p.ksplit) - (int)((long long)tot * sp / p.ksplit);
+          if (wgrad) {
+            const int tg = tile / p.ksplit / ntn / ntm;
+            ntap = min(p.NT, p.taps - tg * p.NT);
+          }
         }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -278,15 +292,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
+          const uint32_t b_stride = (b_bytes + 1023u) / 1024u * 1024u;
           for (int hh = 0; hh < p.MT; ++hh) {
             const uint32_t sah = sa + hh * kABytes;
+            for (int tt = 0; tt < ntap; ++tt) {
+              const uint32_t sbt = sb + tt * b_stride;
+              const uint32_t dcol = d_tmem + (uint32_t)((hh * p.NT + tt) * p.hstride);
 #pragma unroll
-            for (int j = 0; j < E::NUK; ++j) {
-              const uint64_t ad = a_mn ? make_smem_desc(sah + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
-                                       : make_smem_desc(sah + j * 32, 16, 1024, 2);
-              const uint64_t bd = b_mn ? make_smem_desc(sb + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
-                                       : make_smem_desc(sb + j * 32, 16, 1024, 2);
-              umma<E::TF32>(d_tmem + (uint32_t)(hh * p.hstride), ad, bd, idesc, (k | j) ? 1u : 0u);
+              for (int j = 0; j < E::NUK; ++j) {
+                const uint64_t ad = a_mn ? make_smem_desc(sah + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
+                                         : make_smem_desc(sah + j * 32, 16, 1024, 2);
+                const uint64_t bd = b_mn ? make_smem_desc(sbt + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
+                                         : make_smem_desc(sbt + j * 32, 16, 1024, 2);
+                umma<E::TF32>(dcol, ad, bd, idesc, (k | j) ? 1u : 0u);
+              }
             }
           }
           if (p.mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3);   // frees the slot in both CTAs
@@ -320,15 +339,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         const int sp = t % p.ksplit; t /= p.ksplit;
         nt = t % ntn; t /= ntn;
         mt = t % ntm; t /= ntm;
-        tap = t;
+        tap = t * p.NT;              // first tap of the group
         nk = (int)((long long)p.nvb * (sp + 1) / p.ksplit) - (int)((long long)p.nvb * sp / p.ksplit);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      for (int hh = 0; hh < p.MT; ++hh) {
+      const int nsub = p.MT * p.NT;
+      for (int u = 0; u < nsub; ++u) {
+      const int hh = u / p.NT, tt = u % p.NT;
+      const int wtap = tap + tt;                     // wgrad: tap of this sub-accumulator
+      if (wgrad && wtap >= p.taps) continue;
       const int row = (mt * p.MT + hh) * kBM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(hh * p.hstride) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(u * p.hstride) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
         if (nk > 0) {
@@ -437,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           }
         } else if (row_ok && nk > 0) {
           // wgrad: accumulate the split-K partial into dW[row][tap][col]
-          float* o = p.out + ((long long)row * p.taps + tap) * p.ldc + col0;
+          float* o = p.out + ((long long)row * p.taps + wtap) * p.ldc + col0;
           if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -644,6 +667,7 @@ static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
   if (mt_enabled >= 1 && p.BN <= 128 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ntn_ >= g_num_sms) p.MT = 2;
   if (mt_enabled >= 2 && p.BN > 128 && nk_total >= 32 && ((p.M + 2 * kBM - 1) / (2 * kBM)) * ntn_ >= g_num_sms)
     p.MT = 2;
+  p.NT = 1;
   p.hstride = p.BN <= 128 ? 128 : 256;
   p.nacc = (p.MT * p.hstride <= 256) ? 2 : 1;
   {
@@ -821,20 +845,10 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.mode = MODE_WGRAD;
-  p.MT = 1;
-  p.nstages = kStages;
-  p.nacc = 2;
-  p.hstride = 128;
   p.mc = 0;
   p.es = es;
   p.M = d->Cout;
   p.N = d->Cin;
-  p.BN = ((d->Cin + ch - 1) / ch) * ch;
-  if (p.BN > kMaxBN) {
-    p.BN = kMaxBN;
-    for (int t = 256; t >= ch; t -= ch)
-      if (d->Cin % t == 0) { p.BN = t; break; }
-  }
   p.taps = taps;
   p.Cin = d->Cin;
   p.oX = oX; p.oY = oY; p.oZ = oZ;
@@ -842,7 +856,35 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   p.lo = -(d->ksize / 2);
   p.out = dw; p.ldc = d->Cin;
   p.nvb = (int)((Vo + ch - 1) / ch);
-  const int base_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN) * taps;
+  // CTA tile shape (fewer operand bytes per MAC, like fprop):
+  //   Cout >= 256          : two cout tiles share one X tile        (MT = 2, BN <= 256)
+  //   Cout <= 128, 27 taps : three taps share one dY^T tile          (NT = 3, BN <= 128)
+  static int wg_shape = -1;
+  if (wg_shape < 0) {
+    const char* e = getenv("COOCC_WGRAD_SHAPES");
+    wg_shape = (e && e[0] == '0') ? 0 : 1;
+  }
+  p.MT = 1;
+  p.NT = 1;
+  int bn_cap = kMaxBN;
+  if (wg_shape && p.nvb >= 64) {
+    if (d->Cout >= 256) p.MT = 2;
+    else if (taps == 27) { p.NT = 3; bn_cap = 128; }
+  }
+  p.BN = ((d->Cin + ch - 1) / ch) * ch;
+  if (p.BN > bn_cap) {
+    p.BN = bn_cap;
+    for (int t = bn_cap; t >= ch; t -= ch)
+      if (d->Cin % t == 0) { p.BN = t; break; }
+  }
+  p.hstride = p.BN <= 128 ? 128 : 256;
+  p.nacc = (p.MT * p.NT * p.hstride <= 256) ? 2 : 1;
+  {
+    const int stage = kABytes * p.MT + p.NT * ((p.BN * 128 + 1023) / 1024 * 1024);
+    p.nstages = kRingBytes / stage;
+    if (p.nstages > kStages) p.nstages = kStages;
+  }
+  const int base_tiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN) * ((taps + p.NT - 1) / p.NT);
   // split-K factor: tiles are dealt round-robin to the persistent CTAs, so pick the factor whose
   // tile count fills whole waves (297 tiles on 148 SMs cost 3 waves, 296 cost 2)
   int ks = 1;
