@@ -129,10 +129,9 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const float* __restrict__ dout, long long ldd, const float* __restrict__ out, long long ldo,
     const float* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
     const float* __restrict__ gamma, const float* __restrict__ sums, int relu, OutT* __restrict__ dx,
-    long long lddx, float* __restrict__ dres, long long lddr) {
+    long long lddx, float* __restrict__ dres, long long lddr, float inv_n) {
   const int c4 = C >> 2;
   const long long total = V * c4;
-  const float inv_n = 1.f / (float)V;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const long long r = i / c4;
     const int c = (int)(i % c4) * 4;
@@ -214,15 +213,16 @@ extern "C" int coocc_bn_act_fwd(const float* x, long long ldx, long long V, int 
   return CK_LAUNCH();
 }
 
-// sums: float[2*C], zeroed by the caller.  dgamma = sums[C:], dbeta = sums[:C].
-extern "C" int coocc_bn_act_bwd(const float* dout, long long ldd, const float* out, long long ldo, const float* x,
-                                long long ldx, long long V, int C, const float* mean_invstd, const float* gamma,
-                                int relu, float* sums, void* dx, long long lddx, int dx_bf16, float* dres,
-                                long long lddr, void* stream) {
-  if (!dout || !x || !mean_invstd || !gamma || !sums || !dx || (C & 3) || (ldd & 3) || (ldx & 3) || (lddx & 3))
-    return COOCC_ERR_ARG;
+// Backward in two stream-ordered halves so that SyncBatchNorm can all-reduce `sums` in between:
+//   reduce: sums (float[2*C], zeroed by the caller) += (sum dz, sum dz*xhat) over this rank's rows
+//   apply : dx = gamma*invstd*(dz - sums[0:C]/count - xhat*sums[C:2C]/count); dres = dz (optional)
+// count = number of rows the statistics were taken over (V, or the sum of V over all ranks).
+// After the reduce, sums[0:C] = dbeta and sums[C:2C] = dgamma (of this rank / of all ranks).
+extern "C" int coocc_bn_act_bwd_reduce(const float* dout, long long ldd, const float* out, long long ldo,
+                                       const float* x, long long ldx, long long V, int C, const float* mean_invstd,
+                                       int relu, float* sums, void* stream) {
+  if (!dout || !x || !mean_invstd || !sums || (C & 3) || (ldd & 3) || (ldx & 3)) return COOCC_ERR_ARG;
   if (relu && (!out || (ldo & 3))) return COOCC_ERR_ARG;
-  cudaStream_t st = (cudaStream_t)stream;
   const int cgroups = (C / 4 + 31) / 32;
   int rows_per_block = 256;
   long long nby = (V + rows_per_block - 1) / rows_per_block;
@@ -230,15 +230,28 @@ extern "C" int coocc_bn_act_bwd(const float* dout, long long ldd, const float* o
     rows_per_block *= 2;
     nby = (V + rows_per_block - 1) / rows_per_block;
   }
-  bn_act_bwd_reduce_kernel<<<dim3(cgroups, (unsigned)nby), dim3(32, 8), 0, st>>>(dout, ldd, out, ldo, x, ldx, V, C,
-                                                                               mean_invstd, relu, rows_per_block, sums);
+  bn_act_bwd_reduce_kernel<<<dim3(cgroups, (unsigned)nby), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      dout, ldd, out, ldo, x, ldx, V, C, mean_invstd, relu, rows_per_block, sums);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_bn_act_bwd_apply(const float* dout, long long ldd, const float* out, long long ldo,
+                                      const float* x, long long ldx, long long V, int C, const float* mean_invstd,
+                                      const float* gamma, int relu, const float* sums, long long count, void* dx,
+                                      long long lddx, int dx_bf16, float* dres, long long lddr, void* stream) {
+  if (!dout || !x || !mean_invstd || !gamma || !sums || !dx || (C & 3) || (ldd & 3) || (ldx & 3) || (lddx & 3) ||
+      count < 1)
+    return COOCC_ERR_ARG;
+  if (relu && (!out || (ldo & 3))) return COOCC_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
   const int g = grid_for(V * (C >> 2));
+  const float inv_n = (float)(1.0 / (double)count);
   if (dx_bf16)
     bn_act_bwd_apply_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(dout, ldd, out, ldo, x, ldx, V, C, mean_invstd, gamma, sums,
-                                                             relu, (__nv_bfloat16*)dx, lddx, dres, lddr);
+                                                             relu, (__nv_bfloat16*)dx, lddx, dres, lddr, inv_n);
   else
     bn_act_bwd_apply_kernel<float><<<g, 256, 0, st>>>(dout, ldd, out, ldo, x, ldx, V, C, mean_invstd, gamma, sums, relu,
-                                                     (float*)dx, lddx, dres, lddr);
+                                                     (float*)dx, lddx, dres, lddr, inv_n);
   return CK_LAUNCH();
 }
 

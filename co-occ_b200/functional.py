@@ -221,6 +221,21 @@ def conv3d(x2d, w5d, dims, k, s=1, bias=None, relu=False, want_stats=False):
     return _Conv3dFn.apply(x2d, w5d, bias, dims, k, s, relu, want_stats)
 
 
+def _sync_group():
+    """process group for SyncBatchNorm statistics, or None (single process / disabled)."""
+    import torch.distributed as dist
+    if SYNC_BN["enabled"] and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+# The reference converts every BatchNorm of the model to SyncBatchNorm when training distributed
+# (tools/train.py:222-223, sync_bn=True in the configs): batch statistics and their gradients are
+# reduced over all ranks.  Here that is one small all-reduce of the [2,C] epilogue sums in forward
+# and one of the [2,C] backward sums (SURVEY F9).  Single process: plain BatchNorm3d.
+SYNC_BN = {"enabled": True}
+
+
 class _BNActFn(torch.autograd.Function):
     """out = relu?(batchnorm_train(x) (+ residual)) from the conv-epilogue statistics."""
 
@@ -229,8 +244,13 @@ class _BNActFn(torch.autograd.Function):
         L = _lib.lib()
         V, C = x.shape
         dev = x.device
+        count = V
+        dist = _sync_group()
+        if dist is not None:
+            dist.all_reduce(stats)
+            count = V * dist.get_world_size()
         mi = torch.empty(2, C, device=dev, dtype=torch.float32)
-        _lib.check(L.coocc_bn_finalize(_p(stats), C, V, float(eps), float(momentum), _p(running_mean),
+        _lib.check(L.coocc_bn_finalize(_p(stats), C, count, float(eps), float(momentum), _p(running_mean),
                                        _p(running_var), _p(mi), _stream()), "bn_finalize")
         out = torch.empty(V, C, device=dev, dtype=torch.float32)
         if residual is not None:
@@ -239,23 +259,46 @@ class _BNActFn(torch.autograd.Function):
                                       residual.stride(0) if residual is not None else 0, 1 if relu else 0,
                                       _p(out), out.stride(0), 0, _stream()), "bn_act_fwd")
         ctx.save_for_backward(x, out if relu else None, mi, gamma)
-        ctx.meta = (relu, residual is not None)
+        ctx.meta = (relu, residual is not None, count)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
         x, out, mi, gamma = ctx.saved_tensors
-        relu, has_res = ctx.meta
+        relu, has_res, count = ctx.meta
         V, C = x.shape
         dout = _as_rows(dout)
         sums = torch.zeros(2, C, device=x.device, dtype=torch.float32)
+        ldo = out.stride(0) if out is not None else 0
+        _lib.check(L.coocc_bn_act_bwd_reduce(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C,
+                                             _p(mi), 1 if relu else 0, _p(sums), _stream()), "bn_act_bwd_reduce")
+        local = sums
+        if count != V:                      # SyncBN: batch terms use the sums over all ranks
+            dist = _sync_group()
+            local = sums.clone()            # dgamma / dbeta stay per-rank (DDP averages them)
+            dist.all_reduce(sums)
         dx = torch.empty(V, C, device=x.device, dtype=torch.float32)
         dres = torch.empty(V, C, device=x.device, dtype=torch.float32) if has_res else None
-        _lib.check(L.coocc_bn_act_bwd(_p(dout), dout.stride(0), _p(out), out.stride(0) if out is not None else 0,
-                                      _p(x), x.stride(0), V, C, _p(mi), _p(gamma), 1 if relu else 0, _p(sums), _p(dx),
-                                      dx.stride(0), 0, _p(dres), C if has_res else 0, _stream()), "bn_act_bwd")
-        return dx, None, sums[1], sums[0], dres, None, None, None, None, None
+        _lib.check(L.coocc_bn_act_bwd_apply(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C, _p(mi),
+                                            _p(gamma), 1 if relu else 0, _p(sums), count, _p(dx), dx.stride(0), 0,
+                                            _p(dres), C if has_res else 0, _stream()), "bn_act_bwd_apply")
+        return dx, None, local[1], local[0], dres, None, None, None, None, None
+
+
+def bn_act_eval(x, running_mean, running_var, gamma, beta, eps, residual=None, relu=True):
+    """Inference-mode BatchNorm (+ residual, ReLU) from the running statistics; no autograd."""
+    L = _lib.lib()
+    x = _as_rows(x)
+    V, C = x.shape
+    mi = torch.stack([running_mean.float(), torch.rsqrt(running_var.float() + eps)]).contiguous()
+    out = torch.empty(V, C, device=x.device, dtype=torch.float32)
+    if residual is not None:
+        residual = _as_rows(residual)
+    _lib.check(L.coocc_bn_act_fwd(_p(x), x.stride(0), V, C, _p(mi), _p(gamma), _p(beta), _p(residual),
+                                  residual.stride(0) if residual is not None else 0, 1 if relu else 0,
+                                  _p(out), out.stride(0), 0, _stream()), "bn_act_fwd")
+    return out
 
 
 def bn_act(x, stats, gamma, beta, residual=None, relu=True, eps=1e-5, momentum=0.1, running_mean=None,

@@ -63,6 +63,10 @@ def conv_bn_act(x2d, dims, conv, bn=None, relu=True, residual=None):
                       bn.running_mean if track else None, bn.running_var if track else None)
         return y, odims
     y = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, bias=conv.bias)
+    if (bn is not None and not bn.training and bn.running_mean is not None and not torch.is_grad_enabled()
+            and conv.out_channels % 4 == 0):
+        # inference: running statistics, same fused kernel
+        return CF.bn_act_eval(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.eps, residual, relu), odims
     if bn is not None:
         y = batch_norm2d(y, bn)
     if residual is not None:

@@ -166,13 +166,17 @@ int coocc_bn_finalize(const float* stats, int C, long long count, float eps, flo
 int coocc_bn_act_fwd(const float* x, long long ldx, long long V, int C, const float* mean_invstd,
                      const float* gamma, const float* beta, const float* residual, long long ldr, int relu,
                      void* out, long long ldo, int out_bf16, void* stream);
-/* backward of the above.  sums = float[2*C] zeroed by the caller; on return sums[0:C] = dbeta,
- * sums[C:2C] = dgamma.  dx (fp32 or bf16) = gradient w.r.t. x; dres (optional) = gradient w.r.t.
- * the residual input. */
-int coocc_bn_act_bwd(const float* dout, long long ldd, const float* out, long long ldo, const float* x,
-                     long long ldx, long long V, int C, const float* mean_invstd, const float* gamma, int relu,
-                     float* sums, void* dx, long long lddx, int dx_bf16, float* dres, long long lddr,
-                     void* stream);
+/* backward of the above, in two stream-ordered halves (a SyncBatchNorm all-reduce of `sums` fits in
+ * between).  reduce: sums (float[2*C], zeroed by the caller) += (sum dz, sum dz*xhat), dz = dout*[out>0];
+ * afterwards sums[0:C] = dbeta, sums[C:2C] = dgamma.  apply: dx (fp32 or bf16) = gradient w.r.t. x with
+ * the batch terms divided by `count` (rows the statistics were taken over); dres (optional) = dz. */
+int coocc_bn_act_bwd_reduce(const float* dout, long long ldd, const float* out, long long ldo, const float* x,
+                            long long ldx, long long V, int C, const float* mean_invstd, int relu, float* sums,
+                            void* stream);
+int coocc_bn_act_bwd_apply(const float* dout, long long ldd, const float* out, long long ldo, const float* x,
+                           long long ldx, long long V, int C, const float* mean_invstd, const float* gamma, int relu,
+                           const float* sums, long long count, void* dx, long long lddx, int dx_bf16, float* dres,
+                           long long lddr, void* stream);
 /* dst[(2x,2y,2z)] = src[(x,y,z)], zero elsewhere (dst extent X,Y,Z; src extent oX,oY,oZ) */
 int coocc_dilate2(const void* src, long long lds, int oX, int oY, int oZ, int C, void* dst, long long ldd,
                   int X, int Y, int Z, int is_bf16, void* stream);

@@ -52,3 +52,37 @@ def test_grad_reducer_world2_gloo():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert all(nb > 0 for _, _, nb in res)
+
+
+def _syncbn_worker(rank, world, port, q):
+    """SyncBN bookkeeping on CPU/gloo: the statistics all-reduce of _BNActFn is exercised through its
+    pure-python pieces (the CUDA kernels themselves are covered by the GPU tests)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from coocc_b200 import functional as CF
+    ok = CF._sync_group() is not None
+    CF.SYNC_BN["enabled"] = False
+    ok = ok and CF._sync_group() is None
+    CF.SYNC_BN["enabled"] = True
+    # the reduction the forward performs on the epilogue sums
+    stats = torch.full((2, 4), float(rank + 1))
+    CF._sync_group().all_reduce(stats)
+    ok = ok and bool((stats == 3.0).all())
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_syncbn_group_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res

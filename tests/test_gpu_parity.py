@@ -294,3 +294,32 @@ def test_conv_bn_relu_fused(res, precision):
     assert e["y"] < fwd_b and e["rmean"] < fwd_b and e["rvar"] < fwd_b
     assert max(v for k, v in e.items() if k.startswith("d")) < bwd_b
     assert int(bn_g.num_batches_tracked) == 1
+
+
+def test_eval_mode_matches_oracle_modules():
+    """Inference (model.eval(), no_grad): BatchNorm uses the running statistics -- compared with the
+    same torch modules run on the CPU."""
+    import copy
+    import torch.nn as nn
+    from coocc_b200 import modules as M
+    coocc_b200.set_precision("fp32")
+    try:
+        gen = torch.Generator().manual_seed(11)
+        conv = nn.Conv3d(32, 64, 3, 1, 1, bias=False)
+        bn = nn.BatchNorm3d(64)
+        with torch.no_grad():
+            bn.running_mean.copy_(torch.randn(64, generator=gen) * 0.1)
+            bn.running_var.copy_(torch.rand(64, generator=gen) + 0.5)
+            bn.weight.copy_(torch.rand(64, generator=gen) + 0.5)
+            bn.bias.copy_(torch.randn(64, generator=gen) * 0.1)
+        conv_g, bn_g = copy.deepcopy(conv).to(DEV).eval(), copy.deepcopy(bn).to(DEV).eval()
+        conv.eval(); bn.eval()
+        x0 = torch.randn(1, 32, 9, 8, 4, generator=gen)
+        with torch.no_grad():
+            ref = torch.relu(bn(conv(x0)))
+            x2d, d = CF.to_cl2d(x0.to(DEV).contiguous(memory_format=torch.channels_last_3d))
+            out, _ = M.conv_bn_act(x2d, d, conv_g, bn_g, relu=True)
+        assert rel_err(CF.to_5d(out, d), ref) < 2e-5
+        assert int(bn_g.num_batches_tracked) == 0
+    finally:
+        coocc_b200.set_precision("tf32")
