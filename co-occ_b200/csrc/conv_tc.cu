@@ -40,8 +40,11 @@ constexpr int kMaxBN = 256;           // MMA N upper bound (TMEM columns per acc
 constexpr int kABytes = kBM * 128;    // 16 KiB per stage
 constexpr int kBBytesMax = kMaxBN * 128;
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kRingBytes = kStages * kStageBytes;       // 192 KiB operand ring, cut into `nstages` stages
-constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kRingBytes = 220 * 1024;                  // operand ring(s), cut into `nstages` stages
+constexpr int kMaxBRing = 8;          // ky-fused path: weight-tile ring depth bound
+constexpr int kMaxARing = 4;          // ky-fused path: extended activation-tile ring depth bound
+constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 512 /*barriers*/;
+static_assert(kStages * kStageBytes <= kRingBytes, "ring");
 constexpr int kThreads = 256;
 
 enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
@@ -77,6 +80,14 @@ struct TcParams {
   // wgrad
   int nvb;             // number of voxel (K) blocks
   int ksplit;
+  // ky-fused 3x3x3 stride-1 path (fprop / dgrad): one y-extended activation tile feeds the three
+  // ky taps of a (kx, kz) pair, see the comment above tc_conv_kernel
+  int ky;              // 1: enabled
+  int gX, gYZ;         // grid: x extent, Y*Z
+  int gZ;              // z extent (rows per y step)
+  int ny, nyb;         // y rows per 128-pixel block (128 / Z), y blocks per x (ceil(Y / ny))
+  int ext_bytes;       // bytes of one extended tile ((ny + 2) * Z rows of 128 B, rounded to 1 KiB)
+  int NA, NB;          // ring depths: extended A tiles (MT per entry), B tiles
 };
 
 template <int ES> struct Elt {
@@ -109,10 +120,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRingBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRingBytes);   // operand ring (ky path: B ring)
+  uint64_t* empty_bar = full_bar + kMaxBRing;
+  uint64_t* fulla_bar = empty_bar + kMaxBRing;  // ky path: extended A tiles
+  uint64_t* emptya_bar = fulla_bar + kMaxARing;
+  uint64_t* tfull_bar = emptya_bar + kMaxARing; // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -123,7 +136,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   // ---- tile bookkeeping (identical in every role) ---------------------------------------
   const int ntn = (p.N + p.BN - 1) / p.BN;
-  const int ntm = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
+  // ky path: M is cut into 128-pixel blocks (x, y-block) that never straddle an x row
+  const int nmb = p.ky ? p.gX * p.nyb : (p.M + kBM - 1) / kBM;
+  const int ntm = (nmb + p.MT - 1) / p.MT;
   // with multicast a "tile" of the scheduler is a PAIR of M tiles (one per CTA of the cluster)
   const int crank = p.mc ? (int)cluster_ctarank() : 0;
   const int cidx = p.mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -136,9 +151,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kMaxBRing; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], p.mc ? 2 : 1);   // multicast: both CTAs' MMAs must release the stage
+    }
+    for (int s = 0; s < kMaxARing; ++s) {
+      mbar_init(&fulla_bar[s], 1);
+      mbar_init(&emptya_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -160,7 +179,54 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   if (warp == 0) {
     // =========================== TMA producer ===========================================
-    if (elect_one()) {
+    if (p.ky) {
+      if (elect_one()) {
+        // ---- ky-fused producer: per (kx, kz, k-block) one extended A tile per 128-pixel block, then
+        //      the three weight tiles of ky = 0..2
+        const uint32_t a_entry = (uint32_t)p.MT * (uint32_t)p.ext_bytes;
+        const uint32_t b_entry = (b_bytes + 1023u) / 1024u * 1024u;
+        uint8_t* const ringB = smem + (uint32_t)p.NA * a_entry;
+        const uint32_t ext_tx = (uint32_t)((p.ny + 2) * p.gZ) * 128u;
+        int sa_i = 0, sb_i = 0;
+        uint32_t pa = 0, pb = 0;
+        const int ngroups = 9 * kb_per_tap;
+        for (int tile = cidx; tile < ntiles; tile += cnum) {
+          const int nt = tile % ntn;
+          const int mt = tile / ntn;
+          const int nhalf = max(0, min(p.MT, nmb - mt * p.MT));
+          for (int g = 0; g < ngroups; ++g) {
+            const int kb = g % kb_per_tap;
+            const int t2 = g / kb_per_tap;
+            const int kz = t2 % 3, kx = t2 / 3;
+            mbar_wait(&emptya_bar[sa_i], pa ^ 1);
+            mbar_expect_tx(&fulla_bar[sa_i], (uint32_t)nhalf * ext_tx);
+            for (int hh = 0; hh < nhalf; ++hh) {
+              const int mb = mt * p.MT + hh;
+              const int x = mb / p.nyb, yb = mb - x * p.nyb;
+              tma_load_im2col_5d(smem + sa_i * a_entry + hh * p.ext_bytes, &p.tmA, &fulla_bar[sa_i], kb * E::BKE,
+                                 p.lo, p.lo + yb * p.ny, p.lo + x, 0, (uint16_t)kz, (uint16_t)0, (uint16_t)kx);
+            }
+            if (++sa_i == p.NA) { sa_i = 0; pa ^= 1; }
+            for (int ky = 0; ky < 3; ++ky) {
+              const int tap = kx * 9 + ky * 3 + kz;
+              const int wtap = (p.mode == MODE_DGRAD) ? (26 - tap) : tap;
+              mbar_wait(&empty_bar[sb_i], pb ^ 1);
+              mbar_expect_tx(&full_bar[sb_i], b_bytes);
+              uint8_t* sb = ringB + sb_i * b_entry;
+              if (!b_mn) {
+                tma_load_2d(sb, &p.tmB, &full_bar[sb_i], wtap * p.Cin + kb * E::BKE, nt * p.BN);
+              } else {
+                const int nch = p.BN / E::CH;
+                for (int j = 0; j < nch; ++j)
+                  tma_load_2d(sb + j * E::MN_CHUNK, &p.tmB, &full_bar[sb_i], wtap * p.Cin + nt * p.BN + j * E::CH,
+                              kb * E::KR);
+              }
+              if (++sb_i == p.NB) { sb_i = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cidx; tile < ntiles; tile += cnum) {
@@ -267,7 +333,52 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================================
-    if (elect_one()) {
+    if (p.ky) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc(E::FMT, 0u, b_mn ? 1u : 0u, kBM, (uint32_t)p.BN);
+        const uint32_t a_entry = (uint32_t)p.MT * (uint32_t)p.ext_bytes;
+        const uint32_t b_entry = (b_bytes + 1023u) / 1024u * 1024u;
+        const uint32_t ringA = smem_u32(smem);
+        const uint32_t ringB = ringA + (uint32_t)p.NA * a_entry;
+        const uint32_t ky_step = (uint32_t)p.gZ * 128u;       // one y step inside the extended tile
+        int sa_i = 0, sb_i = 0;
+        uint32_t pa = 0, pb = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int ngroups = 9 * kb_per_tap;
+        for (int tile = cidx; tile < ntiles; tile += cnum) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(&fulla_bar[sa_i], pa);
+            const uint32_t sa = ringA + sa_i * a_entry;
+            for (int ky = 0; ky < 3; ++ky) {
+              mbar_wait(&full_bar[sb_i], pb);
+              tc_fence_after();
+              const uint32_t sbt = ringB + sb_i * b_entry;
+              for (int hh = 0; hh < p.MT; ++hh) {
+                const uint32_t sah = sa + hh * p.ext_bytes + ky * ky_step;
+                const uint32_t dcol = d_tmem + (uint32_t)(hh * p.hstride);
+#pragma unroll
+                for (int j = 0; j < E::NUK; ++j) {
+                  const uint64_t ad = make_smem_desc(sah + j * 32, 16, 1024, 2);
+                  const uint64_t bd = b_mn ? make_smem_desc(sbt + j * E::MN_KSTEP, E::MN_CHUNK, E::MN_SBO, E::MN_LAYOUT)
+                                           : make_smem_desc(sbt + j * 32, 16, 1024, 2);
+                  umma<E::TF32>(dcol, ad, bd, idesc, (g | ky | j) ? 1u : 0u);
+                }
+              }
+              umma_commit(&empty_bar[sb_i]);
+              if (++sb_i == p.NB) { sb_i = 0; pb ^= 1; }
+            }
+            umma_commit(&emptya_bar[sa_i]);
+            if (++sa_i == p.NA) { sa_i = 0; pa ^= 1; }
+          }
+          umma_commit(&tfull_bar[acc]);
+          if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else if (elect_one()) {
       const uint32_t idesc = make_idesc(E::FMT, a_mn ? 1u : 0u, b_mn ? 1u : 0u, kBM, (uint32_t)p.BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -349,8 +460,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       const int hh = u / p.NT, tt = u % p.NT;
       const int wtap = tap + tt;                     // wgrad: tap of this sub-accumulator
       if (wgrad && wtap >= p.taps) continue;
-      const int row = (mt * p.MT + hh) * kBM + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      int row = (mt * p.MT + hh) * kBM + q * 32 + lane;
+      bool row_ok = row < p.M;
+      if (p.ky) {
+        // block (x, yb): 128 consecutive pixels of x row `x` starting at yb * 128
+        const int mb = mt * p.MT + hh;
+        const int x = mb / p.nyb, in_x = (mb - x * p.nyb) * kBM + q * 32 + lane;
+        row = x * p.gYZ + in_x;
+        row_ok = (mb < nmb) && (in_x < p.gYZ);
+      }
       const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(u * p.hstride) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v[32];
@@ -558,12 +676,12 @@ static int make_tm_2d(CUtensorMap* tm, const void* ptr, int es, long long rows, 
 // NDHWC tensor [1][X][Y][Z][C] with pixel stride ld (elements), im2col box {chan, pixels}
 static int make_tm_im2col(CUtensorMap* tm, const void* ptr, int es, int X, int Y, int Z, int C,
                           long long ld, int lo, int hi, int stride, int chan, int pixels,
-                          bool mn_major) {
+                          bool mn_major, int hi_h = -1000) {
   cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, 1};
   cuuint64_t gstr[4] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * Z, (cuuint64_t)ld * es * Z * Y,
                         (cuuint64_t)ld * es * Z * Y * X};
   int lower[3] = {lo, lo, lo};
-  int upper[3] = {hi, hi, hi};
+  int upper[3] = {hi, hi_h == -1000 ? hi : hi_h, hi};     // (W, H, D) = (z, y, x)
   cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUtensorMapSwizzle sw = (mn_major && es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                                                 : CU_TENSOR_MAP_SWIZZLE_128B;
@@ -702,6 +820,55 @@ static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
   return 0;
 }
 
+// ky-fused path for 3x3x3 stride-1 fprop / dgrad.  The im2col A operand of the three taps
+// (kx, 0..2, kz) is the same set of input rows shifted by one y step = Z rows of 128 B, so one
+// y-extended tile ((ny + 2) * Z pixel rows, loaded by a single im2col request whose H bounding box
+// is widened to y in [-1, nyb*ny]) serves all three: the MMA descriptors of tap ky start
+// ky * Z * 128 bytes into the tile (a multiple of the 1 KiB swizzle atom for Z % 8 == 0).  A bytes
+// pulled out of L2 per MAC drop 2.4x (Z = 16) -- the measured limiter of the plain im2col path.
+// M tiles become (x, y-block) blocks of 128 pixels so that a block never straddles an x row.
+static int ky_enabled = -1, ky_mt = 2;
+static bool try_ky(TcParams& p, int X, int Y, int Z, int ksize, int stride, int* upper_h) {
+  if (ky_enabled < 0) {
+    const char* e = getenv("COOCC_CONV_KY");
+    ky_enabled = (e && e[0] == '0') ? 0 : 1;
+    const char* m = getenv("COOCC_CONV_KY_MT");
+    if (m) ky_mt = atoi(m);
+  }
+  if (!ky_enabled || ksize != 3 || stride != 1) return false;
+  if (Z != 8 && Z != 16 && Z != 32 && Z != 64) return false;
+  const int ny = 128 / Z;
+  const int nyb = (Y + ny - 1) / ny;
+  const int up = nyb * ny - Y + 1;
+  if (up > 15) return false;
+  if ((long long)nyb * ny * 100 > (long long)Y * 115) return false;       // > 15 % padded rows: not worth it
+  const int ntn = (p.N + p.BN - 1) / p.BN;
+  const int nmb = X * nyb;
+  int MT = p.BN <= 128 ? ky_mt : 2;
+  if (MT * (p.BN <= 128 ? 128 : 256) > 512) MT = 512 / (p.BN <= 128 ? 128 : 256);
+  while (MT > 1 && ((nmb + MT - 1) / MT) * ntn < g_num_sms) MT >>= 1;
+  if (nmb * ntn < g_num_sms) return false;                                 // under-filled: split-K path
+  const int ext_bytes = ((ny + 2) * Z * 128 + 1023) / 1024 * 1024;
+  const int a_entry = MT * ext_bytes;
+  const int b_entry = (p.BN * 128 + 1023) / 1024 * 1024;
+  int NA = 2;
+  int NB = (kRingBytes - NA * a_entry) / b_entry;
+  if (NB > 6) NB = 6;
+  if (NB < 3) return false;
+  if (kRingBytes - NA * a_entry - NB * b_entry >= a_entry) NA = 3;
+  p.ky = 1;
+  p.gX = X; p.gYZ = Y * Z; p.gZ = Z; p.ny = ny; p.nyb = nyb;
+  p.ext_bytes = ext_bytes; p.NA = NA; p.NB = NB;
+  p.MT = MT; p.NT = 1;
+  p.hstride = p.BN <= 128 ? 128 : 256;
+  p.nacc = (MT * p.hstride <= 256) ? 2 : 1;
+  p.nstages = kStages;
+  p.mc = 0;
+  p.ksplit = 1;
+  *upper_h = up;
+  return true;
+}
+
 static int pick_bn(int n) {
   int bn = ((n + 15) / 16) * 16;
   if (bn <= kMaxBN) return bn;
@@ -754,6 +921,17 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
   const int bke = 128 / es;
   const bool plain = (d->ksize == 1 && d->stride == 1);
   p.a_im2col = plain ? 0 : 1;
+  p.es = es;
+  int up_h = 0;
+  if (!false && try_ky(p, d->X, d->Y, d->Z, d->ksize, d->stride, &up_h)) {
+    rc = make_tm_im2col(&p.tmA, x, es, d->X, d->Y, d->Z, d->Cin, d->ldx, -1, -1, 1, bke, (p.ny + 2) * d->Z, false,
+                        up_h);
+    if (rc) return rc;
+    rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, bke, p.BN, false);
+    if (rc) return rc;
+    const int ntiles = ((p.gX * p.nyb + p.MT - 1) / p.MT) * ((p.N + p.BN - 1) / p.BN);
+    return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+  }
   if (plain) {
     rc = make_tm_2d(&p.tmA, x, es, p.M, d->Cin, d->ldx, bke, kBM, false);
   } else {
@@ -763,7 +941,6 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
   }
   if (rc) return rc;
   float* stats_after = nullptr;
-  p.es = es;
   if ((rc = prepare_split(p, taps * ((d->Cin + bke - 1) / bke), (cudaStream_t)stream))) return rc;
   // weight rows; with multicast each CTA of a pair fetches half of the N tile
   rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, bke,
@@ -814,6 +991,17 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, f
   p.ksplit = 1;
   const bool plain = (d->ksize == 1);
   p.a_im2col = plain ? 0 : 1;
+  p.es = es;
+  int up_h = 0;
+  if (try_ky(p, d->X, d->Y, d->Z, d->ksize, 1, &up_h)) {
+    rc = make_tm_im2col(&p.tmA, dy, es, d->X, d->Y, d->Z, d->Cout, d->ldy, -1, -1, 1, ch, (p.ny + 2) * d->Z, false,
+                        up_h);
+    if (rc) return rc;
+    rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, ch, ch, true);
+    if (rc) return rc;
+    const int ntiles = ((p.gX * p.nyb + p.MT - 1) / p.MT) * ((p.N + p.BN - 1) / p.BN);
+    return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+  }
   if (plain) {
     rc = make_tm_2d(&p.tmA, dy, es, p.M, d->Cout, d->ldy, ch, kBM, false);
   } else {
@@ -970,6 +1158,15 @@ static void split_free(SplitBuf* b, cudaStream_t st) {
   b->hi = b->lo = nullptr;
 }
 }  // namespace coocc
+
+// tuning hook (benchmarks / A-B tests): ky = 0 / 1 disables / enables the ky-fused path,
+// ky_mt = 128-pixel blocks per CTA tile for N <= 128 layers (1, 2 or 4); negative = keep
+extern "C" int coocc_conv_tune(int ky, int ky_mt_) {
+  if (coocc::ky_enabled < 0) { coocc::ky_enabled = 1; }
+  if (ky >= 0) coocc::ky_enabled = ky ? 1 : 0;
+  if (ky_mt_ == 1 || ky_mt_ == 2 || ky_mt_ == 4) coocc::ky_mt = ky_mt_;
+  return 0;
+}
 
 extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, float* y,
                                 long long ldo, const float* bias, int relu, float* stats,

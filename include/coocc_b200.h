@@ -67,6 +67,10 @@ int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, 
 
 /* dw[co][tap][ci] += ... (fp32; caller zero-fills dw; split-K partial sums are added atomically). */
 int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
+/* benchmark hook: ky = 0/1 disables/enables the ky-fused 3x3x3 stride-1 path (one y-extended
+ * activation tile feeds three filter taps); ky_mt = 128-pixel blocks per CTA tile for
+ * Cout <= 128 layers (1, 2, 4).  Negative values keep the current setting. */
+int coocc_conv_tune(int ky, int ky_mt);
 
 /* ------------------------------------------------------------------------------------------
  * GSFusion index pipeline (csrc/gsf_index.cu), integer-exact.

@@ -75,7 +75,7 @@ def run(X, Y, Z, Cin, Cout, k, s, dtype, what=("fwd", "dgrad", "wgrad")):
     print(tag, " ".join("%s rc=%d err=%s" % (k2, v[0], " ".join("%.2e" % e for e in v[1:])) for k2, v in res.items()), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__":  # noqa
     print("lib version", L.coocc_version(), torch.cuda.get_device_name(0))
     cases = [
         (16, 16, 8, 32, 32, 1, 1),      # plain GEMM, single k-block
