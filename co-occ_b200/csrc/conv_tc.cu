@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   // ---- tile bookkeeping (identical in every role) ---------------------------------------
   const int ntn = (p.N + p.BN - 1) / p.BN;
   // ky path: M is cut into 128-pixel blocks (x, y-block) that never straddle an x row
-  const int nmb = p.ky ? p.gX * p.nyb : (p.M + kBM - 1) / kBM;
+  const int nmb = (p.ky && !wgrad) ? p.gX * p.nyb : (p.M + kBM - 1) / kBM;
   const int ntm = (nmb + p.MT - 1) / p.MT;
   // with multicast a "tile" of the scheduler is a PAIR of M tiles (one per CTA of the cluster)
   const int crank = p.mc ? (int)cluster_ctarank() : 0;
@@ -179,7 +179,40 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 
   if (warp == 0) {
     // =========================== TMA producer ===========================================
-    if (p.ky) {
+    if (p.ky && wgrad) {
+      if (elect_one()) {
+        // ---- ky-fused wgrad producer: K blocks are the 128-pixel (x, y-block) blocks; per block the
+        //      dY^T tile (128 couts) and ONE y-extended X tile that serves the three ky taps of (kx, kz)
+        const uint32_t a_chunk = 128u * 128u;
+        const int nchA = kBM / E::CH, nchB = p.BN / E::CH;
+        const uint32_t ext_tx = (uint32_t)((p.ny + 2) * p.gZ) * 128u;
+        const uint32_t stage_b = (uint32_t)nchA * a_chunk + (uint32_t)nchB * (uint32_t)p.ext_bytes;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = cidx; tile < ntiles; tile += cnum) {
+          int t = tile;
+          const int sp = t % p.ksplit; t /= p.ksplit;
+          const int nt = t % ntn; t /= ntn;
+          const int mt = t % ntm; t /= ntm;
+          const int kx = t / 3, kz = t % 3;
+          const int it0 = (int)((long long)p.nvb * sp / p.ksplit);
+          const int it1 = (int)((long long)p.nvb * (sp + 1) / p.ksplit);
+          for (int it = it0; it < it1; ++it) {
+            const int x = it / p.nyb, yb = it - x * p.nyb;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * stage_b;
+            uint8_t* sb = sa + nchA * a_chunk;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)nchA * a_chunk + (uint32_t)nchB * ext_tx);
+            for (int j = 0; j < nchA; ++j)
+              tma_load_3d(sa + j * a_chunk, &p.tmA, &full_bar[stage], mt * kBM + j * E::CH, yb * kBM, x);
+            for (int j = 0; j < nchB; ++j)
+              tma_load_im2col_5d(sb + j * p.ext_bytes, &p.tmB, &full_bar[stage], nt * p.BN + j * E::CH, p.lo,
+                                 p.lo + yb * p.ny, p.lo + x, 0, (uint16_t)kz, (uint16_t)0, (uint16_t)kx);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (p.ky) {
       if (elect_one()) {
         // ---- ky-fused producer: per (kx, kz, k-block) one extended A tile per 128-pixel block, then
         //      the three weight tiles of ky = 0..2
@@ -333,7 +366,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================================
-    if (p.ky) {
+    if (p.ky && wgrad) {
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc(E::FMT, 1u, 1u, kBM, (uint32_t)p.BN);
+        const uint32_t a_chunk = 128u * 128u;
+        const int nchA = kBM / E::CH, nchB = p.BN / E::CH;
+        const uint32_t stage_b = (uint32_t)nchA * a_chunk + (uint32_t)nchB * (uint32_t)p.ext_bytes;
+        const uint32_t ky_step = (uint32_t)p.gZ * 128u;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = cidx; tile < ntiles; tile += cnum) {
+          const int sp = tile % p.ksplit;
+          const int nk = (int)((long long)p.nvb * (sp + 1) / p.ksplit) - (int)((long long)p.nvb * sp / p.ksplit);
+          mbar_wait(&tempty_bar[0], (uint32_t)(((tile - cidx) / cnum) & 1) ^ 1);
+          tc_fence_after();
+          for (int k = 0; k < nk; ++k) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * stage_b);
+            const uint32_t sb = sa + nchA * a_chunk;
+            for (int tt = 0; tt < 3; ++tt) {
+              const uint32_t dcol = tmem_base + (uint32_t)(tt * p.hstride);
+#pragma unroll
+              for (int ks = 0; ks < kBM / E::UK; ++ks) {
+                const uint64_t ad = make_smem_desc(sa + ks * E::MN_KSTEP, a_chunk, E::MN_SBO, E::MN_LAYOUT);
+                const uint64_t bd = make_smem_desc(sb + tt * ky_step + ks * E::MN_KSTEP, (uint32_t)p.ext_bytes,
+                                                   E::MN_SBO, E::MN_LAYOUT);
+                umma<E::TF32>(dcol, ad, bd, idesc, (k | ks) ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+          if (nk > 0) umma_commit(&tfull_bar[0]);
+          else mbar_arrive(&tfull_bar[0]);
+        }
+      }
+    } else if (p.ky) {
       if (elect_one()) {
         const uint32_t idesc = make_idesc(E::FMT, 0u, b_mn ? 1u : 0u, kBM, (uint32_t)p.BN);
         const uint32_t a_entry = (uint32_t)p.MT * (uint32_t)p.ext_bytes;
@@ -450,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         const int sp = t % p.ksplit; t /= p.ksplit;
         nt = t % ntn; t /= ntn;
         mt = t % ntm; t /= ntm;
-        tap = t * p.NT;              // first tap of the group
+        tap = t * p.NT;              // first tap of the group (ky path: t = kx * 3 + kz, see wtap)
         nk = (int)((long long)p.nvb * (sp + 1) / p.ksplit) - (int)((long long)p.nvb * sp / p.ksplit);
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -458,11 +527,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       const int nsub = p.MT * p.NT;
       for (int u = 0; u < nsub; ++u) {
       const int hh = u / p.NT, tt = u % p.NT;
-      const int wtap = tap + tt;                     // wgrad: tap of this sub-accumulator
+      // wgrad: tap of this sub-accumulator (ky path: the group is (kx, 0..2, kz))
+      const int wtap = (wgrad && p.ky) ? ((tap / 9) * 9 + tt * 3 + (tap / 3) % 3) : tap + tt;
       if (wgrad && wtap >= p.taps) continue;
       int row = (mt * p.MT + hh) * kBM + q * 32 + lane;
       bool row_ok = row < p.M;
-      if (p.ky) {
+      if (p.ky && !wgrad) {
         // block (x, yb): 128 consecutive pixels of x row `x` starting at yb * 128
         const int mb = mt * p.MT + hh;
         const int x = mb / p.nyb, in_x = (mb - x * p.nyb) * kBM + q * 32 + lane;
@@ -668,6 +738,26 @@ static int make_tm_2d(CUtensorMap* tm, const void* ptr, int es, long long rows, 
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "[coocc_b200] cuTensorMapEncodeTiled failed: %d (rows=%lld cols=%lld ld=%lld box=%d,%d)\n",
             (int)r, rows, cols, ld, box_c, box_r);
+    return COOCC_ERR_TENSORMAP;
+  }
+  return 0;
+}
+
+// [X][rows][cols] tensor (row stride ld elements, x stride rows*ld), box {box_c, box_r, 1}: rows past
+// the end of an x slab are zero-filled instead of running into the next slab
+static int make_tm_3d(CUtensorMap* tm, const void* ptr, int es, long long X, long long rows, long long cols,
+                      long long ld, int box_c, int box_r, bool mn_major) {
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)X};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * rows};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_r, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = (mn_major && es == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = g_encodeTiled(tm, tm_dtype(es), 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[coocc_b200] cuTensorMapEncodeTiled(3d) failed: %d\n", (int)r);
     return COOCC_ERR_TENSORMAP;
   }
   return 0;
@@ -1019,6 +1109,26 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, f
   return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
 }
 
+// split-K factor of a wgrad launch: tiles are dealt round-robin to the persistent CTAs, so pick the
+// factor whose tile count fills whole waves (297 tiles on 148 SMs cost 3 waves, 296 cost 2)
+static int pick_wgrad_ksplit(int base_tiles, int nvb) {
+  int ks = 1;
+  // every split keeps >= 8 k-blocks so the pipeline fill / atomic epilogue stay amortised
+  int max_ks = nvb / 8;
+  if (max_ks > 48) max_ks = 48;
+  if (max_ks < 1) max_ks = 1;
+  double best = -1.0;
+  for (int c = 1; c <= max_ks; ++c) {
+    const long long tiles = (long long)base_tiles * c;
+    const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
+    double eff = (double)tiles / (double)(waves * g_num_sms);
+    if (tiles < g_num_sms) eff *= 0.9;                 // prefer filling the machine at least once
+    eff -= 0.002 * c;                                  // slight preference for fewer atomic passes
+    if (eff > best) { best = eff; ks = c; }
+  }
+  return ks;
+}
+
 // dW[co, tap, ci] += sum_v dY[v, co] X[v*s + tap - pad, ci]   (dw must be zero-filled by the caller)
 static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
   int rc = check_desc(d);
@@ -1044,6 +1154,32 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   p.lo = -(d->ksize / 2);
   p.out = dw; p.ldc = d->Cin;
   p.nvb = (int)((Vo + ch - 1) / ch);
+  // ky-fused wgrad (bf16): 128 couts x (3 ky taps x <= 128 cins) accumulators; per 128-pixel block one
+  // dY^T tile and one y-extended X tile (see try_ky) -> 170 MACs per operand element pulled from L2
+  // versus 96 (NT = 3) / 128 (MT = 2) of the plain shapes below
+  {
+    TcParams q = p;
+    q.BN = ((d->Cin + ch - 1) / ch) * ch;
+    if (q.BN > 128) q.BN = 128;
+    int up_h = 0;
+    if (es == 2 && try_ky(q, d->X, d->Y, d->Z, d->ksize, d->stride, &up_h)) {
+      p = q;
+      p.MT = 1; p.NT = 3; p.hstride = 128; p.nacc = 1;
+      p.nvb = p.gX * p.nyb;
+      const int stage = (kBM / ch) * 128 * 128 + (p.BN / ch) * p.ext_bytes;
+      p.nstages = kRingBytes / stage;
+      if (p.nstages > kStages) p.nstages = kStages;
+      const int base_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN) * 9;
+      p.ksplit = pick_wgrad_ksplit(base_tiles, p.nvb);
+      rc = make_tm_3d(&p.tmA, dy, es, d->X, (long long)d->Y * d->Z, d->Cout, d->ldy, ch, 128, true);
+      if (rc) return rc;
+      rc = make_tm_im2col(&p.tmB, x, es, d->X, d->Y, d->Z, d->Cin, d->ldx, -1, -1, 1, ch, (p.ny + 2) * d->Z, true,
+                          up_h);
+      if (rc) return rc;
+      p.a_im2col = 1;
+      return launch<2>(p, base_tiles * p.ksplit, (cudaStream_t)stream);
+    }
+  }
   // CTA tile shape (fewer operand bytes per MAC, like fprop):
   //   Cout >= 256          : two cout tiles share one X tile        (MT = 2, BN <= 256)
   //   Cout <= 128, 27 taps : three taps share one dY^T tile          (NT = 3, BN <= 128)
@@ -1075,22 +1211,7 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   const int base_tiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN) * ((taps + p.NT - 1) / p.NT);
   // split-K factor: tiles are dealt round-robin to the persistent CTAs, so pick the factor whose
   // tile count fills whole waves (297 tiles on 148 SMs cost 3 waves, 296 cost 2)
-  int ks = 1;
-  {
-    // every split keeps >= 8 k-blocks so the pipeline fill / atomic epilogue stay amortised
-    int max_ks = p.nvb / 8;
-    if (max_ks > 48) max_ks = 48;
-    if (max_ks < 1) max_ks = 1;
-    double best = -1.0;
-    for (int c = 1; c <= max_ks; ++c) {
-      const long long tiles = (long long)base_tiles * c;
-      const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
-      double eff = (double)tiles / (double)(waves * g_num_sms);
-      if (tiles < g_num_sms) eff *= 0.9;                 // prefer filling the machine at least once
-      eff -= 0.002 * c;                                  // slight preference for fewer atomic passes
-      if (eff > best) { best = eff; ks = c; }
-    }
-  }
+  const int ks = pick_wgrad_ksplit(base_tiles, p.nvb);
   p.ksplit = ks;
   const bool plain = (d->ksize == 1 && d->stride == 1);
   p.a_im2col = plain ? 0 : 1;

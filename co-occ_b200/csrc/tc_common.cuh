@@ -64,6 +64,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const void* tmap, uint64
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem, const void* tmap, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // same, multicast: the box lands at the same shared-memory offset in every CTA of `mask`, and each
 // destination CTA's mbarrier (same offset) receives the complete_tx
 __device__ __forceinline__ void tma_load_2d_mc(void* smem, const void* tmap, uint64_t* bar, int c0,

@@ -17,8 +17,8 @@ if __name__ == "__main__":
         (40, 40, 16, 64, 512, 3, 1),      # two N tiles
         (64, 40, 16, 256, 128, 3, 1),     # 4 k-blocks per tap
     ]
-    what = ("fwd", "dgrad")
-    for mt in (2, 4, 1):
+    what = ("fwd", "dgrad", "wgrad")
+    for mt in (2, 4):
         L.coocc_conv_tune(1, mt)
         print("== ky path, MT=%d" % mt)
         for dtype in (1, 0):
@@ -40,13 +40,15 @@ if __name__ == "__main__":
         y = torch.empty(X * Y * Z, Cout, device=dev)
         dx = torch.empty(X * Y * Z, Cin, device=dev)
         stats = torch.zeros(2, Cout, device=dev)
+        dw = torch.zeros(Cout, 27 * Cin, device=dev)
         d = _lib.ConvDesc(X, Y, Z, Cin, Cout, 3, 1, dtype, Cin, Cout)
         fl = 2.0 * X * Y * Z * 27 * Cin * Cout
-        for (ky, mt) in ((0, 2), (1, 1), (1, 2), (1, 4)):
+        for (ky, mt) in ((0, 2), (1, 2), (1, 4)):
             L.coocc_conv_tune(ky, mt)
             out = []
             for name, fn in (("fwd", lambda: L.coocc_conv3d_fwd(ctypes.byref(d), xc.data_ptr(), wc.data_ptr(), y.data_ptr(), Cout, None, 0, stats.data_ptr(), stream())),
-                             ("dgrad", lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), gyc.data_ptr(), wc.data_ptr(), dx.data_ptr(), Cin, stream()))):
+                             ("dgrad", lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), gyc.data_ptr(), wc.data_ptr(), dx.data_ptr(), Cin, stream())),
+                             ("wgrad", lambda: L.coocc_conv3d_wgrad(ctypes.byref(d), xc.data_ptr(), gyc.data_ptr(), dw.data_ptr(), stream()))):
                 for _ in range(2):
                     fn()
                 torch.cuda.synchronize()
