@@ -20,7 +20,8 @@ ERRORS = {-1: "invalid argument", -2: "pointer/stride not 16-byte aligned", -3: 
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [("X", c_int), ("Y", c_int), ("Z", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("ksize", c_int), ("stride", c_int), ("dtype", c_int), ("ldx", c_ll), ("ldy", c_ll)]
+                ("ksize", c_int), ("stride", c_int), ("dtype", c_int), ("ldx", c_ll), ("ldy", c_ll),
+                ("out_bf16", c_int)]
 
 
 def build(verbose=False):
@@ -58,12 +59,12 @@ _SIGS = {
     "coocc_gsf_scatter_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_bn_finalize": (c_int, [c_void_p, c_int, c_ll, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "coocc_bn_act_fwd": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p]),
-    "coocc_bn_act_bwd_reduce": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "coocc_bn_act_bwd_reduce": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "coocc_bn_act_bwd_apply": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_dilate2": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
-    "coocc_trilinear_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
-    "coocc_trilinear_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
-    "coocc_trilinear_wgrad": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_trilinear_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "coocc_trilinear_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "coocc_trilinear_wgrad": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p]),
     "coocc_render_box": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "coocc_render_box_gather": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "coocc_render_box_scatter_add": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),

@@ -29,6 +29,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_bf16.h>
+
 #include "../../include/coocc_b200.h"
 #include "tc_common.cuh"
 
@@ -76,6 +78,7 @@ struct TcParams {
   const float* bias;
   int relu;
   int accum;          // epilogue adds the previous contents of out (multi-pass precision split)
+  int out_bf16;       // fprop / dgrad: `out` is a bf16 matrix (row stride ldc in bf16 elements)
   float* stats;        // [2][N] sum / sum of squares over rows, or nullptr
   // wgrad
   int nvb;             // number of voxel (K) blocks
@@ -617,7 +620,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
               atomicAdd(&p.stats[p.N + col], ss[0]);
             }
           }
-          if (row_ok) {
+          if (row_ok && p.out_bf16) {
+            // bf16 activations: the next convolution's operand type, written straight from the epilogue
+            __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldc + col0;
+            if (col0 + 32 <= p.N && (p.ldc & 7) == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint32_t w4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float a = __uint_as_float(v[i + 2 * j]), b = __uint_as_float(v[i + 2 * j + 1]);
+                  if (p.bias) { a += p.bias[col0 + i + 2 * j]; b += p.bias[col0 + i + 2 * j + 1]; }
+                  if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                  w4[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(ob + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (col0 + i < p.N) {
+                  float f = __uint_as_float(v[i]);
+                  if (p.bias) f += p.bias[col0 + i];
+                  if (p.relu) f = fmaxf(f, 0.f);
+                  ob[i] = __float2bfloat16_rn(f);
+                }
+              }
+            }
+          } else if (row_ok) {
             if (vec) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
@@ -859,7 +890,7 @@ static int pick_ksplit(int ntiles, int nk_total) {
   return ks < 1 ? 1 : ks;
 }
 
-static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
+static int prepare_split(TcParams& p, int nk_total, cudaStream_t st, bool zero_out = true) {
   // Several 128-row MMA tiles per CTA tile share one B tile: fewer operand bytes per MAC have to
   // be pulled from L2 into the SM (the measured limiter, profiles/r01_ncu_full_tc_conv_bf16.summary.txt).
   //   BN <= 128: MT = 2, two TMEM buffers (epilogue overlaps the next tile)
@@ -902,12 +933,56 @@ static int prepare_split(TcParams& p, int nk_total, cudaStream_t st) {
   }
   p.ksplit = 1;
   if (p.bias == nullptr && !p.relu) p.ksplit = pick_ksplit(ntiles, nk_total);
-  if (p.ksplit > 1 && !p.accum) {
+  if (p.ksplit > 1 && !p.accum && zero_out) {
     if (cudaMemset2DAsync(p.out, (size_t)p.ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), (size_t)p.M, st) !=
         cudaSuccess)
       return COOCC_ERR_CUDA;
   }
   return 0;
+}
+
+// fp32 [M, N] (row stride lds) -> bf16 (row stride ldd): epilogue of split-K launches whose output is bf16
+__global__ void __launch_bounds__(256) f32_to_bf16_rows_kernel(const float* __restrict__ src, long long lds, int M,
+                                                               int N, __nv_bfloat16* __restrict__ dst, long long ldd) {
+  const long long total = (long long)M * N;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long r = i / N;
+    const int c = (int)(i % N);
+    dst[r * ldd + c] = __float2bfloat16_rn(src[r * lds + c]);
+  }
+}
+
+// Split-K launches accumulate with fp32 atomics; when the caller wants bf16 the partial sums go to
+// a stream-ordered fp32 scratch matrix that is converted afterwards (only the small, under-filled
+// layers take this route).
+struct SplitScratch {
+  float* tmp = nullptr;
+  void* real_out = nullptr;
+  long long real_ld = 0;
+};
+static int split_scratch_begin(TcParams& p, SplitScratch& sc, cudaStream_t st) {
+  if (p.ksplit <= 1) return 0;
+  if (p.out_bf16) {
+    const long long ld = ((long long)p.N + 3) / 4 * 4;
+    if (cudaMallocAsync(reinterpret_cast<void**>(&sc.tmp), (size_t)p.M * ld * sizeof(float), st) != cudaSuccess)
+      return COOCC_ERR_CUDA;
+    sc.real_out = p.out; sc.real_ld = p.ldc;
+    p.out = sc.tmp; p.ldc = ld; p.out_bf16 = 0;
+  }
+  if (!p.accum &&
+      cudaMemset2DAsync(p.out, (size_t)p.ldc * sizeof(float), 0, (size_t)p.N * sizeof(float), (size_t)p.M, st) != cudaSuccess)
+    return COOCC_ERR_CUDA;
+  return 0;
+}
+static int split_scratch_end(TcParams& p, SplitScratch& sc, cudaStream_t st) {
+  if (!sc.tmp) return 0;
+  long long blocks = ((long long)p.M * p.N + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_bf16_rows_kernel<<<(int)blocks, 256, 0, st>>>(sc.tmp, p.ldc, p.M, p.N,
+                                                      reinterpret_cast<__nv_bfloat16*>(sc.real_out), sc.real_ld);
+  const int rc = cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+  cudaFreeAsync(sc.tmp, st);
+  return rc;
 }
 
 // ky-fused path for 3x3x3 stride-1 fprop / dgrad.  The im2col A operand of the three taps
@@ -985,7 +1060,7 @@ static int check_desc(const coocc_conv_desc* d) {
   return 0;
 }
 
-static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, float* y, long long ldo,
+static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, void* yv, long long ldo,
                     const float* bias, int relu, float* stats, int accum, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
@@ -994,6 +1069,7 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
   const int taps = d->ksize == 3 ? 27 : 1;
   const int oX = out_dim(d->X, d->ksize, d->stride), oY = out_dim(d->Y, d->ksize, d->stride),
             oZ = out_dim(d->Z, d->ksize, d->stride);
+  float* y = reinterpret_cast<float*>(yv);
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.mode = MODE_FPROP;
@@ -1007,6 +1083,8 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
   p.cstride = d->stride;
   p.lo = -(d->ksize / 2);
   p.out = y; p.ldc = ldo; p.bias = bias; p.relu = relu; p.stats = stats; p.accum = accum;
+  p.out_bf16 = d->out_bf16 ? 1 : 0;
+  if (p.out_bf16 && accum) return COOCC_ERR_ARG;
   p.ksplit = 1;
   const int bke = 128 / es;
   const bool plain = (d->ksize == 1 && d->stride == 1);
@@ -1031,7 +1109,9 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
   }
   if (rc) return rc;
   float* stats_after = nullptr;
-  if ((rc = prepare_split(p, taps * ((d->Cin + bke - 1) / bke), (cudaStream_t)stream))) return rc;
+  if ((rc = prepare_split(p, taps * ((d->Cin + bke - 1) / bke), (cudaStream_t)stream, false))) return rc;
+  SplitScratch sc;
+  if ((rc = split_scratch_begin(p, sc, (cudaStream_t)stream))) return rc;
   // weight rows; with multicast each CTA of a pair fetches half of the N tile
   rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, bke,
                   p.mc ? p.BN / 2 : p.BN, false);
@@ -1045,12 +1125,13 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, floa
     colstats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p.out, p.ldc, p.M, p.N, stats_after);
     rc = cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
   }
-  return rc;
+  const int rc2 = split_scratch_end(p, sc, (cudaStream_t)stream);
+  return rc ? rc : rc2;
 }
 
 // dX[v, ci] = sum_{tap,co} dY[v - tap + pad, co] W[co, tap, ci]; stride-1 convolutions only
 // (for stride 2 the caller scatters dY onto the input lattice first, see conv3d_dgrad docs).
-static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, float* dx, long long ldo,
+static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, void* dxv, long long ldo,
                       int accum, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
@@ -1059,6 +1140,7 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, f
   const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
   const int taps = d->ksize == 3 ? 27 : 1;
   const int ch = 128 / es;
+  float* dx = reinterpret_cast<float*>(dxv);
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.mode = MODE_DGRAD;
@@ -1078,6 +1160,8 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, f
   p.cstride = 1;
   p.lo = -(d->ksize / 2);
   p.out = dx; p.ldc = ldo; p.bias = nullptr; p.relu = 0; p.stats = nullptr; p.accum = accum;
+  p.out_bf16 = d->out_bf16 ? 1 : 0;
+  if (p.out_bf16 && accum) return COOCC_ERR_ARG;
   p.ksplit = 1;
   const bool plain = (d->ksize == 1);
   p.a_im2col = plain ? 0 : 1;
@@ -1103,10 +1187,14 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, f
   rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, ch, ch, true);
   if (rc) return rc;
   p.es = es;
-  if ((rc = prepare_split(p, taps * ((d->Cout + ch - 1) / ch), (cudaStream_t)stream))) return rc;
+  if ((rc = prepare_split(p, taps * ((d->Cout + ch - 1) / ch), (cudaStream_t)stream, false))) return rc;
+  SplitScratch sc;
+  if ((rc = split_scratch_begin(p, sc, (cudaStream_t)stream))) return rc;
   const int ntm_ = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
   const int ntiles = (p.mc ? (ntm_ + 1) / 2 : ntm_) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
-  return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+  rc = es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+  const int rc2 = split_scratch_end(p, sc, (cudaStream_t)stream);
+  return rc ? rc : rc2;
 }
 
 // split-K factor of a wgrad launch: tiles are dealt round-robin to the persistent CTAs, so pick the
@@ -1289,7 +1377,7 @@ extern "C" int coocc_conv_tune(int ky, int ky_mt_) {
   return 0;
 }
 
-extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, float* y,
+extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, void* y,
                                 long long ldo, const float* bias, int relu, float* stats,
                                 void* stream) {
   if (!d) return COOCC_ERR_ARG;
@@ -1310,7 +1398,7 @@ extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const v
   return rc;
 }
 
-extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, float* dx,
+extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, void* dx,
                                   long long ldo, void* stream) {
   if (!d) return COOCC_ERR_ARG;
   if (d->dtype != COOCC_DTYPE_TF32X3) return dgrad_impl(d, dy, w, dx, ldo, 0, stream);

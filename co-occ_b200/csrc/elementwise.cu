@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "../../include/coocc_b200.h"
+#include "act_types.cuh"
 
 namespace coocc {
 
@@ -36,30 +37,21 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, doubl
   }
 }
 
-__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&a);
-  u.y = *reinterpret_cast<uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(p) = u;
-}
-
 // out = relu?( (x - mean) * invstd * gamma + beta (+ residual) )
-template <typename OutT>
-__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ x, long long ldx,
+template <typename T>
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x, long long ldx,
                                                          long long V, int C,
                                                          const float* __restrict__ mean_invstd,
                                                          const float* __restrict__ gamma,
                                                          const float* __restrict__ beta,
-                                                         const float* __restrict__ residual, long long ldr,
-                                                         int relu, OutT* __restrict__ out, long long ldo) {
+                                                         const T* __restrict__ residual, long long ldr,
+                                                         int relu, T* __restrict__ out, long long ldo) {
   const int c4 = C >> 2;
   const long long total = V * c4;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const long long r = i / c4;
     const int c = (int)(i % c4) * 4;
-    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float4 xv = load4(x + r * ldx + c);
     const float4 m = *reinterpret_cast<const float4*>(mean_invstd + c);
     const float4 is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
     const float4 g = *reinterpret_cast<const float4*>(gamma + c);
@@ -70,7 +62,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
     y.z = (xv.z - m.z) * is.z * g.z + b.z;
     y.w = (xv.w - m.w) * is.w * g.w + b.w;
     if (residual != nullptr) {
-      const float4 rv = *reinterpret_cast<const float4*>(residual + r * ldr + c);
+      const float4 rv = load4(residual + r * ldr + c);
       y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
     }
     if (relu) {
@@ -82,9 +74,10 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
 
 // sums[c] = sum_r dz, sums[C + c] = sum_r dz * xhat, dz = dout * [out > 0] (relu) or dout
 // block = 32 x 8: threadIdx.x -> channel group (4 channels), threadIdx.y -> row lane.
+template <typename T>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
-    const float* __restrict__ dout, long long ldd, const float* __restrict__ out, long long ldo,
-    const float* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
+    const T* __restrict__ dout, long long ldd, const T* __restrict__ out, long long ldo,
+    const T* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
     int relu, int rows_per_block, float* __restrict__ sums) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
@@ -94,13 +87,13 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     const long long r1 = min(V, r0 + rows_per_block);
     for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
-      float4 d = *reinterpret_cast<const float4*>(dout + r * ldd + c);
+      float4 d = load4(dout + r * ldd + c);
       if (relu) {
-        const float4 o = *reinterpret_cast<const float4*>(out + r * ldo + c);
+        const float4 o = load4(out + r * ldo + c);
         d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
         d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
       }
-      const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+      const float4 xv = load4(x + r * ldx + c);
       s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
       s2.x += d.x * (xv.x - m.x) * is.x; s2.y += d.y * (xv.y - m.y) * is.y;
       s2.z += d.z * (xv.z - m.z) * is.z; s2.w += d.w * (xv.w - m.w) * is.w;
@@ -124,25 +117,25 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
 }
 
 // dx = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  dres = dz (optional)
-template <typename OutT>
+template <typename T>
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
-    const float* __restrict__ dout, long long ldd, const float* __restrict__ out, long long ldo,
-    const float* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
-    const float* __restrict__ gamma, const float* __restrict__ sums, int relu, OutT* __restrict__ dx,
-    long long lddx, float* __restrict__ dres, long long lddr, float inv_n) {
+    const T* __restrict__ dout, long long ldd, const T* __restrict__ out, long long ldo,
+    const T* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
+    const float* __restrict__ gamma, const float* __restrict__ sums, int relu, T* __restrict__ dx,
+    long long lddx, T* __restrict__ dres, long long lddr, float inv_n) {
   const int c4 = C >> 2;
   const long long total = V * c4;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const long long r = i / c4;
     const int c = (int)(i % c4) * 4;
-    float4 d = *reinterpret_cast<const float4*>(dout + r * ldd + c);
+    float4 d = load4(dout + r * ldd + c);
     if (relu) {
-      const float4 o = *reinterpret_cast<const float4*>(out + r * ldo + c);
+      const float4 o = load4(out + r * ldo + c);
       d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
       d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
     }
-    if (dres != nullptr) *reinterpret_cast<float4*>(dres + r * lddr + c) = d;
-    const float4 xv = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    if (dres != nullptr) store4(dres + r * lddr + c, d);
+    const float4 xv = load4(x + r * ldx + c);
     const float4 m = *reinterpret_cast<const float4*>(mean_invstd + c);
     const float4 is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
     const float4 g = *reinterpret_cast<const float4*>(gamma + c);
@@ -198,18 +191,21 @@ extern "C" int coocc_bn_finalize(const float* stats, int C, long long count, flo
   return CK_LAUNCH();
 }
 
-extern "C" int coocc_bn_act_fwd(const float* x, long long ldx, long long V, int C, const float* mean_invstd,
-                                const float* gamma, const float* beta, const float* residual, long long ldr,
-                                int relu, void* out, long long ldo, int out_bf16, void* stream) {
+// act_bf16 = 1: every activation tensor of the call (x, residual, out / dout, out, x, dx, dres) is
+// stored as bf16; 0: fp32.  Statistics, gamma/beta and the arithmetic are fp32 either way.
+extern "C" int coocc_bn_act_fwd(const void* x, long long ldx, long long V, int C, const float* mean_invstd,
+                                const float* gamma, const float* beta, const void* residual, long long ldr,
+                                int relu, void* out, long long ldo, int act_bf16, void* stream) {
   if (!x || !mean_invstd || !gamma || !beta || !out || (C & 3) || (ldx & 3) || (ldo & 3)) return COOCC_ERR_ARG;
   if (residual && (ldr & 3)) return COOCC_ERR_ARG;
   const int g = grid_for(V * (C >> 2));
-  if (out_bf16)
-    bn_act_fwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, V, C, mean_invstd, gamma, beta, residual,
-                                                                        ldr, relu, (__nv_bfloat16*)out, ldo);
+  if (act_bf16)
+    bn_act_fwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, ldx, V, C, mean_invstd, gamma, beta, (const __nv_bfloat16*)residual, ldr, relu,
+        (__nv_bfloat16*)out, ldo);
   else
-    bn_act_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, V, C, mean_invstd, gamma, beta, residual, ldr,
-                                                                relu, (float*)out, ldo);
+    bn_act_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, V, C, mean_invstd, gamma, beta,
+                                                                (const float*)residual, ldr, relu, (float*)out, ldo);
   return CK_LAUNCH();
 }
 
@@ -218,9 +214,9 @@ extern "C" int coocc_bn_act_fwd(const float* x, long long ldx, long long V, int 
 //   apply : dx = gamma*invstd*(dz - sums[0:C]/count - xhat*sums[C:2C]/count); dres = dz (optional)
 // count = number of rows the statistics were taken over (V, or the sum of V over all ranks).
 // After the reduce, sums[0:C] = dbeta and sums[C:2C] = dgamma (of this rank / of all ranks).
-extern "C" int coocc_bn_act_bwd_reduce(const float* dout, long long ldd, const float* out, long long ldo,
-                                       const float* x, long long ldx, long long V, int C, const float* mean_invstd,
-                                       int relu, float* sums, void* stream) {
+extern "C" int coocc_bn_act_bwd_reduce(const void* dout, long long ldd, const void* out, long long ldo,
+                                       const void* x, long long ldx, long long V, int C, const float* mean_invstd,
+                                       int relu, float* sums, int act_bf16, void* stream) {
   if (!dout || !x || !mean_invstd || !sums || (C & 3) || (ldd & 3) || (ldx & 3)) return COOCC_ERR_ARG;
   if (relu && (!out || (ldo & 3))) return COOCC_ERR_ARG;
   const int cgroups = (C / 4 + 31) / 32;
@@ -230,15 +226,22 @@ extern "C" int coocc_bn_act_bwd_reduce(const float* dout, long long ldd, const f
     rows_per_block *= 2;
     nby = (V + rows_per_block - 1) / rows_per_block;
   }
-  bn_act_bwd_reduce_kernel<<<dim3(cgroups, (unsigned)nby), dim3(32, 8), 0, (cudaStream_t)stream>>>(
-      dout, ldd, out, ldo, x, ldx, V, C, mean_invstd, relu, rows_per_block, sums);
+  const dim3 grid(cgroups, (unsigned)nby), block(32, 8);
+  if (act_bf16)
+    bn_act_bwd_reduce_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)x, ldx, V, C,
+        mean_invstd, relu, rows_per_block, sums);
+  else
+    bn_act_bwd_reduce_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(
+        (const float*)dout, ldd, (const float*)out, ldo, (const float*)x, ldx, V, C, mean_invstd, relu,
+        rows_per_block, sums);
   return CK_LAUNCH();
 }
 
-extern "C" int coocc_bn_act_bwd_apply(const float* dout, long long ldd, const float* out, long long ldo,
-                                      const float* x, long long ldx, long long V, int C, const float* mean_invstd,
+extern "C" int coocc_bn_act_bwd_apply(const void* dout, long long ldd, const void* out, long long ldo,
+                                      const void* x, long long ldx, long long V, int C, const float* mean_invstd,
                                       const float* gamma, int relu, const float* sums, long long count, void* dx,
-                                      long long lddx, int dx_bf16, float* dres, long long lddr, void* stream) {
+                                      long long lddx, int act_bf16, void* dres, long long lddr, void* stream) {
   if (!dout || !x || !mean_invstd || !gamma || !sums || !dx || (C & 3) || (ldd & 3) || (ldx & 3) || (lddx & 3) ||
       count < 1)
     return COOCC_ERR_ARG;
@@ -246,12 +249,14 @@ extern "C" int coocc_bn_act_bwd_apply(const float* dout, long long ldd, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const int g = grid_for(V * (C >> 2));
   const float inv_n = (float)(1.0 / (double)count);
-  if (dx_bf16)
-    bn_act_bwd_apply_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(dout, ldd, out, ldo, x, ldx, V, C, mean_invstd, gamma, sums,
-                                                             relu, (__nv_bfloat16*)dx, lddx, dres, lddr, inv_n);
+  if (act_bf16)
+    bn_act_bwd_apply_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(
+        (const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)x, ldx, V, C,
+        mean_invstd, gamma, sums, relu, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddr, inv_n);
   else
-    bn_act_bwd_apply_kernel<float><<<g, 256, 0, st>>>(dout, ldd, out, ldo, x, ldx, V, C, mean_invstd, gamma, sums, relu,
-                                                     (float*)dx, lddx, dres, lddr, inv_n);
+    bn_act_bwd_apply_kernel<float><<<g, 256, 0, st>>>((const float*)dout, ldd, (const float*)out, ldo, (const float*)x,
+                                                     ldx, V, C, mean_invstd, gamma, sums, relu, (float*)dx, lddx,
+                                                     (float*)dres, lddr, inv_n);
   return CK_LAUNCH();
 }
 

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "../../include/coocc_b200.h"
+#include "act_types.cuh"
 
 namespace coocc {
 
@@ -27,10 +28,11 @@ struct TlDims {
   float fx, fy, fz;   // in / out
 };
 
-__global__ void __launch_bounds__(256) trilinear_fwd_kernel(const float* __restrict__ src, long long lds,
-                                                            TlDims d, int C, const float* __restrict__ base,
+template <typename T>
+__global__ void __launch_bounds__(256) trilinear_fwd_kernel(const T* __restrict__ src, long long lds,
+                                                            TlDims d, int C, const T* __restrict__ base,
                                                             long long ldb, const float* __restrict__ wts,
-                                                            long long ldw, float* __restrict__ out, long long ldo) {
+                                                            long long ldw, T* __restrict__ out, long long ldo) {
   const int c4 = C >> 2;
   const long long total = (long long)d.oX * d.oY * d.oZ * c4;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(256) trilinear_fwd_kernel(const float* __restr
     for (int k = 0; k < 8; ++k) {
       const int xi = (k & 4) ? x1 : x0, yi = (k & 2) ? y1 : y0, zi = (k & 1) ? z1 : z0;
       const float w = ((k & 4) ? lx : 1.f - lx) * ((k & 2) ? ly : 1.f - ly) * ((k & 1) ? lz : 1.f - lz);
-      const float4 s = *reinterpret_cast<const float4*>(src + (((long long)xi * d.sY + yi) * d.sZ + zi) * lds + c);
+      const float4 s = load4(src + (((long long)xi * d.sY + yi) * d.sZ + zi) * lds + c);
       acc.x += w * s.x; acc.y += w * s.y; acc.z += w * s.z; acc.w += w * s.w;
     }
     if (wts != nullptr) {
@@ -55,10 +57,10 @@ __global__ void __launch_bounds__(256) trilinear_fwd_kernel(const float* __restr
       acc.x *= w; acc.y *= w; acc.z *= w; acc.w *= w;
     }
     if (base != nullptr) {
-      const float4 b = *reinterpret_cast<const float4*>(base + v * ldb + c);
+      const float4 b = load4(base + v * ldb + c);
       acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
     }
-    *reinterpret_cast<float4*>(out + v * ldo + c) = acc;
+    store4(out + v * ldo + c, acc);
   }
 }
 
@@ -78,9 +80,10 @@ constexpr int kTlMax = 24;     // enough for x8 upsampling (<= 2*8 + 3 candidate
 // one warp per input voxel (lanes = channel groups of 4): the three per-axis weight lists are built
 // once per voxel (lane j computes candidate j) in shared memory, the inner loops are pure
 // multiply-adds over coalesced 16-byte loads
-__global__ void __launch_bounds__(256) trilinear_bwd_kernel(const float* __restrict__ dout, long long ldd,
+template <typename T>
+__global__ void __launch_bounds__(256) trilinear_bwd_kernel(const T* __restrict__ dout, long long ldd,
                                                             TlDims d, int C, const float* __restrict__ wts,
-                                                            long long ldw, float* __restrict__ dsrc,
+                                                            long long ldw, T* __restrict__ dsrc,
                                                             long long lds) {
   __shared__ float sw[8][3][kTlMax];
   const int wid = threadIdx.x >> 5;
@@ -127,18 +130,19 @@ __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const float* __restr
           if (w == 0.f) continue;
           const long long ov = row0 + iz;
           if (wts != nullptr) w *= wts[ov * ldw];
-          const float4 g = *reinterpret_cast<const float4*>(dout + ov * ldd + c);
+          const float4 g = load4(dout + ov * ldd + c);
           acc.x += w * g.x; acc.y += w * g.y; acc.z += w * g.z; acc.w += w * g.w;
         }
       }
     }
-    *reinterpret_cast<float4*>(dsrc + v * lds + c) = acc;
+    store4(dsrc + v * lds + c, acc);
   }
 }
 
 // dw[v] = sum_c dout[v, c] * interpolate(src)[v, c]     (one warp per output voxel)
-__global__ void __launch_bounds__(256) trilinear_wgrad_kernel(const float* __restrict__ dout, long long ldd,
-                                                              const float* __restrict__ src, long long lds,
+template <typename T>
+__global__ void __launch_bounds__(256) trilinear_wgrad_kernel(const T* __restrict__ dout, long long ldd,
+                                                              const T* __restrict__ src, long long lds,
                                                               TlDims d, int C, float* __restrict__ dw,
                                                               long long lddw) {
   const long long v = blockIdx.x * 8LL + (threadIdx.x >> 5);
@@ -157,9 +161,9 @@ __global__ void __launch_bounds__(256) trilinear_wgrad_kernel(const float* __res
     for (int k = 0; k < 8; ++k) {
       const int xi = (k & 4) ? x1 : x0, yi = (k & 2) ? y1 : y0, zi = (k & 1) ? z1 : z0;
       const float w = ((k & 4) ? lx : 1.f - lx) * ((k & 2) ? ly : 1.f - ly) * ((k & 1) ? lz : 1.f - lz);
-      u += w * src[(((long long)xi * d.sY + yi) * d.sZ + zi) * lds + c];
+      u += w * load1(src + (((long long)xi * d.sY + yi) * d.sZ + zi) * lds + c);
     }
-    acc += u * dout[v * ldd + c];
+    acc += u * load1(dout + v * ldd + c);
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -185,32 +189,51 @@ static int tl_grid(long long total) {
 using namespace coocc;
 #define CK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA)
 
-extern "C" int coocc_trilinear_fwd(const float* src, long long lds, int sX, int sY, int sZ, int C,
-                                   const float* base, long long ldb, const float* wts, long long ldw, float* out,
-                                   long long ldo, int oX, int oY, int oZ, void* stream) {
+typedef __nv_bfloat16 bf16_t;
+
+extern "C" int coocc_trilinear_fwd(const void* src, long long lds, int sX, int sY, int sZ, int C,
+                                   const void* base, long long ldb, const float* wts, long long ldw, void* out,
+                                   long long ldo, int oX, int oY, int oZ, int act_bf16, void* stream) {
   if (!src || !out || (C & 3) || (lds & 3) || (ldo & 3) || (base && (ldb & 3))) return COOCC_ERR_ARG;
   const TlDims d = make_dims(sX, sY, sZ, oX, oY, oZ);
-  trilinear_fwd_kernel<<<tl_grid((long long)oX * oY * oZ * (C >> 2)), 256, 0, (cudaStream_t)stream>>>(
-      src, lds, d, C, base, ldb, wts, ldw, out, ldo);
+  const int g = tl_grid((long long)oX * oY * oZ * (C >> 2));
+  if (act_bf16)
+    trilinear_fwd_kernel<bf16_t><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16_t*)src, lds, d, C, (const bf16_t*)base,
+                                                                    ldb, wts, ldw, (bf16_t*)out, ldo);
+  else
+    trilinear_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, lds, d, C, (const float*)base,
+                                                                   ldb, wts, ldw, (float*)out, ldo);
   return CK_LAUNCH();
 }
 
-extern "C" int coocc_trilinear_bwd(const float* dout, long long ldd, int oX, int oY, int oZ, int C,
-                                   const float* wts, long long ldw, float* dsrc, long long lds, int sX, int sY,
-                                   int sZ, void* stream) {
+extern "C" int coocc_trilinear_bwd(const void* dout, long long ldd, int oX, int oY, int oZ, int C,
+                                   const float* wts, long long ldw, void* dsrc, long long lds, int sX, int sY,
+                                   int sZ, int act_bf16, void* stream) {
   if (!dout || !dsrc || (C & 3) || (lds & 3) || (ldd & 3)) return COOCC_ERR_ARG;
   const TlDims d = make_dims(sX, sY, sZ, oX, oY, oZ);
   const long long Vs = (long long)sX * sY * sZ;
-  trilinear_bwd_kernel<<<(unsigned)((Vs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dout, ldd, d, C, wts, ldw, dsrc, lds);
+  const unsigned g = (unsigned)((Vs + 7) / 8);
+  if (act_bf16)
+    trilinear_bwd_kernel<bf16_t><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16_t*)dout, ldd, d, C, wts, ldw,
+                                                                    (bf16_t*)dsrc, lds);
+  else
+    trilinear_bwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dout, ldd, d, C, wts, ldw,
+                                                                   (float*)dsrc, lds);
   return CK_LAUNCH();
 }
 
-extern "C" int coocc_trilinear_wgrad(const float* dout, long long ldd, const float* src, long long lds, int sX,
+extern "C" int coocc_trilinear_wgrad(const void* dout, long long ldd, const void* src, long long lds, int sX,
                                      int sY, int sZ, int oX, int oY, int oZ, int C, float* dw, long long lddw,
-                                     void* stream) {
+                                     int act_bf16, void* stream) {
   if (!dout || !src || !dw) return COOCC_ERR_ARG;
   const TlDims d = make_dims(sX, sY, sZ, oX, oY, oZ);
   const long long V = (long long)oX * oY * oZ;
-  trilinear_wgrad_kernel<<<(unsigned)((V + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dout, ldd, src, lds, d, C, dw, lddw);
+  const unsigned g = (unsigned)((V + 7) / 8);
+  if (act_bf16)
+    trilinear_wgrad_kernel<bf16_t><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16_t*)dout, ldd, (const bf16_t*)src, lds,
+                                                                      d, C, dw, lddw);
+  else
+    trilinear_wgrad_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dout, ldd, (const float*)src, lds,
+                                                                     d, C, dw, lddw);
   return CK_LAUNCH();
 }

@@ -34,6 +34,16 @@ def get_precision():
     return _PRECISION["mode"]
 
 
+# bf16 mode only: activations / gradients between the convolutions are *stored* in bf16 (the conv
+# epilogue, the BatchNorm/ReLU/residual kernels and the trilinear kernels read and write bf16), which
+# is the operand type the next convolution consumes anyway.  Off: fp32 storage + explicit conversions.
+ACT_BF16 = {"enabled": True}
+
+
+def act_bf16():
+    return _PRECISION["mode"] == "bf16" and ACT_BF16["enabled"]
+
+
 PROFILE = None     # bench.py sets this to a list to time every conv launch with CUDA events
 
 
@@ -85,19 +95,30 @@ def to_5d(x2d, dims):
 
 
 def _rows_ok(t):
-    return t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 \
-        and t.dtype == torch.float32
+    q = 8 if t.dtype == torch.bfloat16 else 4
+    return t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % q == 0 and t.data_ptr() % 16 == 0 \
+        and t.dtype in (torch.float32, torch.bfloat16)
 
 
-def _as_rows(t):
-    """fp32 [R,C] matrix whose rows are 16-byte aligned (pads the row stride if needed)."""
-    if _rows_ok(t):
+def _as_rows(t, dtype=None):
+    """[R,C] fp32 (or bf16) matrix whose rows are 16-byte aligned (pads the row stride if needed);
+    `dtype` forces the storage type."""
+    if dtype is None:
+        dtype = t.dtype if t.dtype == torch.bfloat16 else torch.float32
+    if t.dtype == dtype and _rows_ok(t):
         return t
     R, C = t.shape
-    ld = (C + 3) // 4 * 4
-    buf = torch.zeros(R, ld, device=t.device, dtype=torch.float32)
+    q = 8 if dtype == torch.bfloat16 else 4
+    ld = (C + q - 1) // q * q
+    if ld == C:
+        return t.to(dtype).contiguous()
+    buf = torch.zeros(R, ld, device=t.device, dtype=dtype)
     buf[:, :C] = t
     return buf[:, :C]
+
+
+def _is_bf16(t):
+    return 1 if t.dtype == torch.bfloat16 else 0
 
 
 def weight_rows(w5d):
@@ -136,17 +157,21 @@ def _operand(t, dtype):
     return buf[:, :C]
 
 
-def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=None, out=None, dtype=None):
+def conv_fwd_raw(x2d, w2d, dims, cin, cout, k, s, bias=None, relu=False, stats=None, out=None, dtype=None,
+                 out_bf16=False):
     L = _lib.lib()
     if dtype is None:
         dtype = _DT[_PRECISION["mode"]]
     odims = tuple(out_dim(n, k, s) for n in dims)
     vo = odims[0] * odims[1] * odims[2]
-    ldo = (cout + 3) // 4 * 4
     if out is None:
-        out = torch.empty(vo, ldo, device=x2d.device, dtype=torch.float32)
+        if out_bf16:
+            out = torch.empty(vo, (cout + 7) // 8 * 8, device=x2d.device, dtype=torch.bfloat16)
+        else:
+            out = torch.empty(vo, (cout + 3) // 4 * 4, device=x2d.device, dtype=torch.float32)
     x2d, w2d = _operand(x2d, dtype), _operand(w2d, dtype)      # no-ops when already converted
     d = _conv_desc(dims, cin, cout, k, s, x2d.stride(0), (cout + 7) // 8 * 8, dtype)
+    d.out_bf16 = _is_bf16(out)
     flops = 2.0 * vo * (k ** 3) * cin * cout
     rc = _timed("fwd", flops, lambda: L.coocc_conv3d_fwd(ctypes.byref(d), _p(x2d), _p(w2d), _p(out), out.stride(0),
                                                          _p(bias), 1 if relu else 0, _p(stats), _stream()),
@@ -159,17 +184,20 @@ class _Conv3dFn(torch.autograd.Function):
     """y[Vout,Cout] = conv3d(x[V,Cin], w[Cout,Cin,k,k,k]) (+bias)(relu), padding k//2."""
 
     @staticmethod
-    def forward(ctx, x2d, w5d, bias, dims, k, s, relu, want_stats=False):
+    def forward(ctx, x2d, w5d, bias, dims, k, s, relu, want_stats=False, out_bf16=False):
         _require_cuda(x2d, w5d)
         cout, cin = w5d.shape[0], w5d.shape[1]
         dtype = _DT[_PRECISION["mode"]]
+        out_bf16 = bool(out_bf16) and dtype == DT_BF16
         # operands in their storage type (bf16 mode: converted once here and kept for backward)
         xo = _operand(_as_rows(x2d), dtype)
         wo = _operand(weight_rows(w5d), dtype)
         stats = torch.zeros(2, cout, device=x2d.device, dtype=torch.float32) if want_stats else None
-        y, odims = conv_fwd_raw(xo, wo, dims, cin, cout, k, s, bias, relu, stats=stats, dtype=dtype)
+        y, odims = conv_fwd_raw(xo, wo, dims, cin, cout, k, s, bias, relu, stats=stats, dtype=dtype,
+                                out_bf16=out_bf16)
         ctx.save_for_backward(xo, wo, y if relu else None)
         ctx.meta = (dims, odims, k, s, relu, bias is not None, dtype, cin, cout)
+        ctx.x_bf16 = x2d.dtype == torch.bfloat16
         if want_stats:
             ctx.mark_non_differentiable(stats)
             return y, stats
@@ -183,7 +211,7 @@ class _Conv3dFn(torch.autograd.Function):
         if relu:
             dy = dy * (y > 0)
         dy = _as_rows(dy)
-        db = dy.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
+        db = dy.float().sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
         dyo = _operand(dy, dtype)
         dx = dw = None
         if ctx.needs_input_grad[1]:
@@ -206,19 +234,27 @@ class _Conv3dFn(torch.autograd.Function):
                 dy_in = dy_in[:, :cout]
             else:
                 dy_in = dyo
-            ldo = (cin + 3) // 4 * 4
-            dxb = torch.empty(dims[0] * dims[1] * dims[2], ldo, device=dy.device, dtype=torch.float32)
+            # the data gradient is written in the storage type of x (bf16 activations stay bf16)
+            if ctx.x_bf16 and dtype == DT_BF16:
+                ldo = (cin + 7) // 8 * 8
+                dxb = torch.empty(dims[0] * dims[1] * dims[2], ldo, device=dy.device, dtype=torch.bfloat16)
+            else:
+                ldo = (cin + 3) // 4 * 4
+                dxb = torch.empty(dims[0] * dims[1] * dims[2], ldo, device=dy.device, dtype=torch.float32)
             d = _conv_desc(dims, cin, cout, k, 1, ldo, dy_in.stride(0), dtype)
+            d.out_bf16 = _is_bf16(dxb)
             flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
             _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(wo), _p(dxb),
                                                                           dxb.stride(0), _stream()),
                               " %s %d->%d k%d s%d" % (dims, cin, cout, k, s)), "conv3d_dgrad")
             dx = dxb[:, :cin]
-        return dx, dw, db, None, None, None, None, None
+            if ctx.x_bf16 and dx.dtype != torch.bfloat16:
+                dx = dx.to(torch.bfloat16)
+        return dx, dw, db, None, None, None, None, None, None
 
 
-def conv3d(x2d, w5d, dims, k, s=1, bias=None, relu=False, want_stats=False):
-    return _Conv3dFn.apply(x2d, w5d, bias, dims, k, s, relu, want_stats)
+def conv3d(x2d, w5d, dims, k, s=1, bias=None, relu=False, want_stats=False, out_bf16=False):
+    return _Conv3dFn.apply(x2d, w5d, bias, dims, k, s, relu, want_stats, out_bf16)
 
 
 def _sync_group():
@@ -252,37 +288,43 @@ class _BNActFn(torch.autograd.Function):
         mi = torch.empty(2, C, device=dev, dtype=torch.float32)
         _lib.check(L.coocc_bn_finalize(_p(stats), C, count, float(eps), float(momentum), _p(running_mean),
                                        _p(running_var), _p(mi), _stream()), "bn_finalize")
-        out = torch.empty(V, C, device=dev, dtype=torch.float32)
+        x = _as_rows(x)
+        out = torch.empty(V, C, device=dev, dtype=x.dtype)
+        res_dtype = None
         if residual is not None:
-            residual = _as_rows(residual)
+            res_dtype = residual.dtype
+            residual = _as_rows(residual, x.dtype)
         _lib.check(L.coocc_bn_act_fwd(_p(x), x.stride(0), V, C, _p(mi), _p(gamma), _p(beta), _p(residual),
                                       residual.stride(0) if residual is not None else 0, 1 if relu else 0,
-                                      _p(out), out.stride(0), 0, _stream()), "bn_act_fwd")
+                                      _p(out), out.stride(0), _is_bf16(x), _stream()), "bn_act_fwd")
         ctx.save_for_backward(x, out if relu else None, mi, gamma)
-        ctx.meta = (relu, residual is not None, count)
+        ctx.meta = (relu, residual is not None, count, res_dtype)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
         x, out, mi, gamma = ctx.saved_tensors
-        relu, has_res, count = ctx.meta
+        relu, has_res, count, res_dtype = ctx.meta
         V, C = x.shape
-        dout = _as_rows(dout)
+        dout = _as_rows(dout, x.dtype)
+        bf = _is_bf16(x)
         sums = torch.zeros(2, C, device=x.device, dtype=torch.float32)
         ldo = out.stride(0) if out is not None else 0
         _lib.check(L.coocc_bn_act_bwd_reduce(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C,
-                                             _p(mi), 1 if relu else 0, _p(sums), _stream()), "bn_act_bwd_reduce")
+                                             _p(mi), 1 if relu else 0, _p(sums), bf, _stream()), "bn_act_bwd_reduce")
         local = sums
         if count != V:                      # SyncBN: batch terms use the sums over all ranks
             dist = _sync_group()
             local = sums.clone()            # dgamma / dbeta stay per-rank (DDP averages them)
             dist.all_reduce(sums)
-        dx = torch.empty(V, C, device=x.device, dtype=torch.float32)
-        dres = torch.empty(V, C, device=x.device, dtype=torch.float32) if has_res else None
+        dx = torch.empty(V, C, device=x.device, dtype=x.dtype)
+        dres = torch.empty(V, C, device=x.device, dtype=x.dtype) if has_res else None
         _lib.check(L.coocc_bn_act_bwd_apply(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C, _p(mi),
-                                            _p(gamma), 1 if relu else 0, _p(sums), count, _p(dx), dx.stride(0), 0,
+                                            _p(gamma), 1 if relu else 0, _p(sums), count, _p(dx), dx.stride(0), bf,
                                             _p(dres), C if has_res else 0, _stream()), "bn_act_bwd_apply")
+        if has_res and dres.dtype != res_dtype:
+            dres = dres.to(res_dtype)
         return dx, None, local[1], local[0], dres, None, None, None, None, None
 
 
@@ -292,12 +334,12 @@ def bn_act_eval(x, running_mean, running_var, gamma, beta, eps, residual=None, r
     x = _as_rows(x)
     V, C = x.shape
     mi = torch.stack([running_mean.float(), torch.rsqrt(running_var.float() + eps)]).contiguous()
-    out = torch.empty(V, C, device=x.device, dtype=torch.float32)
+    out = torch.empty(V, C, device=x.device, dtype=x.dtype)
     if residual is not None:
-        residual = _as_rows(residual)
+        residual = _as_rows(residual, x.dtype)
     _lib.check(L.coocc_bn_act_fwd(_p(x), x.stride(0), V, C, _p(mi), _p(gamma), _p(beta), _p(residual),
                                   residual.stride(0) if residual is not None else 0, 1 if relu else 0,
-                                  _p(out), out.stride(0), 0, _stream()), "bn_act_fwd")
+                                  _p(out), out.stride(0), _is_bf16(x), _stream()), "bn_act_fwd")
     return out
 
 
@@ -321,39 +363,45 @@ class _ResizeAddFn(torch.autograd.Function):
         src = _as_rows(src)
         C = src.shape[1]
         Vo = odims[0] * odims[1] * odims[2]
-        out = torch.empty(Vo, C, device=src.device, dtype=torch.float32)
+        out = torch.empty(Vo, C, device=src.device, dtype=src.dtype)
+        base_dtype = None
         if base is not None:
-            base = _as_rows(base)
+            base_dtype = base.dtype
+            base = _as_rows(base, src.dtype)
         wptr, ldw = None, 0
         if wts is not None:
             wts = wts.contiguous()
             wptr, ldw = _pb(wts, 4 * col), wts.stride(0)
         _lib.check(L.coocc_trilinear_fwd(_p(src), src.stride(0), sdims[0], sdims[1], sdims[2], C, _p(base),
                                          base.stride(0) if base is not None else 0, wptr, ldw, _p(out), C,
-                                         odims[0], odims[1], odims[2], _stream()), "trilinear_fwd")
+                                         odims[0], odims[1], odims[2], _is_bf16(src), _stream()), "trilinear_fwd")
         ctx.save_for_backward(src, wts)
-        ctx.meta = (sdims, odims, col, base is not None)
+        ctx.meta = (sdims, odims, col, base_dtype)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
         src, wts = ctx.saved_tensors
-        sdims, odims, col, has_base = ctx.meta
-        dout = _as_rows(dout)
+        sdims, odims, col, base_dtype = ctx.meta
+        dout = _as_rows(dout, src.dtype)
+        bf = _is_bf16(src)
         C = src.shape[1]
         dsrc = dwts = None
         wptr, ldw = (None, 0) if wts is None else (_pb(wts, 4 * col), wts.stride(0))
         if ctx.needs_input_grad[0]:
-            dsrc = torch.empty(src.shape[0], C, device=src.device, dtype=torch.float32)
+            dsrc = torch.empty(src.shape[0], C, device=src.device, dtype=src.dtype)
             _lib.check(L.coocc_trilinear_bwd(_p(dout), dout.stride(0), odims[0], odims[1], odims[2], C, wptr, ldw,
-                                             _p(dsrc), C, sdims[0], sdims[1], sdims[2], _stream()), "trilinear_bwd")
+                                             _p(dsrc), C, sdims[0], sdims[1], sdims[2], bf, _stream()), "trilinear_bwd")
         if wts is not None and ctx.needs_input_grad[4]:
             dwts = torch.zeros_like(wts)
             _lib.check(L.coocc_trilinear_wgrad(_p(dout), dout.stride(0), _p(src), src.stride(0), sdims[0], sdims[1],
                                                sdims[2], odims[0], odims[1], odims[2], C, _pb(dwts, 4 * col),
-                                               dwts.stride(0), _stream()), "trilinear_wgrad")
-        return dsrc, None, None, (dout if has_base else None), dwts, None
+                                               dwts.stride(0), bf, _stream()), "trilinear_wgrad")
+        dbase = None
+        if base_dtype is not None:
+            dbase = dout if dout.dtype == base_dtype else dout.to(base_dtype)
+        return dsrc, None, None, dbase, dwts, None
 
 
 def resize_add(src, sdims, odims, base=None, wts=None, col=0):

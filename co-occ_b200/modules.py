@@ -55,7 +55,7 @@ def conv_bn_act(x2d, dims, conv, bn=None, relu=True, residual=None):
     fused = (bn is not None and bn.training and conv.bias is None and conv.out_channels % 4 == 0
              and bn.momentum is not None)
     if fused:
-        y, stats = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, want_stats=True)
+        y, stats = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, want_stats=True, out_bf16=CF.act_bf16())
         if bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         track = bn.track_running_stats
@@ -348,7 +348,7 @@ def render_fn(voxel_feats, gemo, sigma_head, rgb_head, gt_depth, gt_img):
     B, N, D, H, W, _ = gemo.shape
     assert B == 1
     x2d, dims = CF.to_cl2d(voxel_feats)
-    rows = CF.box_rows(x2d, dims)
+    rows = CF.box_rows(x2d.float(), dims)       # (bf16 activations: the render box is gathered in fp32)
     rgb_raw = rgb_head.forward_rows(rows)                       # [T,3]
     sigma = sigma_head.forward_rows(rows, relu_out=True)        # [T,1] = relu(sigma_head(f))
     tab = torch.cat([rgb_raw, sigma], dim=1)                    # [T,4]

@@ -50,19 +50,21 @@ typedef struct coocc_conv_desc {
   int dtype;       /* COOCC_DTYPE_* : element type of x / w / dy */
   long long ldx;   /* row stride of the input activation matrix, in elements (>= Cin) */
   long long ldy;   /* row stride of the output-gradient matrix dy, in elements (>= Cout) */
+  int out_bf16;    /* 1: y (fwd) / dx (dgrad) are written as bf16 (row stride in bf16 elements, % 8 == 0
+                      for vector stores); 0: fp32.  Not available with COOCC_DTYPE_TF32X3. */
 } coocc_conv_desc;
 
-/* y[v_out, co] = sum x[...] w[...] (+ bias[co]) (relu).  y is fp32 with row stride ldo.
+/* y[v_out, co] = sum x[...] w[...] (+ bias[co]) (relu).  y is fp32 (or bf16, d->out_bf16) with row stride ldo.
  * stats (optional, may be NULL): float[2*Cout], must be zeroed by the caller; receives the
  * per-channel sum and sum of squares of the raw conv output (before bias/relu) -- the batch
  * statistics BatchNorm3d needs, produced in the conv epilogue instead of a second pass. */
-int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, float* y, long long ldo,
+int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, void* y, long long ldo,
                      const float* bias, int relu, float* stats, void* stream);
 
-/* dx[v, ci] (fp32, row stride ldo) for a stride-1 convolution; dy has the conv's output extent
+/* dx[v, ci] (fp32 or bf16 per d->out_bf16, row stride ldo) for a stride-1 convolution; dy has the conv's output extent
  * (= input extent).  Strided convolutions: scatter dy onto the input lattice with
  * coocc_dilate2 first and call this with stride = 1. */
-int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, float* dx, long long ldo,
+int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, void* dx, long long ldo,
                        void* stream);
 
 /* dw[co][tap][ci] += ... (fp32; caller zero-fills dw; split-K partial sums are added atomically). */
@@ -166,20 +168,24 @@ int coocc_render_upsample_loss_bwd(const float* rgbs, const float* depths, int n
  * updates running_mean / running_var (may be NULL) with `momentum` (unbiased variance). */
 int coocc_bn_finalize(const float* stats, int C, long long count, float eps, float momentum,
                       float* running_mean, float* running_var, float* mean_invstd, void* stream);
-/* out = relu?((x - mean) * invstd * gamma + beta (+ residual)); out is fp32 or bf16 */
-int coocc_bn_act_fwd(const float* x, long long ldx, long long V, int C, const float* mean_invstd,
-                     const float* gamma, const float* beta, const float* residual, long long ldr, int relu,
-                     void* out, long long ldo, int out_bf16, void* stream);
+/* Storage type of the [V, C] activation tensors of the calls below: act_bf16 = 0 -> fp32,
+ * 1 -> bf16 (every activation / gradient pointer of the call; statistics, gamma, beta, per-voxel
+ * weights and all arithmetic stay fp32).  bf16 mode keeps activations between convolutions in the
+ * operand type the next convolution consumes. */
+/* out = relu?((x - mean) * invstd * gamma + beta (+ residual)) */
+int coocc_bn_act_fwd(const void* x, long long ldx, long long V, int C, const float* mean_invstd,
+                     const float* gamma, const float* beta, const void* residual, long long ldr, int relu,
+                     void* out, long long ldo, int act_bf16, void* stream);
 /* backward of the above, in two stream-ordered halves (a SyncBatchNorm all-reduce of `sums` fits in
  * between).  reduce: sums (float[2*C], zeroed by the caller) += (sum dz, sum dz*xhat), dz = dout*[out>0];
- * afterwards sums[0:C] = dbeta, sums[C:2C] = dgamma.  apply: dx (fp32 or bf16) = gradient w.r.t. x with
- * the batch terms divided by `count` (rows the statistics were taken over); dres (optional) = dz. */
-int coocc_bn_act_bwd_reduce(const float* dout, long long ldd, const float* out, long long ldo, const float* x,
+ * afterwards sums[0:C] = dbeta, sums[C:2C] = dgamma.  apply: dx = gradient w.r.t. x with the batch
+ * terms divided by `count` (rows the statistics were taken over); dres (optional) = dz. */
+int coocc_bn_act_bwd_reduce(const void* dout, long long ldd, const void* out, long long ldo, const void* x,
                             long long ldx, long long V, int C, const float* mean_invstd, int relu, float* sums,
-                            void* stream);
-int coocc_bn_act_bwd_apply(const float* dout, long long ldd, const float* out, long long ldo, const float* x,
+                            int act_bf16, void* stream);
+int coocc_bn_act_bwd_apply(const void* dout, long long ldd, const void* out, long long ldo, const void* x,
                            long long ldx, long long V, int C, const float* mean_invstd, const float* gamma, int relu,
-                           const float* sums, long long count, void* dx, long long lddx, int dx_bf16, float* dres,
+                           const float* sums, long long count, void* dx, long long lddx, int act_bf16, void* dres,
                            long long lddr, void* stream);
 /* dst[(2x,2y,2z)] = src[(x,y,z)], zero elsewhere (dst extent X,Y,Z; src extent oX,oY,oZ) */
 int coocc_dilate2(const void* src, long long lds, int oX, int oY, int oZ, int C, void* dst, long long ldd,
@@ -191,15 +197,17 @@ int coocc_dilate2(const void* src, long long lds, int oX, int oY, int oZ, int C,
  * P/coocc/necks/fpn3d.py:91-94 and P/coocc/dense_heads/occ_head.py:161-165.
  *   out[v,:] = base[v,:] (optional) + wts[v*ldw] (optional) * interp(src)[v,:]
  * ------------------------------------------------------------------------------------------ */
-int coocc_trilinear_fwd(const float* src, long long lds, int sX, int sY, int sZ, int C, const float* base,
-                        long long ldb, const float* wts, long long ldw, float* out, long long ldo, int oX,
-                        int oY, int oZ, void* stream);
+int coocc_trilinear_fwd(const void* src, long long lds, int sX, int sY, int sZ, int C, const void* base,
+                        long long ldb, const float* wts, long long ldw, void* out, long long ldo, int oX,
+                        int oY, int oZ, int act_bf16, void* stream);
 /* dsrc = transpose(interp) applied to (wts * dout) */
-int coocc_trilinear_bwd(const float* dout, long long ldd, int oX, int oY, int oZ, int C, const float* wts,
-                        long long ldw, float* dsrc, long long lds, int sX, int sY, int sZ, void* stream);
-/* dw[v*lddw] = sum_c dout[v,c] * interp(src)[v,c] */
-int coocc_trilinear_wgrad(const float* dout, long long ldd, const float* src, long long lds, int sX, int sY,
-                          int sZ, int oX, int oY, int oZ, int C, float* dw, long long lddw, void* stream);
+int coocc_trilinear_bwd(const void* dout, long long ldd, int oX, int oY, int oZ, int C, const float* wts,
+                        long long ldw, void* dsrc, long long lds, int sX, int sY, int sZ, int act_bf16,
+                        void* stream);
+/* dw[v*lddw] = sum_c dout[v,c] * interp(src)[v,c]   (dw fp32) */
+int coocc_trilinear_wgrad(const void* dout, long long ldd, const void* src, long long lds, int sX, int sY,
+                          int sZ, int oX, int oY, int oZ, int C, float* dw, long long lddw, int act_bf16,
+                          void* stream);
 
 #ifdef __cplusplus
 }
