@@ -64,6 +64,9 @@ _SIGS = {
     "coocc_dilate2": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "coocc_trilinear_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "coocc_trilinear_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "coocc_trilinear_mix_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "coocc_trilinear_mix_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
+    "coocc_trilinear_tune": (c_int, [c_int]),
     "coocc_trilinear_wgrad": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p]),
     "coocc_render_box": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "coocc_render_box_gather": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

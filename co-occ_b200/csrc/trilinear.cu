@@ -7,6 +7,7 @@
 // deterministic); w.r.t. wts a per-voxel dot product.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/coocc_b200.h"
 #include "act_types.cuh"
@@ -139,6 +140,46 @@ __global__ void __launch_bounds__(256) trilinear_bwd_kernel(const T* __restrict_
   }
 }
 
+// Separable form of the same transpose: interp = Tx (x) Ty (x) Tz, so interp^T is three 1-D passes,
+// each reading its input once with fully coalesced rows and writing a tensor `scale` times smaller.
+// The direct gather above pulls every dout row 8 times through L2 (2x2x2 footprint); the passes read
+// dout once.  View of a pass: in [outer][n_in][inner][C] -> out [outer][n_out][inner][C],
+//   out[a, i, r, :] = sum_{o : i in {i0(o), i1(o)}} lambda(o, i) * vw(a, o, r) * in[a, o, r, :]
+// (vw = optional per-voxel weight of the first pass).  One warp per output row.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) trilinear_bwd_axis_kernel(const Tin* __restrict__ in, long long ldi,
+                                                                 int outer, int n_in, int n_out, int inner, int C,
+                                                                 float scale, const float* __restrict__ vw,
+                                                                 long long ldw, Tout* __restrict__ out,
+                                                                 long long ldo) {
+  const int lane = threadIdx.x & 31;
+  const int c4 = C >> 2;
+  const long long rows = (long long)outer * n_out * inner;
+  for (long long row = blockIdx.x * 8LL + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8LL) {
+    const int r = (int)(row % inner);
+    const long long t = row / inner;
+    const int i = (int)(t % n_out);
+    const long long a = t / n_out;
+    int lo, hi;
+    tl_range(i, scale, n_in, lo, hi);
+    for (int cg = lane; cg < c4; cg += 32) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int o = lo; o <= hi; ++o) {
+        int a0, a1;
+        float la;
+        tl_src(o, scale, n_out, a0, a1, la);
+        float w = (a0 == i ? 1.f - la : 0.f) + (a1 == i ? la : 0.f);
+        if (w == 0.f) continue;
+        const long long irow = (a * n_in + o) * inner + r;
+        if (vw != nullptr) w *= vw[irow * ldw];
+        const float4 g = load4(in + irow * ldi + cg * 4);
+        acc.x += w * g.x; acc.y += w * g.y; acc.z += w * g.z; acc.w += w * g.w;
+      }
+      store4(out + row * ldo + cg * 4, acc);
+    }
+  }
+}
+
 // dw[v] = sum_c dout[v, c] * interpolate(src)[v, c]     (one warp per output voxel)
 template <typename T>
 __global__ void __launch_bounds__(256) trilinear_wgrad_kernel(const T* __restrict__ dout, long long ldd,
@@ -170,6 +211,161 @@ __global__ void __launch_bounds__(256) trilinear_wgrad_kernel(const T* __restric
   if (lane == 0) dw[v * lddw] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-level mix: out[v,:] = base[v,:] (opt) + sum_{l < nlev} w_l(v) * interp_l(src_l)[v,:], with
+// w_l(v) = wts[v*ldw + l] (or 1).  One kernel for the whole OccHead level fusion
+// (P/coocc/dense_heads/occ_head.py:161-165) instead of one read-modify-write pass per level: the
+// [V, C] output is written once and the small coarse levels stay L2-resident.
+// One warp per output voxel, lanes over channel groups of 4; the index arithmetic (32-bit) is done
+// once per voxel and level, zero-weight corners (e.g. every corner but one of a same-size level) are
+// skipped warp-uniformly.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTlLevels = 4;
+constexpr int kTileXY = 4;
+struct TlMix {
+  const void* src[kTlLevels];
+  void* dsrc[kTlLevels];        // backward only: gradient of same-size levels (else nullptr)
+  long long lds[kTlLevels];
+  int sX[kTlLevels], sY[kTlLevels], sZ[kTlLevels];
+  float fx[kTlLevels], fy[kTlLevels], fz[kTlLevels];
+  int nlev;
+};
+
+template <typename T, int G>
+__global__ void __launch_bounds__(256) trilinear_mix_fwd_kernel(TlMix m, int oX, int oY, int oZ, int C,
+                                                                const T* __restrict__ base, long long ldb,
+                                                                const float* __restrict__ wts, long long ldw,
+                                                                T* __restrict__ out, long long ldo) {
+  const int lane = threadIdx.x & 31;
+  const int c4 = C >> 2;
+  // blocks walk compact (kTileXY x kTileXY x oZ) bricks of the output so that the corner rows of the
+  // coarse levels, shared by neighbouring output voxels, are re-read from L1 instead of L2
+  const int tilesY = (oY + kTileXY - 1) / kTileXY;
+  const int ntile = ((oX + kTileXY - 1) / kTileXY) * tilesY;
+  const int per_tile = kTileXY * kTileXY * oZ;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x)
+  for (int idx = threadIdx.x >> 5; idx < per_tile; idx += 8) {
+    const int z = idx % oZ, cxy = idx / oZ;
+    const int x = (tile / tilesY) * kTileXY + cxy / kTileXY, y = (tile % tilesY) * kTileXY + cxy % kTileXY;
+    if (x >= oX || y >= oY) continue;
+    const int v = (x * oY + y) * oZ + z;
+    float4 acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (base != nullptr) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (lane + 32 * g < c4) acc[g] = load4(base + (long long)v * ldb + (lane + 32 * g) * 4);
+    }
+    for (int l = 0; l < m.nlev; ++l) {
+      const T* src = reinterpret_cast<const T*>(m.src[l]);
+      int x0, x1, y0, y1, z0, z1;
+      float lx, ly, lz;
+      tl_src(x, m.fx[l], m.sX[l], x0, x1, lx);
+      tl_src(y, m.fy[l], m.sY[l], y0, y1, ly);
+      tl_src(z, m.fz[l], m.sZ[l], z0, z1, lz);
+      const float wl = wts ? wts[(long long)v * ldw + l] : 1.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float w = wl * ((k & 4) ? lx : 1.f - lx) * ((k & 2) ? ly : 1.f - ly) * ((k & 1) ? lz : 1.f - lz);
+        if (w == 0.f) continue;
+        const int xi = (k & 4) ? x1 : x0, yi = (k & 2) ? y1 : y0, zi = (k & 1) ? z1 : z0;
+        const T* row = src + (long long)((xi * m.sY[l] + yi) * m.sZ[l] + zi) * m.lds[l];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (lane + 32 * g < c4) {
+            const float4 sv = load4(row + (lane + 32 * g) * 4);
+            acc[g].x += w * sv.x; acc[g].y += w * sv.y; acc[g].z += w * sv.z; acc[g].w += w * sv.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (lane + 32 * g < c4) store4(out + (long long)v * ldo + (lane + 32 * g) * 4, acc[g]);
+  }
+}
+
+// Backward companion of the mix, one pass over dout:
+//   dw[v*lddw + l] = sum_c dout[v,c] * interp_l(src_l)[v,c]            (when dw != nullptr)
+//   dsrc_l[v,:]    = w_l(v) * dout[v,:]   for the levels whose size equals the output size
+// (the coarser levels' gradients are transposed gathers: trilinear_bwd_kernel per level).
+template <typename T, int G>
+__global__ void __launch_bounds__(256) trilinear_mix_bwd_kernel(TlMix m, int oX, int oY, int oZ, int C,
+                                                                const T* __restrict__ dout, long long ldd,
+                                                                const float* __restrict__ wts, long long ldw,
+                                                                float* __restrict__ dw, long long lddw) {
+  const int lane = threadIdx.x & 31;
+  const int c4 = C >> 2;
+  // blocks walk compact (kTileXY x kTileXY x oZ) bricks of the output so that the corner rows of the
+  // coarse levels, shared by neighbouring output voxels, are re-read from L1 instead of L2
+  const int tilesY = (oY + kTileXY - 1) / kTileXY;
+  const int ntile = ((oX + kTileXY - 1) / kTileXY) * tilesY;
+  const int per_tile = kTileXY * kTileXY * oZ;
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x)
+  for (int idx = threadIdx.x >> 5; idx < per_tile; idx += 8) {
+    const int z = idx % oZ, cxy = idx / oZ;
+    const int x = (tile / tilesY) * kTileXY + cxy / kTileXY, y = (tile % tilesY) * kTileXY + cxy % kTileXY;
+    if (x >= oX || y >= oY) continue;
+    const int v = (x * oY + y) * oZ + z;
+    float4 g4[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      g4[g] = (lane + 32 * g < c4) ? load4(dout + (long long)v * ldd + (lane + 32 * g) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float dots[kTlLevels];
+#pragma unroll
+    for (int l = 0; l < kTlLevels; ++l) dots[l] = 0.f;
+#pragma unroll
+    for (int l = 0; l < kTlLevels; ++l) {
+      if (l >= m.nlev) break;
+      const float wl = wts ? wts[(long long)v * ldw + l] : 1.f;
+      if (m.dsrc[l] != nullptr) {
+        T* drow = reinterpret_cast<T*>(m.dsrc[l]) + (long long)v * m.lds[l];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (lane + 32 * g < c4)
+            store4(drow + (lane + 32 * g) * 4, make_float4(wl * g4[g].x, wl * g4[g].y, wl * g4[g].z, wl * g4[g].w));
+      }
+      if (dw == nullptr) continue;
+      const T* src = reinterpret_cast<const T*>(m.src[l]);
+      int x0, x1, y0, y1, z0, z1;
+      float lx, ly, lz;
+      tl_src(x, m.fx[l], m.sX[l], x0, x1, lx);
+      tl_src(y, m.fy[l], m.sY[l], y0, y1, ly);
+      tl_src(z, m.fz[l], m.sZ[l], z0, z1, lz);
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float w = ((k & 4) ? lx : 1.f - lx) * ((k & 2) ? ly : 1.f - ly) * ((k & 1) ? lz : 1.f - lz);
+        if (w == 0.f) continue;
+        const int xi = (k & 4) ? x1 : x0, yi = (k & 2) ? y1 : y0, zi = (k & 1) ? z1 : z0;
+        const T* row = src + (long long)((xi * m.sY[l] + yi) * m.sZ[l] + zi) * m.lds[l];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (lane + 32 * g < c4) {
+            const float4 sv = load4(row + (lane + 32 * g) * 4);
+            d += w * (sv.x * g4[g].x + sv.y * g4[g].y + sv.z * g4[g].z + sv.w * g4[g].w);
+          }
+        }
+      }
+      dots[l] = d;
+    }
+    if (dw != nullptr) {
+#pragma unroll
+      for (int l = 0; l < kTlLevels; ++l) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) dots[l] += __shfl_xor_sync(0xffffffffu, dots[l], o);
+      }
+      if (lane < m.nlev) {
+        float val = dots[0];
+#pragma unroll
+        for (int l = 1; l < kTlLevels; ++l) val = (lane == l) ? dots[l] : val;
+        dw[(long long)v * lddw + lane] = val;
+      }
+    }
+  }
+}
+
 static TlDims make_dims(int sX, int sY, int sZ, int oX, int oY, int oZ) {
   TlDims d;
   d.sX = sX; d.sY = sY; d.sZ = sZ; d.oX = oX; d.oY = oY; d.oZ = oZ;
@@ -187,9 +383,8 @@ static int tl_grid(long long total) {
 }  // namespace coocc
 
 using namespace coocc;
-#define CK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA)
-
 typedef __nv_bfloat16 bf16_t;
+#define CK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA)
 
 extern "C" int coocc_trilinear_fwd(const void* src, long long lds, int sX, int sY, int sZ, int C,
                                    const void* base, long long ldb, const float* wts, long long ldw, void* out,
@@ -206,10 +401,50 @@ extern "C" int coocc_trilinear_fwd(const void* src, long long lds, int sX, int s
   return CK_LAUNCH();
 }
 
+static int tl_axis_grid(long long rows) {
+  long long b = (rows + 7) / 8;
+  if (b > 148LL * 32) b = 148LL * 32;
+  return b < 1 ? 1 : (int)b;
+}
+
+// three 1-D transposed passes (x, then y, then z) with fp32 intermediates in stream-ordered scratch
+template <typename T>
+static int trilinear_bwd_separable(const T* dout, long long ldd, int oX, int oY, int oZ, int C, const float* wts,
+                                   long long ldw, T* dsrc, long long lds, int sX, int sY, int sZ, cudaStream_t st) {
+  const long long n1 = (long long)sX * oY * oZ, n2 = (long long)sX * sY * oZ;
+  float* tmp = nullptr;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&tmp), (size_t)(n1 + n2) * C * sizeof(float), st) != cudaSuccess)
+    return COOCC_ERR_CUDA;
+  float* t1 = tmp;
+  float* t2 = tmp + n1 * C;
+  trilinear_bwd_axis_kernel<T, float><<<tl_axis_grid(n1), 256, 0, st>>>(dout, ldd, 1, oX, sX, oY * oZ, C,
+                                                                       (float)sX / (float)oX, wts, ldw, t1, C);
+  trilinear_bwd_axis_kernel<float, float><<<tl_axis_grid(n2), 256, 0, st>>>(t1, C, sX, oY, sY, oZ, C,
+                                                                           (float)sY / (float)oY, nullptr, 0, t2, C);
+  trilinear_bwd_axis_kernel<float, T><<<tl_axis_grid((long long)sX * sY * sZ), 256, 0, st>>>(
+      t2, C, sX * sY, oZ, sZ, 1, C, (float)sZ / (float)oZ, nullptr, 0, dsrc, lds);
+  const int rc = cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+  cudaFreeAsync(tmp, st);
+  return rc;
+}
+
+static int g_tl_separable = 1;
+/* benchmark hook: 0 = direct transposed gather, 1 = separable passes (default) */
+extern "C" int coocc_trilinear_tune(int separable) {
+  g_tl_separable = separable ? 1 : 0;
+  return 0;
+}
+
 extern "C" int coocc_trilinear_bwd(const void* dout, long long ldd, int oX, int oY, int oZ, int C,
                                    const float* wts, long long ldw, void* dsrc, long long lds, int sX, int sY,
                                    int sZ, int act_bf16, void* stream) {
   if (!dout || !dsrc || (C & 3) || (lds & 3) || (ldd & 3)) return COOCC_ERR_ARG;
+  if (g_tl_separable && (long long)oX * oY * oZ >= 4096) {
+    return act_bf16 ? trilinear_bwd_separable<bf16_t>((const bf16_t*)dout, ldd, oX, oY, oZ, C, wts, ldw, (bf16_t*)dsrc,
+                                                      lds, sX, sY, sZ, (cudaStream_t)stream)
+                    : trilinear_bwd_separable<float>((const float*)dout, ldd, oX, oY, oZ, C, wts, ldw, (float*)dsrc,
+                                                     lds, sX, sY, sZ, (cudaStream_t)stream);
+  }
   const TlDims d = make_dims(sX, sY, sZ, oX, oY, oZ);
   const long long Vs = (long long)sX * sY * sZ;
   const unsigned g = (unsigned)((Vs + 7) / 8);
@@ -235,5 +470,76 @@ extern "C" int coocc_trilinear_wgrad(const void* dout, long long ldd, const void
   else
     trilinear_wgrad_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)dout, ldd, (const float*)src, lds,
                                                                      d, C, dw, lddw);
+  return CK_LAUNCH();
+}
+
+// ---- multi-level mix (see trilinear_mix_fwd_kernel) ------------------------------------------
+static int fill_mix(TlMix& m, int nlev, const void* const* src, const long long* lds, const int* sdims, int oX, int oY,
+                    int oZ) {
+  if (nlev < 1 || nlev > kTlLevels || !src || !lds || !sdims) return COOCC_ERR_ARG;
+  memset(&m, 0, sizeof(m));
+  m.nlev = nlev;
+  for (int l = 0; l < nlev; ++l) {
+    if (!src[l] || (lds[l] & 3)) return COOCC_ERR_ARG;
+    m.src[l] = src[l];
+    m.lds[l] = lds[l];
+    m.sX[l] = sdims[3 * l]; m.sY[l] = sdims[3 * l + 1]; m.sZ[l] = sdims[3 * l + 2];
+    m.fx[l] = (float)m.sX[l] / (float)oX;
+    m.fy[l] = (float)m.sY[l] / (float)oY;
+    m.fz[l] = (float)m.sZ[l] / (float)oZ;
+  }
+  return 0;
+}
+static int mix_grid(int oX, int oY) {
+  long long b = (long long)((oX + kTileXY - 1) / kTileXY) * ((oY + kTileXY - 1) / kTileXY);
+  if (b > 148LL * 8) b = 148LL * 8;
+  return b < 1 ? 1 : (int)b;
+}
+
+#define TL_DISPATCH_G(KERNEL, T, ...)                                                          \
+  do {                                                                                         \
+    const int groups_ = ((C >> 2) + 31) / 32;                                                  \
+    if (groups_ <= 1) KERNEL<T, 1><<<g, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);          \
+    else if (groups_ == 2) KERNEL<T, 2><<<g, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);     \
+    else if (groups_ <= 4) KERNEL<T, 4><<<g, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);     \
+    else return COOCC_ERR_CAPACITY;                                                            \
+  } while (0)
+
+extern "C" int coocc_trilinear_mix_fwd(int nlev, const void* const* src, const long long* lds, const int* sdims,
+                                       int C, const void* base, long long ldb, const float* wts, long long ldw,
+                                       void* out, long long ldo, int oX, int oY, int oZ, int act_bf16,
+                                       void* stream) {
+  if (!out || (C & 3) || (ldo & 3) || (base && (ldb & 3))) return COOCC_ERR_ARG;
+  TlMix m;
+  int rc = fill_mix(m, nlev, src, lds, sdims, oX, oY, oZ);
+  if (rc) return rc;
+  const int g = mix_grid(oX, oY);
+  if (act_bf16)
+    TL_DISPATCH_G(trilinear_mix_fwd_kernel, bf16_t, m, oX, oY, oZ, C, (const bf16_t*)base, ldb, wts, ldw, (bf16_t*)out,
+                  ldo);
+  else
+    TL_DISPATCH_G(trilinear_mix_fwd_kernel, float, m, oX, oY, oZ, C, (const float*)base, ldb, wts, ldw, (float*)out,
+                  ldo);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_trilinear_mix_bwd(int nlev, const void* const* src, const long long* lds, const int* sdims,
+                                       void* const* dsrc_same, int C, const void* dout, long long ldd,
+                                       const float* wts, long long ldw, float* dw, long long lddw, int oX, int oY,
+                                       int oZ, int act_bf16, void* stream) {
+  if (!dout || (C & 3) || (ldd & 3)) return COOCC_ERR_ARG;
+  TlMix m;
+  int rc = fill_mix(m, nlev, src, lds, sdims, oX, oY, oZ);
+  if (rc) return rc;
+  if (dsrc_same)
+    for (int l = 0; l < nlev; ++l) {
+      if (dsrc_same[l] && (m.sX[l] != oX || m.sY[l] != oY || m.sZ[l] != oZ)) return COOCC_ERR_ARG;
+      m.dsrc[l] = dsrc_same[l];
+    }
+  const int g = mix_grid(oX, oY);
+  if (act_bf16)
+    TL_DISPATCH_G(trilinear_mix_bwd_kernel, bf16_t, m, oX, oY, oZ, C, (const bf16_t*)dout, ldd, wts, ldw, dw, lddw);
+  else
+    TL_DISPATCH_G(trilinear_mix_bwd_kernel, float, m, oX, oY, oZ, C, (const float*)dout, ldd, wts, ldw, dw, lddw);
   return CK_LAUNCH();
 }

@@ -408,6 +408,82 @@ def resize_add(src, sdims, odims, base=None, wts=None, col=0):
     return _ResizeAddFn.apply(src, tuple(sdims), tuple(odims), base, wts, col)
 
 
+class _ResizeMixFn(torch.autograd.Function):
+    """out = base (opt.) + sum_l wts[:, l] (opt.) * trilinear_resize(src_l)  -- all levels in one pass."""
+
+    @staticmethod
+    def forward(ctx, sdims_list, odims, base, wts, *srcs):
+        L = _lib.lib()
+        n = len(srcs)
+        dt = torch.bfloat16 if srcs[0].dtype == torch.bfloat16 else torch.float32
+        srcs = [_as_rows(s_, dt) for s_ in srcs]
+        C = srcs[0].shape[1]
+        Vo = odims[0] * odims[1] * odims[2]
+        out = torch.empty(Vo, C, device=srcs[0].device, dtype=dt)
+        base_dtype = None
+        if base is not None:
+            base_dtype = base.dtype
+            base = _as_rows(base, dt)
+        wptr, ldw = None, 0
+        if wts is not None:
+            wts = wts.contiguous()
+            assert wts.dtype == torch.float32 and wts.shape == (Vo, n)
+            wptr, ldw = _p(wts), wts.stride(0)
+        ptrs = (ctypes.c_void_p * n)(*[s_.data_ptr() for s_ in srcs])
+        lds = (ctypes.c_longlong * n)(*[s_.stride(0) for s_ in srcs])
+        sd = (ctypes.c_int * (3 * n))(*[int(v) for d_ in sdims_list for v in d_])
+        _lib.check(L.coocc_trilinear_mix_fwd(n, ptrs, lds, sd, C, _p(base), base.stride(0) if base is not None else 0,
+                                             wptr, ldw, _p(out), out.stride(0), odims[0], odims[1], odims[2],
+                                             1 if dt == torch.bfloat16 else 0, _stream()), "trilinear_mix_fwd")
+        ctx.save_for_backward(wts, *srcs)
+        ctx.meta = (tuple(tuple(d_) for d_ in sdims_list), tuple(odims), base_dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        wts, *srcs = ctx.saved_tensors
+        sdims_list, odims, base_dtype = ctx.meta
+        n = len(srcs)
+        dt = srcs[0].dtype
+        bf = 1 if dt == torch.bfloat16 else 0
+        dout = _as_rows(dout, dt)
+        C = srcs[0].shape[1]
+        Vo = odims[0] * odims[1] * odims[2]
+        need_dw = wts is not None and ctx.needs_input_grad[3]
+        dsrcs = [None] * n
+        same_ptrs = [None] * n
+        for l in range(n):
+            if ctx.needs_input_grad[4 + l] and sdims_list[l] == odims:
+                dsrcs[l] = torch.empty(Vo, srcs[l].stride(0), device=dout.device, dtype=dt)[:, :C]
+                same_ptrs[l] = dsrcs[l].data_ptr()
+        dw = torch.empty(Vo, n, device=dout.device, dtype=torch.float32) if need_dw else None
+        if need_dw or any(p_ is not None for p_ in same_ptrs):
+            ptrs = (ctypes.c_void_p * n)(*[s_.data_ptr() for s_ in srcs])
+            lds = (ctypes.c_longlong * n)(*[s_.stride(0) for s_ in srcs])
+            sd = (ctypes.c_int * (3 * n))(*[int(v) for d_ in sdims_list for v in d_])
+            dp = (ctypes.c_void_p * n)(*same_ptrs)
+            _lib.check(L.coocc_trilinear_mix_bwd(n, ptrs, lds, sd, dp, C, _p(dout), dout.stride(0), _p(wts),
+                                                 wts.stride(0) if wts is not None else 0, _p(dw), n if need_dw else 0,
+                                                 odims[0], odims[1], odims[2], bf, _stream()), "trilinear_mix_bwd")
+        for l in range(n):
+            if ctx.needs_input_grad[4 + l] and dsrcs[l] is None:
+                sdm = sdims_list[l]
+                dsrcs[l] = torch.empty(srcs[l].shape[0], C, device=dout.device, dtype=dt)
+                wptr, ldw = (None, 0) if wts is None else (_pb(wts, 4 * l), wts.stride(0))
+                _lib.check(L.coocc_trilinear_bwd(_p(dout), dout.stride(0), odims[0], odims[1], odims[2], C, wptr, ldw,
+                                                 _p(dsrcs[l]), C, sdm[0], sdm[1], sdm[2], bf, _stream()), "trilinear_bwd")
+        dbase = None
+        if base_dtype is not None:
+            dbase = dout if dout.dtype == base_dtype else dout.to(base_dtype)
+        return (None, None, dbase, dw, *dsrcs)
+
+
+def resize_mix(srcs, sdims_list, odims, base=None, wts=None):
+    """base + sum_l wts[:, l] * resize(srcs[l]) on [V,C] rows (one fused pass, see csrc/trilinear.cu)."""
+    return _ResizeMixFn.apply([tuple(d) for d in sdims_list], tuple(odims), base, wts, *srcs)
+
+
 # ----------------------------------------------------------------------------------------
 # GSFusion
 # ----------------------------------------------------------------------------------------

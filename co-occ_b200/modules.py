@@ -219,7 +219,7 @@ class FPN3D(nn.Module):
             lat.append(y)
             dims.append(d)
         for i in range(self.num_out - 1, 0, -1):       # fpn3d.py:91-94, resize fused with the add
-            lat[i - 1] = CF.resize_add(lat[i], dims[i], dims[i - 1], base=lat[i - 1])
+            lat[i - 1] = CF.resize_mix([lat[i]], [dims[i]], dims[i - 1], base=lat[i - 1])
         outs = []
         for i in range(self.num_out):
             m = self.fpn_convs[i][0]
@@ -276,15 +276,11 @@ class OccHead(nn.Module):
             w = torch.softmax(w, dim=1)
         else:
             w = torch.full((1, self.num_level), 1.0 / self.num_level, device=occs[0].device)
-        feats = None
         if self.soft_weights:
-            for i, f in enumerate(occs):               # occ_head.py:161-165, resize * weight + add fused
-                feats = CF.resize_add(f, dims[i], d0, base=feats, wts=w, col=i)
+            # occ_head.py:161-165: every level resized, weighted and summed in one pass
+            feats = CF.resize_mix(occs, dims, d0, wts=w)
         else:
-            for i, f in enumerate(occs):
-                r = CF.resize_add(f, dims[i], d0, base=feats)
-                feats = r
-            feats = feats * (1.0 / self.num_level)
+            feats = CF.resize_mix(occs, dims, d0) * (1.0 / self.num_level)
         y, _ = conv_bn_act(feats, d0, self.occ_pred_conv[0], self.occ_pred_conv[1])
         occ, _ = conv_bn_act(y, d0, self.occ_pred_conv[3], None, relu=False)
         return {"out_voxel_feats": [CF.to_5d(feats, d0)], "occ": [CF.to_5d(occ, d0)]}

@@ -204,10 +204,27 @@ int coocc_trilinear_fwd(const void* src, long long lds, int sX, int sY, int sZ, 
 int coocc_trilinear_bwd(const void* dout, long long ldd, int oX, int oY, int oZ, int C, const float* wts,
                         long long ldw, void* dsrc, long long lds, int sX, int sY, int sZ, int act_bf16,
                         void* stream);
+/* benchmark hook: 0 = direct transposed gather in coocc_trilinear_bwd, 1 = three separable 1-D passes (default) */
+int coocc_trilinear_tune(int separable);
 /* dw[v*lddw] = sum_c dout[v,c] * interp(src)[v,c]   (dw fp32) */
 int coocc_trilinear_wgrad(const void* dout, long long ldd, const void* src, long long lds, int sX, int sY,
                           int sZ, int oX, int oY, int oZ, int C, float* dw, long long lddw, int act_bf16,
                           void* stream);
+
+/* Multi-level mix, the whole OccHead level fusion (occ_head.py:161-165) in one pass:
+ *   out[v,:] = base[v,:] (optional) + sum_{l<nlev} w_l(v) * interp_l(src_l)[v,:],  w_l(v) = wts[v*ldw + l] or 1
+ * src / lds: nlev source matrices and row strides; sdims = {sX,sY,sZ} per level (3*nlev ints); nlev <= 4.
+ * The dsrc rows of a same-size level use that level's lds. */
+int coocc_trilinear_mix_fwd(int nlev, const void* const* src, const long long* lds, const int* sdims, int C,
+                            const void* base, long long ldb, const float* wts, long long ldw, void* out,
+                            long long ldo, int oX, int oY, int oZ, int act_bf16, void* stream);
+/* one pass over dout: dw[v*lddw + l] = <dout[v,:], interp_l(src_l)[v,:]> (dw may be NULL) and, for the
+ * levels with dsrc_same[l] != NULL (their size must equal the output size), dsrc_l[v,:] = w_l(v)*dout[v,:].
+ * Coarser levels' gradients: coocc_trilinear_bwd per level. */
+int coocc_trilinear_mix_bwd(int nlev, const void* const* src, const long long* lds, const int* sdims,
+                            void* const* dsrc_same, int C, const void* dout, long long ldd, const float* wts,
+                            long long ldw, float* dw, long long lddw, int oX, int oY, int oZ, int act_bf16,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,8 @@ TOL = {
     "fp32": dict(fused=1e-3, fused_grad=1e-2, occ=1e-3, stack_grad=2e-2, render=1e-3, render_grad=1e-2),
     "tf32": dict(fused=3e-3, fused_grad=3e-1, occ=2e-2, stack_grad=5e-1, render=2e-3, render_grad=5e-1),
     # bf16 operands (8-bit mantissa), fp32 accumulation: per-layer ~3e-3, reported separately
-    "bf16": dict(fused=2e-2, fused_grad=8e-1, occ=1e-1, stack_grad=1.0, render=2e-2, render_grad=1.0),
+    # (activations are also *stored* in bf16 between layers: one more rounding per layer)
+    "bf16": dict(fused=2e-2, fused_grad=8e-1, occ=1.5e-1, stack_grad=1.0, render=2e-2, render_grad=1.0),
 }
 
 
