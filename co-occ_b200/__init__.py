@@ -13,3 +13,4 @@ from . import _lib  # noqa: F401
 from .functional import get_precision, set_precision  # noqa: F401
 from .modules import BiFuser_N, CustomResNet3D, FPN3D, MLP, OccHead, render_fn  # noqa: F401
 from .hotpath import HotPath, model_cfg  # noqa: F401
+from .graph import GraphedStep  # noqa: F401

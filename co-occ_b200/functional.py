@@ -46,6 +46,21 @@ def act_bf16():
 
 PROFILE = None     # bench.py sets this to a list to time every conv launch with CUDA events
 
+# Device-side error flags cannot be read while a CUDA graph is being captured: graph.GraphedStep
+# sets this to a list, the (flag, exception) pairs land there and GraphedStep.check() reads them
+# after a replay.
+DEFERRED_ERRORS = None
+
+
+def _raise_if_set(flag, exc):
+    if torch.cuda.is_current_stream_capturing():
+        if DEFERRED_ERRORS is None:
+            raise RuntimeError("device error flag read during stream capture outside GraphedStep")
+        DEFERRED_ERRORS.append((flag, exc))
+        return
+    if int(flag.item()) != 0:
+        raise exc
+
 
 def _timed(tag, flops, fn, info=""):
     if PROFILE is None:
@@ -511,9 +526,11 @@ def _gsf_direction(L, st, qlist, qrank, qcnt, nq, klist, krank, dims, K, dev, wa
     return None
 
 
-def gsf_index(img5d, pts5d, K, fix_k1_fps=False, want_parts=False):
-    """Runs pack + compact + (FPS, top-K, ball-assign | direct NN) for both directions.
-    Returns the [V,4C] concat buffer with img/pts slices filled and the index state."""
+def gsf_prologue(img5d, pts5d, out=None):
+    """pack + compact of both grids (bifuser_n.py:129-135), no host synchronisation.
+    Returns dict(cat [V,4C] with the img/pts slices filled and the fused slices zero, flags, lists,
+    ranks, counts [2] int32 on the device, ws).  `out` = a previous result whose buffers are reused
+    (graph.GraphedStep keeps them at fixed addresses)."""
     L = _lib.lib()
     st = _stream()
     _require_cuda(img5d, pts5d)
@@ -522,28 +539,66 @@ def gsf_index(img5d, pts5d, K, fix_k1_fps=False, want_parts=False):
     assert img5d.dtype == torch.float32 and pts5d.dtype == torch.float32
     dev = img5d.device
     V = X * Y * Z
-    dims = (X, Y, Z)
-    cat = torch.zeros(V, 4 * C, device=dev, dtype=torch.float32)
-    flags = torch.empty(2, V, device=dev, dtype=torch.uint8)
-    lists = torch.empty(2, V, device=dev, dtype=torch.int32)
-    ranks = torch.empty(2, V, device=dev, dtype=torch.int32)
-    counts = torch.zeros(2, device=dev, dtype=torch.int32)
-    ws = torch.empty(max(int(L.coocc_gsf_compact_workspace(V)), 4), device=dev, dtype=torch.uint8)
+    if out is None:
+        out = dict(cat=torch.zeros(V, 4 * C, device=dev, dtype=torch.float32),
+                   flags=torch.empty(2, V, device=dev, dtype=torch.uint8),
+                   lists=torch.empty(2, V, device=dev, dtype=torch.int32),
+                   ranks=torch.empty(2, V, device=dev, dtype=torch.int32),
+                   counts=torch.zeros(2, device=dev, dtype=torch.int32),
+                   ws=torch.empty(max(int(L.coocc_gsf_compact_workspace(V)), 4), device=dev, dtype=torch.uint8),
+                   dims=(X, Y, Z), C=C)
+    else:
+        assert out["dims"] == (X, Y, Z) and out["C"] == C
+        out["cat"][:, 2 * C:].zero_()
+        out["counts"].zero_()
+    cat, flags, lists, ranks, counts, ws = (out[k] for k in ("cat", "flags", "lists", "ranks", "counts", "ws"))
     for i, t in enumerate((img5d, pts5d)):
         sB, sC, sX, sY, sZ = t.stride()
         _lib.check(L.coocc_gsf_pack(_p(t), sC, sX, sY, sZ, C, X, Y, Z, _pb(cat, i * C * 4), 4 * C,
                                     _p(flags[i]), st), "gsf_pack")
         _lib.check(L.coocc_gsf_compact(_p(flags[i]), V, _p(lists[i]), _p(ranks[i]), _pb(counts, 4 * i),
                                        _p(ws), st), "gsf_compact")
-    n_img, n_pts = (int(v) for v in counts.tolist())          # the one host sync of the fuser
-    state = dict(dims=dims, C=C, K=K, n_img=n_img, n_pts=n_pts, lists=lists, ranks=ranks, counts=counts)
+    return out
+
+
+# graph.GraphedStep sets this while it captures / replays a step: the prologue has already run
+# (eagerly, into fixed buffers) and the occupied-voxel counts are known on the host, so the rest of
+# the fuser needs no synchronisation.  dict(prologue=..., n_img, n_pts, nb_img, nb_pts): n_* exact
+# counts (they select the reference's branches), nb_* >= n_* launch bounds baked into the graph
+# (every kernel reads the exact count from `counts` on the device).
+GSF_OVERRIDE = None
+
+
+def gsf_index(img5d, pts5d, K, fix_k1_fps=False, want_parts=False):
+    """Runs pack + compact + (FPS, top-K, ball-assign | direct NN) for both directions.
+    Returns the [V,4C] concat buffer with img/pts slices filled and the index state."""
+    L = _lib.lib()
+    st = _stream()
+    ov = GSF_OVERRIDE
+    if ov is not None:
+        pro = ov["prologue"]
+        n_img, n_pts, nb_img, nb_pts = ov["n_img"], ov["n_pts"], ov["nb_img"], ov["nb_pts"]
+        assert tuple(img5d.shape[2:]) == pro["dims"] and img5d.shape[1] == pro["C"]
+    else:
+        pro = gsf_prologue(img5d, pts5d)
+        n_img, n_pts = (int(v) for v in pro["counts"].tolist())          # the one host sync of the fuser
+        nb_img, nb_pts = n_img, n_pts
+    cat, lists, ranks, counts = pro["cat"], pro["lists"], pro["ranks"], pro["counts"]
+    dims, C = pro["dims"], pro["C"]
+    X, Y, Z = dims
+    V = X * Y * Z
+    dev = cat.device
+    state = dict(dims=dims, C=C, K=K, n_img=n_img, n_pts=n_pts, nb_img=nb_img, nb_pts=nb_pts, lists=lists,
+                 ranks=ranks, counts=counts)
 
     # direction A: queries = LiDAR voxels, keys = image voxels (bifuser_n.py:137)
     # direction B: queries = image voxels, keys = LiDAR voxels (bifuser_n.py:151)
-    specs = [("A", 1, 0, n_pts), ("B", 0, 1, n_img)]
+    specs = [("A", 1, 0, n_pts, nb_pts), ("B", 0, 1, n_img, nb_img)]
     fps_jobs = []
-    for name, qi, ki, nq in specs:
+    for name, qi, ki, nq, nb in specs:
         if nq <= FPS_NUM:
+            if ov is not None:
+                raise RuntimeError("GSF_OVERRIDE covers the FPS branch only (N_query > 2048)")
             state[name] = _gsf_direction(L, st, lists[qi], ranks[qi], counts[qi:qi + 1], nq, lists[ki], ranks[ki],
                                          dims, K, dev)
         else:
@@ -552,7 +607,7 @@ def gsf_index(img5d, pts5d, K, fix_k1_fps=False, want_parts=False):
                 # the caller's gather broadcasts [1,4,C] against [N,C] and fails
                 raise ReferenceQuirk("reference BiFuser_N(knum=1) fails for N_query > 2048 (fps_NN_fast returns "
                                      "None, bifuser_n.py:62-85); pass fix_k1_fps=True for the intended result")
-            fps_jobs.append((name, qi, ki, nq))
+            fps_jobs.append((name, qi, ki, nb))
     if fps_jobs:
         reps = [torch.empty(FPS_NUM, device=dev, dtype=torch.int32) for _ in fps_jobs]
         j0 = fps_jobs[0]
@@ -612,7 +667,7 @@ class _GSFusionFn(torch.autograd.Function):
         saved = {}
         for name, qi, own_col, key_col, look, dst_col in plan:
             d = state[name]
-            nrep, nq = d["nrep"], (state["n_pts"] if name == "A" else state["n_img"])
+            nrep, nq = d["nrep"], (state["nb_pts"] if name == "A" else state["nb_img"])
             rows = torch.empty(K, nrep + 1, C, device=dev, dtype=torch.float32)
             _lib.check(L.coocc_gsf_gather_rows(_pb(cat, key_col * C * 4), 4 * C, _p(lists[look]),
                                                _pb(counts, 4 * look), _p(d["topk_idx"]), nrep, K, C, _p(rows),
@@ -652,7 +707,7 @@ class _GSFusionFn(torch.autograd.Function):
         for name, qi, own_col, key_col, look, dst_col in plan:
             d = state[name]
             rows, P = saved[name]
-            nrep, nq = d["nrep"], (state["n_pts"] if name == "A" else state["n_img"])
+            nrep, nq = d["nrep"], (state["nb_pts"] if name == "A" else state["nb_img"])
             if nq == 0:
                 continue
             dP = torch.zeros_like(P)
@@ -737,9 +792,9 @@ class _CompositeFn(torch.autograd.Function):
                                                 _p(rgb_map), _p(depth_map), _p(err), _stream()),
                    "render_composite_fwd")
         box = render_box(dims)
-        if box != (100, 100, 8) and int(err.item()) != 0:
-            raise IndexError("render sample inside the 100x100x8 box but outside the feature grid "
-                             "(reference coocc_ray.py:385 raises, SURVEY Q6)")
+        if box != (100, 100, 8):
+            _raise_if_set(err, IndexError("render sample inside the 100x100x8 box but outside the feature grid "
+                                          "(reference coocc_ray.py:385 raises, SURVEY Q6)"))
         ctx.save_for_backward(tab, geom)
         ctx.dims = dims
         return rgb_map, depth_map

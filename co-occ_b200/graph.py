@@ -1,0 +1,182 @@
+"""Whole-step CUDA graphs for the hot path.
+
+One training step of the path is ~800 kernel launches of 10-1000 us each; issued one by one from
+Python the host cannot keep ahead of a B200 (measured: 57 ms of device work took 63-75 ms of wall
+time).  GraphedStep captures forward + backward + gradient all-reduce + optimizer update into one
+CUDA graph and replays it, so the step costs one launch.
+
+What stays outside the graph is the only data-dependent host decision of the path: after
+`pack + compact` (functional.gsf_prologue, run eagerly into fixed buffers) the occupied-voxel counts
+N_img / N_pts are read back, because they select the reference's branches (bifuser_n.py:55 vs :62,
+SURVEY Q1/Q2/Q11) and size the FPS cluster.  Graphs are keyed by the counts rounded up to
+`bucket`; every kernel reads the exact counts from device memory, so one graph serves all scenes of
+its bucket.  Scenes that take a reference branch the graphs do not cover (N <= 2048, N_pts > N_img
+with K > 1) run the ordinary eager path.
+
+Data parallel: the gradient all-reduce (ddp.GradReducer) and the SyncBN statistics all-reduces are
+NCCL calls on the capturing stream and become graph nodes.  NCCL's watchdog thread must not poll
+events of a capturing stream: set TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before init_process_group
+(bench.py does), as PyTorch's CUDA-graph notes require for whole-iteration capture with DDP.
+"""
+import os
+import sys
+
+import torch
+
+from . import functional as CF
+
+
+def _dbg(msg):
+    if os.environ.get("COOCC_DEBUG"):
+        print("[coocc_b200.graph rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
+
+class GraphedStep:
+    """step(img, pts, geom, gt_depth, gt_img, gt_occ) -> loss (a 0-dim tensor that the next
+    replay overwrites).
+
+    model      HotPath (train mode)
+    optimizer  torch optimizer constructed with capturable=True (or None: forward+backward only)
+    reducer    ddp.GradReducer or None
+    loss_keys  which entries of forward_train's loss dict are summed (None = all)
+    """
+
+    def __init__(self, model, optimizer=None, reducer=None, loss_keys=None, bucket=8192, max_graphs=4,
+                 enabled=True):
+        self.model, self.opt, self.reducer = model, optimizer, reducer
+        self.loss_keys = loss_keys
+        self.bucket, self.max_graphs = int(bucket), int(max_graphs)
+        self.enabled = enabled
+        self.graphs = {}            # key -> dict(graph, loss, static inputs, launches)
+        self.prologue = None        # fixed-address pack/compact buffers
+        self.static = None          # fixed-address copies of the small inputs
+        self.stats = dict(replays=0, eager=0, captures=0)
+        self.launches_per_replay = 0
+        self._stream = None         # capture stream; the warm-up step runs on it too, so that autograd's
+        self._warm = False
+        self._last = None           # AccumulateGrad nodes live on the stream the capture uses
+
+    # ------------------------------------------------------------------------------------
+    def _loss(self, losses):
+        keys = self.loss_keys if self.loss_keys is not None else list(losses)
+        return sum(losses[k] for k in keys)
+
+    def _eager(self, img, pts, geom, gt_depth, gt_img, gt_occ):
+        if self.opt is not None:
+            self.opt.zero_grad(set_to_none=True)
+        else:
+            self.model.zero_grad(set_to_none=True)
+        losses, _, _ = self.model.forward_train(img, pts, geom, gt_depth, gt_img, gt_occ)
+        loss = self._loss(losses)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        if self.opt is not None:
+            self.opt.step()
+        return loss.detach()
+
+    def _round(self, n, cap):
+        return min(cap, (n + self.bucket - 1) // self.bucket * self.bucket)
+
+    def _bind_static(self, geom, gt_depth, gt_img, gt_occ):
+        new = dict(geom=geom, gt_depth=gt_depth, gt_img=gt_img, gt_occ=gt_occ)
+        if self.static is None:
+            self.static = {k: (v.clone() if v is not None else None) for k, v in new.items()}
+            return
+        for k, v in new.items():
+            s = self.static[k]
+            if (s is None) != (v is None) or (v is not None and (s.shape != v.shape or s.dtype != v.dtype)):
+                raise RuntimeError("GraphedStep: input %r changed shape/dtype; build a new GraphedStep" % k)
+            if v is not None:
+                s.copy_(v, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------
+    def __call__(self, img, pts, geom, gt_depth, gt_img, gt_occ=None):
+        if not self.enabled:
+            self.stats["eager"] += 1
+            return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+        K = self.model.occ_fuser.knum
+        # optimizer state must exist before a capture (lazy state init allocates and syncs)
+        if self._stream is None:
+            self._stream = torch.cuda.Stream()
+        if not self._warm or (self.opt is not None and len(self.opt.state) == 0):
+            # first call: one ordinary step on the capture stream (lazy CUDA / optimizer-state
+            # initialisation allocates and synchronises, which a capture cannot)
+            self._warm = True
+            self.stats["eager"] += 1
+            _dbg("warm-up step (eager)")
+            cur = torch.cuda.current_stream()
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                loss = self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+            cur.wait_stream(self._stream)
+            return loss
+        self.prologue = CF.gsf_prologue(img, pts, out=self.prologue)
+        n_img, n_pts = (int(v) for v in self.prologue["counts"].tolist())     # the step's one host sync
+        X, Y, Z = self.prologue["dims"]
+        V = X * Y * Z
+        covered = (n_img > CF.FPS_NUM and n_pts > CF.FPS_NUM and not (K > 1 and n_pts > n_img)
+                   and (K > 1 or self.model.occ_fuser.fix_k1_fps))
+        if not covered:
+            self.stats["eager"] += 1
+            return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+        nb_img, nb_pts = self._round(n_img, V), self._round(n_pts, V)
+        key = (nb_img, nb_pts)
+        self._bind_static(geom, gt_depth, gt_img, gt_occ)
+        ov = dict(prologue=self.prologue, n_img=n_img, n_pts=n_pts, nb_img=nb_img, nb_pts=nb_pts)
+        entry = self.graphs.get(key)
+        if entry is None:
+            if len(self.graphs) >= self.max_graphs:
+                self.stats["eager"] += 1
+                return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+            entry = self._capture(key, ov, img, pts)
+        entry["graph"].replay()
+        self.stats["replays"] += 1
+        if self.stats["replays"] <= 2 and os.environ.get("COOCC_DEBUG"):
+            torch.cuda.synchronize()
+            _dbg("replay %d done, loss %.6f" % (self.stats["replays"], float(entry["loss"])))
+        self._last = entry
+        return entry["loss"]
+
+    def check(self):
+        """Raise what the eager path would have raised from device-side error flags of the last
+        replayed step (synchronises; the reference's IndexError cases)."""
+        entry = self._last
+        if entry is None:
+            return
+        for flag, exc in entry["deferred"]:
+            if int(flag.item()) != 0:
+                raise exc
+
+    def _capture(self, key, ov, img, pts):
+        from . import _lib
+        s = self.static
+        if self.opt is not None:
+            self.opt.zero_grad(set_to_none=True)
+        else:
+            self.model.zero_grad(set_to_none=True)
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.CALLS["n"]
+        CF.GSF_OVERRIDE = ov
+        CF.DEFERRED_ERRORS = deferred = []
+        try:
+            _dbg("capture begin key=%s" % (key,))
+            # thread_local: NCCL's watchdog / heartbeat threads query events while this thread captures
+            with torch.cuda.graph(g, stream=self._stream, capture_error_mode="thread_local"):
+                losses, _, _ = self.model.forward_train(img, pts, s["geom"], s["gt_depth"], s["gt_img"], s["gt_occ"])
+                loss = self._loss(losses)
+                loss.backward()
+                if self.reducer is not None:
+                    self.reducer.finish()
+                if self.opt is not None:
+                    self.opt.step()
+                loss = loss.detach()
+        finally:
+            CF.GSF_OVERRIDE = None
+            CF.DEFERRED_ERRORS = None
+        _dbg("capture end")
+        entry = dict(graph=g, loss=loss, launches=_lib.CALLS["n"] - n0, deferred=deferred)
+        self.launches_per_replay = entry["launches"]
+        self.graphs[key] = entry
+        self.stats["captures"] += 1
+        return entry

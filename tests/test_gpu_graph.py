@@ -1,0 +1,139 @@
+"""GraphedStep (co-occ_b200/graph.py): a step replayed as one CUDA graph must give the same losses
+and the same updated parameters as the step launched kernel by kernel, also when the scene (and
+therefore N_img / N_pts inside the bucket) changes between replays."""
+import copy
+
+import pytest
+import torch
+
+import coocc_b200
+from coocc_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+KEYS = ["loss_voxel_ce_c_0", "loss_depth_render", "loss_rgb"]
+
+
+def _scene(name, seed):
+    cfg = S.CONFIGS[name]
+    inp = S.make_inputs(name, seed)
+    img, pts, geom, gi, gd = (inp[k] for k in ("img_voxel_feats", "pts_voxel_feats", "geom", "gt_img", "gt_depth"))
+    g = torch.Generator().manual_seed(seed + 5)
+    occ = torch.randint(0, 17, (1,) + tuple(cfg["grid"]), generator=g)
+    return [t.to(DEV) for t in (img, pts, geom, gd, gi, occ)]
+
+
+def _build(name, seed=0, lr=1e-3):
+    cfg = S.CONFIGS[name]
+    torch.manual_seed(seed)
+    model = coocc_b200.HotPath(coocc_b200.model_cfg(cfg["C"], cfg["K"]), cfg["C"]).to(DEV).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=0.01, fused=True, capturable=True)
+    return model, opt
+
+
+def _rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+LAST = ("pts_bbox_head.occ_pred_conv.3.weight", "rgb_head.output_layer.weight", "sigma_head.output_layer.weight")
+
+
+def _grad_err(ma, mb):
+    """(relative L2 over all parameter gradients, worst relative L2 over the last-layer gradients)."""
+    num = den = 0.0
+    last = 0.0
+    for (n, p), q in zip(ma.named_parameters(), mb.parameters()):
+        if p.grad is None:
+            assert q.grad is None, n
+            continue
+        d = (p.grad.double() - q.grad.double())
+        num += float((d * d).sum())
+        den += float((p.grad.double() ** 2).sum())
+        if n in LAST:
+            last = max(last, _rel_l2(q.grad, p.grad))
+    return (num / max(den, 1e-300)) ** 0.5, last
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_forward_backward_matches_eager(precision):
+    """No optimizer, fixed parameters: per scene, the replayed graph gives the eager step's loss and
+    gradients.  The step is not bit-reproducible run to run (BatchNorm statistics and split-K use
+    atomics) and the ReLU/BatchNorm stack amplifies that rounding noise in the deep gradients (tiny
+    13x13x1 / 7x7x1 levels), so: the loss and the last-layer gradients (no ReLU mask behind them) are
+    held to a tight bound, all gradients together to a small multiple of the eager-vs-eager noise."""
+    coocc_b200.set_precision(precision)
+    try:
+        scenes = [_scene("c1", s) for s in (0, 1, 2, 0)]
+        m_e, _ = _build("c1")
+        m_2, _ = _build("c1")
+        m_g, _ = _build("c1")
+        m_2.load_state_dict(copy.deepcopy(m_e.state_dict()))
+        m_g.load_state_dict(copy.deepcopy(m_e.state_dict()))
+        eager = coocc_b200.GraphedStep(m_e, None, None, KEYS, enabled=False)
+        eager2 = coocc_b200.GraphedStep(m_2, None, None, KEYS, enabled=False)
+        graph = coocc_b200.GraphedStep(m_g, None, None, KEYS, bucket=1 << 20)      # one bucket: one graph
+        tol_l, tol_last = (2e-5, 1e-3) if precision == "fp32" else (2e-3, 3e-2)
+        for sc in scenes:
+            le, l2, lg = float(eager(*sc)), float(eager2(*sc)), float(graph(*sc))
+            graph.check()
+            assert abs(le - lg) <= tol_l * abs(le), (le, lg)
+            noise, _ = _grad_err(m_e, m_2)
+            err, last = _grad_err(m_e, m_g)
+            assert last <= tol_last, (last, err, noise)
+            assert err <= 4 * noise + 1e-4, (err, noise)
+        assert graph.stats["captures"] == 1 and graph.stats["replays"] == len(scenes) - 1 and graph.stats["eager"] == 1
+        assert graph.launches_per_replay > 50
+    finally:
+        coocc_b200.set_precision("tf32")
+
+
+def test_graph_training_steps_track_eager():
+    """With AdamW inside the graph.  Adam's first updates are ~lr*sign(g) for every weight, so rounding
+    noise in near-zero gradients becomes lr-sized parameter differences and a run at a normal learning
+    rate decorrelates from its own repeat within a few steps (tiny 7x7x1 BatchNorm levels); the check
+    therefore uses a small learning rate: losses track the eager run closely, the accumulated parameter
+    update has the eager run's direction and size, integer buffers advance identically."""
+    coocc_b200.set_precision("fp32")
+    try:
+        lr, n = 1e-5, 6
+        scenes = [_scene("c1", s % 2) for s in range(n)]
+        m_e, o_e = _build("c1", lr=lr)
+        m_g, o_g = _build("c1", lr=lr)
+        p0 = copy.deepcopy(m_e.state_dict())
+        m_g.load_state_dict(copy.deepcopy(p0))
+        eager = coocc_b200.GraphedStep(m_e, o_e, None, KEYS, enabled=False)
+        graph = coocc_b200.GraphedStep(m_g, o_g, None, KEYS, bucket=1 << 20)
+        le = [float(eager(*sc)) for sc in scenes]
+        lg = [float(graph(*sc)) for sc in scenes]
+        torch.cuda.synchronize()
+        assert graph.stats["captures"] == 1 and graph.stats["replays"] == n - 1
+        for a, b in zip(le, lg):
+            assert abs(a - b) <= 1e-3 * abs(a), (le, lg)
+        for (k, b), c in zip(m_e.named_buffers(), m_g.buffers()):
+            if not b.dtype.is_floating_point:
+                assert torch.equal(b, c) and (k.endswith("scales") or int(b) == n), k   # num_batches_tracked
+        dot = ne = ng = 0.0
+        for (k, p), q in zip(m_e.named_parameters(), m_g.parameters()):
+            de, dg = (p.detach() - p0[k]).double(), (q.detach() - p0[k]).double()
+            dot, ne, ng = dot + float((de * dg).sum()), ne + float((de * de).sum()), ng + float((dg * dg).sum())
+        assert ne > 0 and ng > 0
+        assert dot / (ne * ng) ** 0.5 > 0.9, dot / (ne * ng) ** 0.5          # same direction
+        assert 0.9 < (ng / ne) ** 0.5 < 1.1, (ng / ne) ** 0.5                # same size
+    finally:
+        coocc_b200.set_precision("tf32")
+
+
+def test_graph_falls_back_to_eager_outside_covered_branches():
+    """c1k1 (K=1, N <= 2048) takes the reference's brute-force branch: not captured, still correct."""
+    coocc_b200.set_precision("fp32")
+    try:
+        sc = _scene("c1k1", 0)
+        m, o = _build("c1k1")
+        g = coocc_b200.GraphedStep(m, o, None, KEYS)
+        l0 = float(g(*sc))
+        l1 = float(g(*sc))
+        l2 = float(g(*sc))
+        assert g.stats["captures"] == 0 and g.stats["eager"] == 3
+        assert l2 < l0 or l1 < l0       # the optimizer is stepping
+    finally:
+        coocc_b200.set_precision("tf32")

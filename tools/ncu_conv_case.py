@@ -11,9 +11,10 @@ for (X, Y, Z, Cin, Cout) in ((200, 200, 16, 512, 256), (200, 200, 16, 128, 128))
     xc = torch.randn(X * Y * Z, Cin, device=dev).to(torch.bfloat16)
     wc = (torch.randn(Cout, 27 * Cin, device=dev) * 0.01).to(torch.bfloat16)
     gy = torch.randn(X * Y * Z, Cout, device=dev).to(torch.bfloat16)
-    y = torch.empty(X * Y * Z, Cout, device=dev); dx = torch.empty(X * Y * Z, Cin, device=dev)
+    y = torch.empty(X * Y * Z, Cout, device=dev, dtype=torch.bfloat16)      # bf16 activation storage (the step's default)
+    dx = torch.empty(X * Y * Z, Cin, device=dev, dtype=torch.bfloat16)
     dw = torch.zeros(Cout, 27 * Cin, device=dev); stats = torch.zeros(2, Cout, device=dev)
-    d = _lib.ConvDesc(X, Y, Z, Cin, Cout, 3, 1, dtype, Cin, Cout)
+    d = _lib.ConvDesc(X, Y, Z, Cin, Cout, 3, 1, dtype, Cin, Cout, 1)
     for _ in range(2):
         L.coocc_conv3d_fwd(ctypes.byref(d), xc.data_ptr(), wc.data_ptr(), y.data_ptr(), Cout, None, 0, stats.data_ptr(), st())
         L.coocc_conv3d_dgrad(ctypes.byref(d), gy.data_ptr(), wc.data_ptr(), dx.data_ptr(), Cin, st())
