@@ -32,6 +32,14 @@ import torch  # noqa: E402
 METRIC = "voxels/sec fwd+bwd (fused-voxel hot path: GSFusion + 3D conv decoder/head + volume render)"
 UNIT = "voxels/s"
 CPU_SAMPLE_GRID = (40, 40, 8)
+# dram__bytes_read.sum + dram__bytes_write.sum of one tc_conv_kernel launch from the committed
+# `ncu --set full` capture (tools/profile_round.sh -> profiles/r01b_ncu_full_tc_conv_bf16.summary.txt)
+NCU_TRAFFIC = dict(bytes=286.06e6,
+                   note="ncu --set full, fwd 3x3x3 128->128 on the 200x200x16 grid, bf16 in/out: DRAM read 164.85 MB + write "
+                        "121.21 MB per launch vs 327.7 MB algorithmic (x read once, y written once, tail of y still in L2); "
+                        "tensor pipe 79% active; dgrad 285.9 MB; wgrad 872 MB vs 327.7 MB algorithmic (the three ky taps "
+                        "re-read X through L2 misses) at 89% tensor-pipe activity "
+                        "(profiles/r01b_ncu_full_tc_conv_bf16.summary.txt)")
 
 
 def parse():
@@ -214,7 +222,6 @@ def run_ours(args, cfg):
         if args.launch == "graph":
             # whole-step capture includes NCCL calls: the watchdog must not poll a capturing stream
             os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
-            os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
     coocc_b200.set_precision(args.precision)
     C, K = cfg["C"], cfg["K"]
@@ -341,10 +348,21 @@ def run_ours(args, cfg):
         peak, peak_src = 1400.0, "fallback sustained bf16 (B200_PROFILING.md)"
     achieved = f_conv / t_conv / 1e12 if t_conv > 0 else 0.0
 
+    def shutdown():
+        if world == 1:
+            return
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if args.launch == "graph":
+            # measured on 2 x B200: destroy_process_group() does not return while CUDA graphs holding
+            # captured NCCL kernels are alive; all ranks are past the final barrier, so just exit
+            os._exit(0)
+        dist.destroy_process_group()
+
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        shutdown()
         return
     value = nvox * world * args.steps / (ms / 1e3)
     e2e_val = nvox * world * args.steps / (ms_e2e / 1e3)
@@ -356,13 +374,12 @@ def run_ours(args, cfg):
                          d2h_bytes_per_step=4, loss=last.get("loss")),
                 gpu_launches=launches,
                 roofline=dict(bound="tensor", kernel="tc_conv_kernel (all conv/linear launches of one step)",
-                              achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                              achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                              traffic=NCU_TRAFFIC["bytes"] if args.precision == "bf16" else None,
                               launches_per_step=n_conv, algorithmic_flops_per_step=f_conv,
                               kernel_ms_per_step=t_conv * 1e3, share_of_step=t_conv * 1e3 / (ms / args.steps),
                               peak_source=peak_src,
-                              traffic_note="ncu --set full of the same kernel (profiles/r01_ncu_full_tc_conv_bf16.summary.txt): "
-                                           "DRAM read+write ~= algorithmic bytes (input read once, output written once); the "
-                                           "kernel is bound by the L2->SM operand stream, not HBM",
+                              traffic_note=NCU_TRAFFIC["note"],
                               note="tf32 math has half the nominal bf16 rate" if args.precision == "tf32" else ""))
     line["parity"] = dict(mode=args.precision,
                           note="fp32 mode (3xTF32 split) matches the oracle to 3e-5 on logits; tf32 ~1e-2; bf16 ~5e-2 "
@@ -370,9 +387,7 @@ def run_ours(args, cfg):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():
