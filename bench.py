@@ -5,7 +5,8 @@
                     [--workload northstar|r50|r101|openocc] [--precision tf32|bf16|fp32]
 
 One "step" = one training pass of the hot path over one synthetic scene per GPU:
-GSFusion (BiFuser_N) -> CustomResNet3D-18 -> FPN3D -> OccHead coarse logits + cross-entropy,
+GSFusion (BiFuser_N) -> CustomResNet3D-18 -> FPN3D -> OccHead coarse logits + OccHead.loss (label
+vote to the working grid, CE + sem_scal + geo_scal + Lovasz-softmax),
 the volume-render regulariser with its two losses, backward through all of it, the data-parallel
 gradient all-reduce (N > 1) and the AdamW update.  `value` = X*Y*Z voxels of the working grid x
 scenes per step / time, summed over ranks (weak scaling, one scene per GPU like samples_per_gpu=1).
@@ -66,10 +67,7 @@ def cpu_sample_inputs(cfg, seed=0):
     inp = dict(img_voxel_feats=img, pts_voxel_feats=pts,
                geom=S.make_geom(grid, cfg["cams"], cfg["fH"], cfg["fW"], cfg["D"], seed))
     inp["gt_img"], inp["gt_depth"] = S.make_render_targets(cfg["cams"], cfg["fH"], cfg["fW"], seed)
-    g = torch.Generator().manual_seed(seed + 5)
-    occ = torch.randint(1, 17, (1,) + grid, generator=g)
-    occ[torch.rand((1,) + grid, generator=g) < 0.9] = 0
-    inp["gt_occ"] = occ
+    inp["gt_occ"] = S.make_gt_occ(grid, 2, seed)
     return inp, grid
 
 
@@ -78,6 +76,7 @@ def cpu_step_fn(cfg, seed=0):
     import torch.nn.functional as F
     from coocc_b200 import synthetic as S
     from oracle import oracle as O
+    from oracle import losses as OL
     inp, grid = cpu_sample_inputs(cfg, seed)
     C, K = cfg["C"], cfg["K"]
     planes = [C, 2 * C, 4 * C, 8 * C]
@@ -94,7 +93,7 @@ def cpu_step_fn(cfg, seed=0):
         img = inp["img_voxel_feats"].clone().requires_grad_(True)
         pts = inp["pts_voxel_feats"].clone().requires_grad_(True)
         out = O.hot_path_forward(P, dict(inp, img_voxel_feats=img, pts_voxel_feats=pts), K, tie="canonical")
-        loss = F.cross_entropy(out["occ"], inp["gt_occ"], ignore_index=255) + out["loss_depth_render"] + out["loss_rgb"]
+        loss = sum(OL.loss_voxel(out["occ"], inp["gt_occ"]).values()) + out["loss_depth_render"] + out["loss_rgb"]
         loss.backward()
         return loss.item()
 
@@ -144,7 +143,8 @@ def workload_config(args, cfg):
     X, Y, Z = cfg["grid"]
     return dict(workload="%s: %dx%dx%d working grid, C=%d, K=%d, %d cams x %d rays x %d samples, 1 scene/GPU"
                          % (args.workload, X, Y, Z, cfg["C"], cfg["K"], cfg["cams"], cfg["fH"] * cfg["fW"], cfg["D"]),
-                step="GSFusion + ResNet3D-18 + FPN3D + OccHead(coarse)+CE + render losses, backward, grad all-reduce, AdamW",
+                step="GSFusion + ResNet3D-18 + FPN3D + OccHead(coarse) + OccHead.loss (label vote, CE, sem_scal, geo_scal, "
+                     "Lovasz) + render losses, backward, grad all-reduce, AdamW",
                 l2="inputs (%.0f MB/step) exceed the 126 MB L2" % (2 * X * Y * Z * cfg["C"] * 4 / 1e6),
                 parallelism="dp%d (replicas only)" % args.gpus, precision=args.precision,
                 launch="cuda_graph (whole step, co-occ_b200/graph.py)" if args.launch == "graph" else "eager")
@@ -234,7 +234,8 @@ def run_ours(args, cfg):
     params = [p for p in model.parameters() if p.requires_grad]
     reducer = GradReducer(params)
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True, capturable=(args.launch == "graph"))
-    LOSS_KEYS = ["loss_voxel_ce_c_0", "loss_depth_render", "loss_rgb"]
+    LOSS_KEYS = ["loss_voxel_ce_c_0", "loss_voxel_sem_scal_c_0", "loss_voxel_geo_scal_c_0", "loss_voxel_lovasz_c_0",
+                 "loss_depth_render", "loss_rgb"]
     gstep = coocc_b200.GraphedStep(model, opt, reducer, LOSS_KEYS, enabled=(args.launch == "graph"))
 
     # ---- synthetic scene of this rank in pinned host memory (upstream memory layouts) ------
@@ -245,10 +246,7 @@ def run_ours(args, cfg):
                 geom=S.make_geom(cfg["grid"], cfg["cams"], cfg["fH"], cfg["fW"], cfg["D"], seed).pin_memory())
     gi, gd = S.make_render_targets(cfg["cams"], cfg["fH"], cfg["fW"], seed)
     host["gt_img"], host["gt_depth"] = gi.pin_memory(), gd.pin_memory()
-    g = torch.Generator().manual_seed(seed + 5)
-    occ = torch.randint(1, 17, (1, X, Y, Z), generator=g)
-    occ[torch.rand(1, X, Y, Z, generator=g) < 0.9] = 0
-    host["gt_occ"] = occ.pin_memory()
+    host["gt_occ"] = S.make_gt_occ(cfg["grid"], 2, seed).pin_memory()      # int64 labels at twice the working grid
     h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
 
     def to_device():

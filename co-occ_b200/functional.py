@@ -99,9 +99,11 @@ def to_cl2d(x5d):
     B, C, X, Y, Z = x5d.shape
     assert B == 1, "the hot path is batch-1 like the reference (coocc_ray.py:365)"
     x = x5d.permute(0, 2, 3, 4, 1)
-    if not x.is_contiguous():
-        x = x.contiguous()
-    return x.reshape(X * Y * Z, C), (X, Y, Z)
+    try:
+        # also zero-copy for rows with a padded stride (e.g. the 17-class logits, row stride 20)
+        return x.view(X * Y * Z, C), (X, Y, Z)
+    except RuntimeError:
+        return x.contiguous().reshape(X * Y * Z, C), (X, Y, Z)
 
 
 def to_5d(x2d, dims):
@@ -856,3 +858,66 @@ def composite(tab, geom, dims):
 
 def upsample_losses(rgb_map, depth_map, gt_img, gt_depth, D):
     return _UpsampleLossFn.apply(rgb_map, depth_map, gt_img, gt_depth, D)
+
+
+# ----------------------------------------------------------------------------------------
+# Occupancy-head voxel losses (OccHead.loss_voxel, occ_head.py:267-293)
+# ----------------------------------------------------------------------------------------
+def downsample_labels(target_voxels, dims, empty_idx=0):
+    """[1, X*r, Y*r, Z*r] integer labels -> int32 [X*Y*Z]: the reference's torch.mode vote
+    (occ_head.py:269-280); r = 1 just converts."""
+    L = _lib.lib()
+    _require_cuda(target_voxels)
+    assert target_voxels.dim() == 4 and target_voxels.shape[0] == 1, "batch 1 like the rest of the path"
+    X, Y, Z = dims
+    r = target_voxels.shape[2] // X      # occ_head.py:271 takes the ratio from the second spatial extent
+    assert tuple(target_voxels.shape[1:]) == (X * r, Y * r, Z * r), "label grid must be an integer multiple of the output"
+    if target_voxels.dtype not in (torch.uint8, torch.int32, torch.int64):
+        target_voxels = target_voxels.long()
+    t = target_voxels.contiguous()
+    if r == 1:
+        return t.reshape(-1).to(torch.int32)
+    out = torch.empty(X * Y * Z, device=t.device, dtype=torch.int32)
+    _lib.check(L.coocc_occ_label_mode(_p(t), t.element_size(), X, Y, Z, r, int(empty_idx), _p(out), _stream()),
+               "occ_label_mode")
+    return out
+
+
+class _OccLossFn(torch.autograd.Function):
+    """logits [V,C] fp32 rows, labels int32 [V] -> float[4] = (CE, sem_scal, geo_scal, lovasz)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, class_w, ignore, empty_idx):
+        L = _lib.lib()
+        _require_cuda(logits, labels)
+        logits = _as_rows(logits.float() if logits.dtype != torch.float32 else logits)
+        V, C = logits.shape
+        assert labels.dtype == torch.int32 and labels.numel() == V
+        nbytes = int(L.coocc_occ_loss_workspace(V, C))
+        if nbytes < 0:
+            raise RuntimeError("coocc_occ_loss: unsupported size V=%d C=%d" % (V, C))
+        ws = torch.empty(nbytes, device=logits.device, dtype=torch.uint8)
+        losses = torch.empty(4, device=logits.device, dtype=torch.float32)
+        cw = class_w.to(device=logits.device, dtype=torch.float32).contiguous() if class_w is not None else None
+        _lib.check(L.coocc_occ_loss_fwd(_p(logits), logits.stride(0), _p(labels), V, C, _p(cw), int(ignore),
+                                        int(empty_idx), _p(ws), _p(losses), _stream()), "occ_loss_fwd")
+        ctx.save_for_backward(logits, labels, cw, ws)
+        ctx.meta = (int(ignore), int(empty_idx))
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        logits, labels, cw, ws = ctx.saved_tensors
+        ignore, empty_idx = ctx.meta
+        V, C = logits.shape
+        g = g.contiguous().float()
+        ld = (C + 3) // 4 * 4
+        d = torch.empty(V, ld, device=logits.device, dtype=torch.float32)
+        _lib.check(L.coocc_occ_loss_bwd(_p(logits), logits.stride(0), _p(labels), V, C, _p(cw), ignore, empty_idx,
+                                        _p(ws), _p(g), _p(d), ld, _stream()), "occ_loss_bwd")
+        return d[:, :C], None, None, None, None
+
+
+def occ_voxel_losses(logits2d, labels, class_w=None, ignore=255, empty_idx=0):
+    return _OccLossFn.apply(logits2d, labels, class_w, ignore, empty_idx)

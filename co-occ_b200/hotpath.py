@@ -9,7 +9,6 @@ package; this class is what tests, smoke() and bench.py drive.
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import registry
 from .modules import MLP, render_fn
@@ -54,7 +53,7 @@ class HotPath(nn.Module):
             self.rgb_head.load_state_dict({k[9:]: v for k, v in r.items() if k.startswith("rgb_head.")})
 
     def forward_train(self, img_voxel_feats, pts_voxel_feats, geom=None, gt_depth=None, gt_img=None,
-                      gt_occ=None, class_weights=None):
+                      gt_occ=None):
         voxel_feats = self.occ_fuser(img_voxel_feats, pts_voxel_feats)          # coocc_ray.py:252-253
         mid_voxel = self.semantic_encoder(voxel_feats)                          # :328
         semantic_voxel = self.semantic_neck(mid_voxel)                          # :329
@@ -62,9 +61,9 @@ class HotPath(nn.Module):
         occ = outs["output_voxels"][0]
         losses = {}
         if gt_occ is not None:
-            # coarse cross-entropy of OccHead.loss_voxel (occ_head.py:289, CE_ssc_loss); the other
-            # three occupancy losses belong to SURVEY §8f rank 1 ("next")
-            losses["loss_voxel_ce_c_0"] = F.cross_entropy(occ, gt_occ, weight=class_weights, ignore_index=255)
+            # coocc_ray.py:349-351 -> OccHead.loss: CE + sem_scal + geo_scal + Lovasz on the coarse logits
+            # against gt_occ (label grid = integer multiple of the working grid, 255 = ignore)
+            losses.update(self.pts_bbox_head.loss(output_voxels=outs["output_voxels"], target_voxels=gt_occ))
         if self.use_rendering and geom is not None:                             # :358-433
             _, _, rl = render_fn(voxel_feats, geom, self.sigma_head, self.rgb_head, gt_depth, gt_img)
             losses.update(rl)

@@ -19,6 +19,12 @@ from . import functional as CF
 from .registry import BACKBONES, FUSION_LAYERS, HEADS, NECKS
 
 
+# voxel counts per nuScenes-occupancy class (P/utils/nusc_param.py:10-12), class 0 = free
+NUSC_CLASS_FREQUENCIES = [2242961742295, 25985376, 1561108, 28862014, 196106643, 15920504, 2158753, 26539491,
+                          4004729, 34838681, 75173306, 2255027978, 50959399, 646022466, 869055679, 1446141335,
+                          1724391378]
+
+
 def _norm_layer(norm_cfg, c):
     cfg = dict(norm_cfg or dict(type="BN3d"))
     typ = cfg.pop("type")
@@ -248,6 +254,21 @@ class OccHead(nn.Module):
         self.empty_idx = empty_idx
         self.final_occ_size = final_occ_size
         self.fine_topk = fine_topk
+        # loss weights and class weights: occ_head.py:82-98, 134-145
+        lw = loss_weight_cfg or {}
+        self.loss_voxel_ce_weight = lw.get('loss_voxel_ce_weight', 1.0)
+        self.loss_voxel_sem_scal_weight = lw.get('loss_voxel_sem_scal_weight', 1.0)
+        self.loss_voxel_geo_scal_weight = lw.get('loss_voxel_geo_scal_weight', 1.0)
+        self.loss_voxel_lovasz_weight = lw.get('loss_voxel_lovasz_weight', 1.0)
+        if data_type != 'nus':
+            raise NotImplementedError("hot path covers the nuScenes head (17 classes)")
+        if balance_cls_weight:
+            cw = 1.0 / torch.log(torch.tensor(NUSC_CLASS_FREQUENCIES, dtype=torch.float64) + 0.001)
+        else:
+            cw = torch.ones(17, dtype=torch.float64) / 17
+        # a plain attribute in the reference (not in its state_dict): non-persistent buffer, so it follows
+        # .to(device) and no host->device copy happens inside a captured step
+        self.register_buffer("class_weights", cw.float(), persistent=False)
         bias = dict(conv_cfg).get("bias", True)
         self.occ_convs = nn.ModuleList()
         for i in range(num_level):
@@ -284,6 +305,30 @@ class OccHead(nn.Module):
         y, _ = conv_bn_act(feats, d0, self.occ_pred_conv[0], self.occ_pred_conv[1])
         occ, _ = conv_bn_act(y, d0, self.occ_pred_conv[3], None, relu=False)
         return {"out_voxel_feats": [CF.to_5d(feats, d0)], "occ": [CF.to_5d(occ, d0)]}
+
+    def loss_voxel(self, output_voxels, target_voxels, tag):
+        """occ_head.py:267-293: label vote to the output resolution, then CE / sem_scal / geo_scal /
+        Lovasz-softmax, all in csrc/occ_loss.cu (one autograd node)."""
+        x2d, dims = CF.to_cl2d(output_voxels)
+        labels = CF.downsample_labels(target_voxels, dims, self.empty_idx)
+        cw = self.class_weights
+        if cw.device != x2d.device:
+            cw = cw.to(x2d.device)
+        l4 = CF.occ_voxel_losses(x2d, labels, cw, 255, self.empty_idx)
+        return {'loss_voxel_ce_{}'.format(tag): self.loss_voxel_ce_weight * l4[0],
+                'loss_voxel_sem_scal_{}'.format(tag): self.loss_voxel_sem_scal_weight * l4[1],
+                'loss_voxel_geo_scal_{}'.format(tag): self.loss_voxel_geo_scal_weight * l4[2],
+                'loss_voxel_lovasz_{}'.format(tag): self.loss_voxel_lovasz_weight * l4[3]}
+
+    def loss(self, output_voxels=None, output_coords_fine=None, output_voxels_fine=None, target_voxels=None,
+             target_points=None, img_metas=None, visible_mask=None, **kwargs):
+        """occ_head.py:314-337 (coarse levels; the fine/cascade stage and lidarseg are not on the path)."""
+        loss_dict = {}
+        for index, output_voxel in enumerate(output_voxels):
+            loss_dict.update(self.loss_voxel(output_voxel, target_voxels, tag='c_{}'.format(index)))
+        if output_voxels_fine is not None or target_points:
+            raise NotImplementedError("OccHead fine stage / lidarseg losses are outside the hot path (SURVEY §8f)")
+        return loss_dict
 
     def forward(self, voxel_feats, img_feats=None, img_metas=None, pts_feats=None, target_points=None,
                 transform=None, **kwargs):

@@ -99,6 +99,28 @@ def make_render_targets(cams, fH, fW, seed=0):
     return gt_img, gt_depth
 
 
+def make_gt_occ(grid, ratio=2, seed=0, num_cls=17):
+    """gt_occ [1, X*r, Y*r, Z*r] int64 labels (0 = free, 1..16 classes, 255 = ignore) at `ratio` times the
+    working grid, like the 200x200x16 nuScenes-occupancy labels over the 100x100x8 grid
+    (coocc_multi_r50_256x704.py: occ_size vs. voxel grid).  About a quarter of the coarse cells hold
+    an object; inside them roughly half of the sub-voxels carry its label, a few carry another class
+    (so the reference's torch.mode vote, occ_head.py:269-280, sees majorities, ties and singletons),
+    1 % of all sub-voxels are 255."""
+    X, Y, Z = grid
+    g = _gen(seed + 97)
+    coarse = torch.randint(1, num_cls, (X, Y, Z), generator=g)
+    occupied = torch.rand(X, Y, Z, generator=g) < 0.25
+    up = lambda t: t.repeat_interleave(ratio, 0).repeat_interleave(ratio, 1).repeat_interleave(ratio, 2)
+    fine = up(coarse)
+    shape = fine.shape
+    keep = up(occupied) & (torch.rand(shape, generator=g) < 0.5)
+    fine = torch.where(keep, fine, torch.zeros_like(fine))
+    other = torch.rand(shape, generator=g) < 0.03
+    fine = torch.where(other, torch.randint(1, num_cls, shape, generator=g), fine)
+    fine = torch.where(torch.rand(shape, generator=g) < 0.01, torch.full_like(fine, 255), fine)
+    return fine[None].contiguous()
+
+
 def make_inputs(name, seed=0, with_render=True):
     cfg = CONFIGS[name]
     img, pts = make_voxel_feats(cfg["grid"], cfg["C"], cfg["p_img"], cfg["p_pts"], seed,

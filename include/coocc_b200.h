@@ -159,6 +159,30 @@ int coocc_render_upsample_loss_bwd(const float* rgbs, const float* depths, int n
                                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Occupancy-head voxel losses (csrc/occ_loss.cu) -- SURVEY §8f rank 1, coarse level.
+ * Replaces OccHead.loss_voxel, P/coocc/dense_heads/occ_head.py:267-293: the torch.mode label
+ * downsample (:269-280), CE_ssc_loss / sem_scal_loss / geo_scal_loss (P/utils/semkitti.py:139-149,
+ * 92-136, 62-89) and lovasz_softmax (P/coocc/dense_heads/lovasz_softmax.py:20-34, 156-203).
+ * ------------------------------------------------------------------------------------------ */
+/* labels: [X*ratio][Y*ratio][Z*ratio] contiguous, label_bytes = 1 (uint8), 4 (int32) or 8 (int64);
+ * out int32[X*Y*Z]: the most frequent label of each ratio^3 cell, where inside a non-empty cell every 0
+ * counts as a value of its own (so an empty sub-voxel never out-votes a pair of equal labels and a
+ * cell of singletons becomes 255), ties -> smallest value (torch.mode). */
+int coocc_occ_label_mode(const void* labels, int label_bytes, int X, int Y, int Z, int ratio, int empty_idx,
+                         int* out, void* stream);
+/* bytes of the workspace shared by coocc_occ_loss_fwd / _bwd for V voxels and C classes (C <= 32) */
+long long coocc_occ_loss_workspace(int V, int C);
+/* logits [V][ld] fp32 (ld >= C), labels int32[V] (`ignore` = void label), class_w float[C] or NULL.
+ * losses4 (device float[4]) = (CE, sem_scal, geo_scal, lovasz_softmax), unweighted.
+ * The workspace keeps what the backward needs (coefficients, Lovasz gradients). */
+int coocc_occ_loss_fwd(const float* logits, long long ld, const int* labels, int V, int C, const float* class_w,
+                       int ignore, int empty_idx, void* workspace, float* losses4, void* stream);
+/* dlogits [V][ldd] = sum_k g_losses4[k] * d losses4[k] / d logits  (g_losses4: device float[4]) */
+int coocc_occ_loss_bwd(const float* logits, long long ld, const int* labels, int V, int C, const float* class_w,
+                       int ignore, int empty_idx, const void* workspace, const float* g_losses4, float* dlogits,
+                       long long ldd, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * BatchNorm3d (training mode) + ReLU + residual, and x2 zero insertion (csrc/elementwise.cu).
  * Replaces torch.nn.BatchNorm3d / SyncBatchNorm + nn.ReLU (+ `out += residual`) at
  * P/coocc/fuser/bifuser_n.py:25-29, P/coocc/backbones/resnet3d.py:46-62, P/coocc/necks/fpn3d.py:48-67,

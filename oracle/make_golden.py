@@ -125,9 +125,62 @@ def golden_for(name, ns):
     return g
 
 
+def golden_losses(ns):
+    """Reference OccHead.loss_voxel (occ_head.py:267-293) and its four loss functions, run as they are
+    on seeded logits / labels of the c1 grid (labels at twice the resolution) and on a ratio-1 case."""
+    import sys
+    mod = sys.modules["projects.mmdet3d_plugin.coocc.dense_heads.occ_head"]
+    cfg = S.CONFIGS["c1"]
+    grid = cfg["grid"]
+    head = ns.OccHead(norm_cfg=dict(type="SyncBN", requires_grad=True), soft_weights=True, cascade_ratio=2,
+                      sample_from_voxel=False, sample_from_img=False, final_occ_size=[2 * s for s in grid],
+                      fine_topk=15000, empty_idx=0, num_level=4, in_channels=[64] * 4, out_channel=17,
+                      point_cloud_range=[-50, -50, -5.0, 50, 50, 3.0])
+    g = {}
+    gen = torch.Generator().manual_seed(2024)
+    logits = (torch.randn(1, 17, *grid, generator=gen) * 2.0)
+    logits[:, 0] += 1.5                                   # free space dominates, like a trained head
+    gt = S.make_gt_occ(grid, 2, seed=0)
+    seen = {}
+    orig = mod.CE_ssc_loss
+
+    def spy(pred, target, *a, **k):
+        seen["tv"] = target.clone()
+        return orig(pred, target, *a, **k)
+
+    mod.CE_ssc_loss = spy
+    try:
+        x = logits.clone().requires_grad_(True)
+        ld = head.loss_voxel(x, gt.clone(), tag="c_0")
+    finally:
+        mod.CE_ssc_loss = orig
+    g["tv"] = seen["tv"].numpy().astype(np.uint8)
+    names = ["loss_voxel_ce_c_0", "loss_voxel_sem_scal_c_0", "loss_voxel_geo_scal_c_0", "loss_voxel_lovasz_c_0"]
+    g["losses"] = np.array([ld[k].item() for k in names], dtype=np.float64)
+    coef = [1.0, 0.7, 1.3, 0.9]
+    sum(c * ld[k] for c, k in zip(coef, names)).backward()
+    g["coef"] = np.array(coef)
+    g["dlogits_sample"], g["dlogits_stats"] = sample(x.grad), stats(x.grad)
+    for i, k in enumerate(names):                          # per-loss gradients
+        x2 = logits.clone().requires_grad_(True)
+        head.loss_voxel(x2, gt.clone(), tag="c_0")[k].backward()
+        g["d%d_sample" % i], g["d%d_stats" % i] = sample(x2.grad), stats(x2.grad)
+    # ratio 1 (labels already at the output resolution), a class-poor label set
+    gt1 = seen["tv"].clone()
+    gt1[(gt1 > 5) & (gt1 != 255)] = 0
+    ld1 = head.loss_voxel(logits.clone(), gt1.clone(), tag="c_0")
+    g["losses_r1"] = np.array([ld1[k].item() for k in names], dtype=np.float64)
+    g["class_weights"] = head.class_weights.numpy().astype(np.float64)
+    return g
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = refshim.load_reference()
+    gl = golden_losses(ns)
+    path = os.path.join(OUT, "reference_losses.npz")
+    np.savez_compressed(path, **gl)
+    print("losses ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
     for name in ("c1", "c1k1"):
         g = golden_for(name, ns)
         path = os.path.join(OUT, "reference_%s.npz" % name)

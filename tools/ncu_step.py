@@ -19,7 +19,7 @@ model = coocc_b200.HotPath(coocc_b200.model_cfg(C, K), C).to(dev).train()
 inp = S.make_inputs(a.workload)
 d = {k: v.to(dev) for k, v in inp.items()}
 X, Y, Z = cfg["grid"]
-occ = torch.randint(0, 17, (1, X, Y, Z), device=dev)
+occ = S.make_gt_occ(cfg["grid"], 2, 0).to(dev)
 
 
 def step():
