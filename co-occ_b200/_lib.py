@@ -79,6 +79,7 @@ _SIGS = {
     "coocc_occ_loss_workspace": (c_ll, [c_int, c_int]),
     "coocc_occ_loss_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "coocc_occ_loss_bwd": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "coocc_eval_confusion": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -921,3 +921,33 @@ class _OccLossFn(torch.autograd.Function):
 
 def occ_voxel_losses(logits2d, labels, class_w=None, ignore=255, empty_idx=0):
     return _OccLossFn.apply(logits2d, labels, class_w, ignore, empty_idx)
+
+
+# ----------------------------------------------------------------------------------------
+# Test-time metric (COOCC_Ray.evaluation_semantic, coocc_ray.py:659-684)
+# ----------------------------------------------------------------------------------------
+def eval_confusion(logits2d, dims, gt, visible_mask=None, empty_idx=0, ignore=255):
+    """logits [V,C] fp32 rows of the [1,C,X,Y,Z] prediction, gt [1,GX,GY,GZ] integer labels ->
+    (hist_ssc [C,C], hist_ssc_visible [C,C] or None, hist_sc [2,2]) int64 on the device: trilinear
+    up-sampling to the label grid, argmax and fast_hist in one kernel."""
+    L = _lib.lib()
+    _require_cuda(logits2d, gt)
+    x = _as_rows(logits2d.float() if logits2d.dtype != torch.float32 else logits2d)
+    V, C = x.shape
+    X, Y, Z = dims
+    assert gt.dim() == 4 and gt.shape[0] == 1
+    if gt.dtype not in (torch.uint8, torch.int32, torch.int64):
+        gt = gt.long()
+    g = gt.contiguous()
+    GX, GY, GZ = g.shape[1:]
+    vis = None
+    if visible_mask is not None:
+        vis = (visible_mask[0] != 0).to(torch.uint8).contiguous()
+        assert tuple(vis.shape) == (GX, GY, GZ)
+    h_ssc = torch.empty(C, C, device=x.device, dtype=torch.int64)
+    h_vis = torch.empty(C, C, device=x.device, dtype=torch.int64) if vis is not None else None
+    h_sc = torch.empty(2, 2, device=x.device, dtype=torch.int64)
+    _lib.check(L.coocc_eval_confusion(_p(x), x.stride(0), X, Y, Z, C, _p(g), g.element_size(), GX, GY, GZ, _p(vis),
+                                      int(empty_idx), int(ignore), _p(h_ssc), _p(h_vis), _p(h_sc), _stream()),
+               "eval_confusion")
+    return h_ssc, h_vis, h_sc

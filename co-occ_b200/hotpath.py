@@ -68,3 +68,31 @@ class HotPath(nn.Module):
             _, _, rl = render_fn(voxel_feats, geom, self.sigma_head, self.rgb_head, gt_depth, gt_img)
             losses.update(rl)
         return losses, occ, voxel_feats
+
+    # ------------------------------------------------------------------------------------
+    def evaluation_semantic(self, pred, gt, eval_type, visible_mask=None):
+        """COOCC_Ray.evaluation_semantic (coocc_ray.py:659-684): confusion matrices of the up-sampled
+        argmax prediction against gt_occ; returns numpy arrays like the reference's fast_hist."""
+        from . import functional as CF
+        x2d, dims = CF.to_cl2d(pred)
+        empty = self.pts_bbox_head.empty_idx
+        h_ssc, h_vis, h_sc = CF.eval_confusion(x2d, dims, gt, visible_mask if eval_type == 'SSC' else None, empty, 255)
+        if eval_type == 'SC':
+            return h_sc.cpu().numpy(), None
+        if eval_type == 'SSC':
+            return h_ssc.cpu().numpy(), (h_vis.cpu().numpy() if h_vis is not None else None)
+        raise ValueError(eval_type)
+
+    @torch.no_grad()
+    def simple_test(self, img_voxel_feats, pts_voxel_feats, gt_occ=None, visible_mask=None):
+        """The hot-path slice of COOCC_Ray.simple_test (coocc_ray.py:520-575): fuser -> encoder -> neck ->
+        head (eval-mode BatchNorm) and the SC / SSC confusion matrices of the coarse prediction."""
+        voxel_feats = self.occ_fuser(img_voxel_feats, pts_voxel_feats)
+        semantic_voxel = self.semantic_neck(self.semantic_encoder(voxel_feats))
+        output = self.pts_bbox_head(voxel_feats=semantic_voxel)
+        pred_c = output['output_voxels'][0]
+        out = {'pred_c': pred_c, 'pred_f': None, 'output_voxels': pred_c, 'target_voxels': gt_occ}
+        if gt_occ is not None:
+            out['SC_metric'], _ = self.evaluation_semantic(pred_c, gt_occ, 'SC', visible_mask)
+            out['SSC_metric'], out['SSC_occ_metric'] = self.evaluation_semantic(pred_c, gt_occ, 'SSC', visible_mask)
+        return out

@@ -183,6 +183,21 @@ int coocc_occ_loss_bwd(const float* logits, long long ld, const int* labels, int
                        long long ldd, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Test-time metric (csrc/eval_hist.cu) -- SURVEY §8f rank 4.
+ * Replaces COOCC_Ray.evaluation_semantic + fast_hist, P/coocc/detectors/coocc_ray.py:659-684, 726-730:
+ * trilinear up-sampling (align_corners=False) of the logits [X*Y*Z][ld] to the label grid GX x GY x GZ,
+ * argmax, and the confusion matrices hist[label][prediction] over the voxels whose label != ignore:
+ *   hist_ssc          long long[C*C]  ('SSC', max_label = C)
+ *   hist_ssc_visible  long long[C*C]  same, restricted to visible[g] != 0 (NULL when visible is NULL)
+ *   hist_sc           long long[4]    ('SC': empty vs. non-empty on both sides)
+ * gt: labels of gt_bytes = 1, 4 or 8 bytes.  The three outputs are zeroed by the call.
+ * ------------------------------------------------------------------------------------------ */
+int coocc_eval_confusion(const float* logits, long long ld, int X, int Y, int Z, int C, const void* gt,
+                         int gt_bytes, int GX, int GY, int GZ, const unsigned char* visible, int empty_idx,
+                         int ignore, long long* hist_ssc, long long* hist_ssc_visible, long long* hist_sc,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * BatchNorm3d (training mode) + ReLU + residual, and x2 zero insertion (csrc/elementwise.cu).
  * Replaces torch.nn.BatchNorm3d / SyncBatchNorm + nn.ReLU (+ `out += residual`) at
  * P/coocc/fuser/bifuser_n.py:25-29, P/coocc/backbones/resnet3d.py:46-62, P/coocc/necks/fpn3d.py:48-67,

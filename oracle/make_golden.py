@@ -174,8 +174,30 @@ def golden_losses(ns):
     return g
 
 
+def golden_eval():
+    """Reference evaluation_semantic / fast_hist (coocc_ray.py:659-684, 726-730) on seeded logits of the c1
+    grid against labels at twice the resolution, with and without a visibility mask."""
+    grid = S.CONFIGS["c1"]["grid"]
+    gen = torch.Generator().manual_seed(77)
+    pred = torch.randn(1, 17, *grid, generator=gen) * 2.0
+    pred[:, 0] += 1.0
+    gt = S.make_gt_occ(grid, 2, seed=1)
+    vis = (torch.rand(gt.shape, generator=gen) < 0.6).to(torch.uint8)
+    g = {}
+    g["sc"], _ = refshim.reference_evaluation_semantic(pred, gt, "SC")
+    g["ssc"], g["ssc_vis"] = refshim.reference_evaluation_semantic(pred, gt, "SSC", vis)
+    # labels at the prediction's own resolution (identity up-sampling)
+    gt1 = gt[:, ::2, ::2, ::2].contiguous()
+    g["ssc_r1"], _ = refshim.reference_evaluation_semantic(pred, gt1, "SSC")
+    return {k: np.asarray(v, dtype=np.int64) for k, v in g.items()}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    ge = golden_eval()
+    path = os.path.join(OUT, "reference_eval.npz")
+    np.savez_compressed(path, **ge)
+    print("eval ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
     ns = refshim.load_reference()
     gl = golden_losses(ns)
     path = os.path.join(OUT, "reference_losses.npz")

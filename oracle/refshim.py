@@ -250,3 +250,33 @@ def reference_render_block(voxel_feats, gemo, sigma_head, rgb_head, gt_depth, gt
                                          rgb_head=rgb_head))
     exec(_render_code, ns)
     return ns["rgbs"], ns["depths"], ns["losses"]
+
+
+_EVAL_LINES = (659, 684)      # `def evaluation_semantic(self, pred, gt, eval_type, visible_mask=None):` ... `return hist, hist_occ`
+_HIST_LINES = (726, 730)      # `def fast_hist(pred, label, max_label=18):`
+_eval_ns = None
+
+
+def reference_evaluation_semantic(pred, gt, eval_type, visible_mask=None, empty_idx=0):
+    """Runs COOCC_Ray.evaluation_semantic and fast_hist (coocc_ray.py:659-684, 726-730) as they are: the
+    two functions' own lines are read from the reference tree, dedented and exec'd (the detector file
+    cannot be imported whole).  `np.int` (removed in numpy 2, used at :664) is supplied as `int`."""
+    global _eval_ns
+    import copy
+    import textwrap
+    import numpy
+    import torch.nn.functional as F
+    if _eval_ns is None:
+        with open(_RENDER_FILE) as f:
+            lines = f.readlines()
+        src = textwrap.dedent("".join(lines[_EVAL_LINES[0] - 1:_EVAL_LINES[1]])) + "\n" + \
+            textwrap.dedent("".join(lines[_HIST_LINES[0] - 1:_HIST_LINES[1]]))
+        assert src.lstrip().startswith("def evaluation_semantic(self, pred, gt, eval_type"), "reference layout changed"
+
+        class _NP:
+            def __getattr__(self, k):
+                return int if k == "int" else getattr(numpy, k)
+
+        _eval_ns = dict(torch=torch, F=F, np=_NP(), copy=copy)
+        exec(compile(src, _RENDER_FILE, "exec"), _eval_ns)
+    return _eval_ns["evaluation_semantic"](types.SimpleNamespace(empty_idx=empty_idx), pred, gt, eval_type, visible_mask)
