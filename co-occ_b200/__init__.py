@@ -14,3 +14,4 @@ from .functional import get_precision, set_precision  # noqa: F401
 from .modules import BiFuser_N, CustomResNet3D, FPN3D, MLP, OccHead, render_fn  # noqa: F401
 from .hotpath import HotPath, model_cfg  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
+from . import lss  # noqa: F401

@@ -80,6 +80,11 @@ _SIGS = {
     "coocc_occ_loss_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "coocc_occ_loss_bwd": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "coocc_eval_confusion": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "coocc_lss_geometry": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "coocc_lss_workspace": (c_ll, [c_ll, c_ll]),
+    "coocc_lss_sort": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "coocc_lss_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_lss_pool_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
 }
 
 

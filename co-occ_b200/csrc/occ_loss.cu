@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "../../include/coocc_b200.h"
+#include "radix_sort.cuh"
 
 namespace coocc {
 
@@ -65,7 +66,7 @@ static size_t ws_layout(char* base, int V, int C, OccWs* w) {
   uint32_t* kB = reinterpret_cast<uint32_t*>(take((size_t)C * V * 4));
   uint32_t* vA = reinterpret_cast<uint32_t*>(take((size_t)C * V * 4));
   uint32_t* vB = reinterpret_cast<uint32_t*>(take((size_t)C * V * 4));
-  int* counters = reinterpret_cast<int*>(take((size_t)C * kBins * nchunks * 4));
+  int* counters = reinterpret_cast<int*>(take(radix_counters_bytes(V, C)));
   int* lcnt = reinterpret_cast<int*>(take((size_t)C * nchunks * 4));
   if (w) *w = OccWs{acc, coef, G, kA, kB, vA, vB, counters, lcnt, nchunks};
   return off;
@@ -232,14 +233,28 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) radix_hist_kernel(const u
   }
 }
 
-// exclusive scan of counters[c] in (digit, chunk) order; thread d owns digit d (a column of the
-// chunk-major [chunk][digit] matrix, so every step is one coalesced 4 KB row across the block)
-__global__ void __launch_bounds__(kBins) radix_scan_kernel(int* __restrict__ counters, int nchunks) {
-  __shared__ int wsum[kBins / 32];
-  int* col = counters + (size_t)blockIdx.x * nchunks * kBins + threadIdx.x;
+// Exclusive scan of counters[seg] in (digit, chunk) order, chunk-major [chunk][digit] storage so that every
+// step is one coalesced 4 KB row.  The chunk range is cut into kScanSlices slices handled by different
+// blocks: (1) per-slice digit totals, (2) one block per segment turns them into slice bases, (3) every slice
+// writes its exclusive prefixes.
+constexpr int kScanSlices = 32;
+
+__global__ void __launch_bounds__(kBins) radix_scan1_kernel(const int* __restrict__ counters, int nchunks,
+                                                            int* __restrict__ slice_tot) {
+  const int seg = blockIdx.y, s = blockIdx.x, d = threadIdx.x;
+  const int per = (nchunks + kScanSlices - 1) / kScanSlices;
+  const int beg = s * per, end = min(nchunks, beg + per);
+  const int* col = counters + (size_t)seg * nchunks * kBins + d;
   int tot = 0;
-  for (int i = 0; i < nchunks; ++i) tot += col[(size_t)i * kBins];
-  // block exclusive scan of tot
+  for (int i = beg; i < end; ++i) tot += col[(size_t)i * kBins];
+  slice_tot[((size_t)seg * kScanSlices + s) * kBins + d] = tot;
+}
+
+__global__ void __launch_bounds__(kBins) radix_scan2_kernel(int* __restrict__ slice_tot) {
+  __shared__ int wsum[kBins / 32];
+  int* st = slice_tot + (size_t)blockIdx.x * kScanSlices * kBins + threadIdx.x;
+  int tot = 0;
+  for (int s = 0; s < kScanSlices; ++s) tot += st[(size_t)s * kBins];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = tot;
 #pragma unroll
@@ -260,7 +275,21 @@ __global__ void __launch_bounds__(kBins) radix_scan_kernel(int* __restrict__ cou
   }
   __syncthreads();
   int base = incl - tot + (warp > 0 ? wsum[warp - 1] : 0);
-  for (int i = 0; i < nchunks; ++i) {
+  for (int s = 0; s < kScanSlices; ++s) {
+    const int t = st[(size_t)s * kBins];
+    st[(size_t)s * kBins] = base;
+    base += t;
+  }
+}
+
+__global__ void __launch_bounds__(kBins) radix_scan3_kernel(int* __restrict__ counters, int nchunks,
+                                                            const int* __restrict__ slice_tot) {
+  const int seg = blockIdx.y, s = blockIdx.x, d = threadIdx.x;
+  const int per = (nchunks + kScanSlices - 1) / kScanSlices;
+  const int beg = s * per, end = min(nchunks, beg + per);
+  int* col = counters + (size_t)seg * nchunks * kBins + d;
+  int base = slice_tot[((size_t)seg * kScanSlices + s) * kBins + d];
+  for (int i = beg; i < end; ++i) {
     const int t = col[(size_t)i * kBins];
     col[(size_t)i * kBins] = base;
     base += t;
@@ -301,6 +330,33 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) radix_scatter_kernel(cons
     __syncwarp();
     if (act) { ko[base + rank] = key; vo[base + rank] = val; }
   }
+}
+
+// Sorts `nseg` independent segments of n (key, value) pairs (segment s at offset s*n) ascending by the
+// low `bits` key bits (rounded up to a multiple of 10), stable.  Ping-pongs between (kA, vA) and (kB, vB);
+// *k_out / *v_out receive the buffers that hold the result.  counters: radix_counters_bytes(n, nseg).
+size_t radix_counters_bytes(int n, int nseg) {
+  const int nchunks = (n + kChunk - 1) / kChunk;
+  return ((size_t)nseg * nchunks * kBins + (size_t)nseg * kScanSlices * kBins) * sizeof(int);
+}
+int radix_sort_pairs(uint32_t* kA, uint32_t* vA, uint32_t* kB, uint32_t* vB, int n, int nseg, int bits, int* counters,
+                     cudaStream_t st, uint32_t** k_out, uint32_t** v_out) {
+  const int nchunks = (n + kChunk - 1) / kChunk;
+  const dim3 grid((nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock, nseg);
+  uint32_t *kin = kA, *vin = vA, *kout = kB, *vout = vB;
+  int* slice_tot = counters + (size_t)nseg * nchunks * kBins;
+  for (int shift = 0; shift < bits; shift += kRadixBits) {
+    radix_hist_kernel<<<grid, 32 * kWarpsPerBlock, 0, st>>>(kin, n, nchunks, shift, counters);
+    radix_scan1_kernel<<<dim3(kScanSlices, nseg), kBins, 0, st>>>(counters, nchunks, slice_tot);
+    radix_scan2_kernel<<<nseg, kBins, 0, st>>>(slice_tot);
+    radix_scan3_kernel<<<dim3(kScanSlices, nseg), kBins, 0, st>>>(counters, nchunks, slice_tot);
+    radix_scatter_kernel<<<grid, 32 * kWarpsPerBlock, 0, st>>>(kin, vin, n, nchunks, shift, counters, kout, vout);
+    uint32_t* t = kin; kin = kout; kout = t;
+    t = vin; vin = vout; vout = t;
+  }
+  *k_out = kin;
+  *v_out = vin;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -557,18 +613,10 @@ extern "C" int coocc_occ_loss_fwd(const float* logits, long long ld, const int* 
   int blocks = (V + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   occ_stats_kernel<<<blocks, 256, 0, st>>>(logits, ld, labels, V, C, class_w, ignore, w.acc, w.keyA, w.valA);
-  // 3 x 10-bit LSD passes: A -> B -> A -> B
+  // 3 x 10-bit LSD passes over the 30 significant key bits
   const dim3 grid((w.nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock, C);
-  uint32_t *kin = w.keyA, *vin = w.valA, *kout = w.keyB, *vout = w.valB;
-  for (int pass = 0; pass < 3; ++pass) {
-    const int shift = pass * kRadixBits;
-    radix_hist_kernel<<<grid, 32 * kWarpsPerBlock, 0, st>>>(kin, V, w.nchunks, shift, w.counters);
-    radix_scan_kernel<<<C, kBins, 0, st>>>(w.counters, w.nchunks);
-    radix_scatter_kernel<<<grid, 32 * kWarpsPerBlock, 0, st>>>(kin, vin, V, w.nchunks, shift, w.counters, kout, vout);
-    uint32_t* t = kin; kin = kout; kout = t;
-    t = vin; vin = vout; vout = t;
-  }
-  // sorted data is in (kin, vin) == (keyB, valB)
+  uint32_t *kin = nullptr, *vin = nullptr;
+  if (radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, V, C, 30, w.counters, st, &kin, &vin) != 0) return COOCC_ERR_CUDA;
   lovasz_count_kernel<<<grid, 32 * kWarpsPerBlock, 0, st>>>(vin, labels, V, w.nchunks, w.lcnt);
   lovasz_scan_kernel<<<C, 32, 0, st>>>(w.lcnt, w.nchunks);
   lovasz_apply_kernel<<<grid, 32 * kWarpsPerBlock, 0, st>>>(kin, vin, labels, V, w.nchunks, w.lcnt, w.acc, w.G);

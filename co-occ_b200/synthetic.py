@@ -121,6 +121,33 @@ def make_gt_occ(grid, ratio=2, seed=0, num_cls=17):
     return fine[None].contiguous()
 
 
+def make_camera_rig(cams=6, seed=0, in_h=256, in_w=704):
+    """Plausible nuScenes-like calibration for N cameras (img_inputs[1:7] of P/datasets/pipelines/loading.py:129):
+    rots [1,N,3,3] camera->ego, trans [1,N,3], intrins [1,N,3,3], post_rots / post_trans (image augmentation:
+    resize + crop), bda [1,3,3] (BEV augmentation: small rotation, scale, flip)."""
+    g = _gen(seed + 211)
+    rots, trans, intr, prot, ptr = [], [], [], [], []
+    for c in range(cams):
+        yaw = math.radians(360.0 * c / cams + 5.0 * float(torch.rand(1, generator=g)))
+        cy, sy = math.cos(yaw), math.sin(yaw)
+        # camera axes (x right, y down, z forward) in the ego frame (x forward, y left, z up)
+        fwd = torch.tensor([cy, sy, 0.0])
+        right = torch.tensor([sy, -cy, 0.0])
+        down = torch.tensor([0.0, 0.0, -1.0])
+        rots.append(torch.stack([right, down, fwd], 1))
+        trans.append(torch.tensor([1.5 * cy, 1.5 * sy, 1.6]) + 0.1 * torch.randn(3, generator=g))
+        f = 1260.0 + 20.0 * float(torch.randn(1, generator=g))
+        intr.append(torch.tensor([[f, 0.0, 800.0], [0.0, f, 450.0], [0.0, 0.0, 1.0]]))
+        sc = in_w / 1600.0 * (1.0 + 0.05 * float(torch.randn(1, generator=g)))
+        prot.append(torch.tensor([[sc, 0.0, 0.0], [0.0, sc, 0.0], [0.0, 0.0, 1.0]]))
+        ptr.append(torch.tensor([-3.0 * float(torch.rand(1, generator=g)), -(900 * sc - in_h) * 0.9, 0.0]))
+    a = math.radians(4.0)
+    bda = torch.tensor([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]]) * 1.02
+    bda[1] = -bda[1]                     # flip_dy
+    st = lambda ts: torch.stack(ts)[None].float()
+    return dict(rots=st(rots), trans=st(trans), intrins=st(intr), post_rots=st(prot), post_trans=st(ptr), bda=bda[None])
+
+
 def make_inputs(name, seed=0, with_render=True):
     cfg = CONFIGS[name]
     img, pts = make_voxel_feats(cfg["grid"], cfg["C"], cfg["p_img"], cfg["p_pts"], seed,

@@ -198,6 +198,37 @@ int coocc_eval_confusion(const float* logits, long long ld, int X, int Y, int Z,
                          void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Lift-Splat voxel pooling + frustum geometry (csrc/lss_pool.cu) -- SURVEY §8f rank 2, the producer of
+ * img_voxel_feats and geom.  Replaces voxel_pooling (P/coocc/image2bev/ViewTransformerLSSVoxel.py:100-123),
+ * bev_pool (M/ops/bev_pool/bev_pool.py:80-97, src/bev_pool_cuda.cu:20-98) and get_geometry
+ * (P/coocc/image2bev/ViewTransformerLSSBEVDepth.py:117-150).  Batch 1.
+ * ------------------------------------------------------------------------------------------ */
+/* frustum [D][H][W][3]; cam_mats [ncam][24] = post_trans(3) | inverse(post_rots)(9) | rots @ inverse(intrins)(9) |
+ * trans(3), row-major; bda [9]; geom [ncam][D][H][W][3] (ego-frame metres). */
+int coocc_lss_geometry(const float* frustum, int ncam, int D, int H, int W, const float* cam_mats,
+                       const float* bda, float* geom, void* stream);
+long long coocc_lss_workspace(long long npts, long long V);
+/* geom [npts][3]; lo3 / dx3: HOST float[3] = (bx - dx/2) and dx of the voxel grid, X,Y,Z = nx.
+ * key(point) = voxel id (x*Y + y)*Z + z of trunc((geom - lo) / dx), or X*Y*Z for a dropped point.
+ * Sorts (key, point id) stably by key inside `workspace` (coocc_lss_workspace(npts, X*Y*Z) bytes); the four
+ * outputs receive device pointers into the workspace: sorted keys, sorted point ids, per-point keys and
+ * segments int[V+2] (segments[v] = first sorted position with key >= v). */
+int coocc_lss_sort(const float* geom, long long npts, const float* lo3, const float* dx3, int X, int Y, int Z,
+                   void* workspace, const unsigned int** sorted_keys, const unsigned int** sorted_vals,
+                   const unsigned int** point_keys, const int** segments, void* stream);
+/* out[v][0..C) = sum over the points of voxel v of w * feat[row]   (out: [V][ldo], fully written).
+ * depth == NULL: row = point id, w = 1 (feat = the reference's flattened volume [npts][ldf]).
+ * depth != NULL (fused lift + splat): point id = ((n*D + d)*HW + hw), row = n*HW + hw, w = depth[point id]
+ * (feat = image features as [ncam*HW][ldf], depth = depth_prob [ncam][D][HW]). */
+int coocc_lss_pool_fwd(const unsigned int* sorted_keys, const unsigned int* sorted_vals, const int* segments,
+                       long long npts, int V, int C, const float* feat, long long ldf, const float* depth, int D,
+                       int HW, float* out, long long ldo, void* stream);
+/* depth == NULL: dfeat [npts][lddf] = gout[key]; else dfeat [ncam*HW][lddf] and ddepth [npts]. */
+int coocc_lss_pool_bwd(const unsigned int* point_keys, long long npts, int V, int C, const float* gout,
+                       long long ldg, const float* feat, long long ldf, const float* depth, int ncam, int D, int HW,
+                       float* dfeat, long long lddf, float* ddepth, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * BatchNorm3d (training mode) + ReLU + residual, and x2 zero insertion (csrc/elementwise.cu).
  * Replaces torch.nn.BatchNorm3d / SyncBatchNorm + nn.ReLU (+ `out += residual`) at
  * P/coocc/fuser/bifuser_n.py:25-29, P/coocc/backbones/resnet3d.py:46-62, P/coocc/necks/fpn3d.py:48-67,

@@ -192,8 +192,56 @@ def golden_eval():
     return {k: np.asarray(v, dtype=np.int64) for k, v in g.items()}
 
 
+LSS_GRID = dict(xbound=[-25.0, 25.0, 1.0], ybound=[-25.0, 25.0, 1.0], zbound=[-5.0, 3.0, 1.0], dbound=[2.0, 34.0, 0.5])
+LSS_DATA = dict(input_size=(256, 704))
+
+
+def lss_inputs(seed=0, C=32, cams=6):
+    """Seeded inputs of the Lift-Splat golden case: a 50x50x8 grid, 6 cameras, 64 depth bins, 16x44 feature maps."""
+    from oracle import lss as OLS
+    rig = S.make_camera_rig(cams, seed)
+    gen = torch.Generator().manual_seed(seed + 31)
+    fH, fW = LSS_DATA["input_size"][0] // 16, LSS_DATA["input_size"][1] // 16
+    ds = torch.arange(*LSS_GRID["dbound"], dtype=torch.float).view(-1, 1, 1).expand(-1, fH, fW)
+    D = ds.shape[0]
+    xs = torch.linspace(0, LSS_DATA["input_size"][1] - 1, fW).view(1, 1, fW).expand(D, fH, fW)
+    ys = torch.linspace(0, LSS_DATA["input_size"][0] - 1, fH).view(1, fH, 1).expand(D, fH, fW)
+    frustum = torch.stack((xs, ys, ds), -1)
+    depth = torch.softmax(torch.randn(cams, D, fH, fW, generator=gen), 1)
+    feat = torch.randn(cams, C, fH, fW, generator=gen)
+    dx = torch.Tensor([LSS_GRID[k][2] for k in ("xbound", "ybound", "zbound")])
+    bx = torch.Tensor([LSS_GRID[k][0] + LSS_GRID[k][2] / 2.0 for k in ("xbound", "ybound", "zbound")])
+    nx = torch.Tensor([(LSS_GRID[k][1] - LSS_GRID[k][0]) / LSS_GRID[k][2] for k in ("xbound", "ybound", "zbound")])
+    return dict(rig=rig, frustum=frustum, depth=depth, feat=feat, dx=dx, bx=bx, nx=nx)
+
+
+def golden_lss():
+    from oracle import lss as OLS
+    i = lss_inputs()
+    r = i["rig"]
+    g = {}
+    geom = refshim.reference_get_geometry(i["frustum"], r["rots"], r["trans"], r["intrins"], r["post_rots"],
+                                          r["post_trans"], r["bda"])
+    g["geom_sample"], g["geom_stats"] = sample(geom), stats(geom)
+    vol = OLS.lift(i["depth"], i["feat"]).clone().requires_grad_(True)
+    out = refshim.reference_voxel_pooling(geom, vol, i["bx"], i["dx"], i["nx"])      # [1,C,Z,X,Y] permuted to [1,C,X,Y,Z]
+    g["out_shape"] = np.array(out.shape)
+    g["out_sample"], g["out_stats"] = sample(out.contiguous()), stats(out)
+    g["occupied"] = np.int64((out.abs().sum(1) != 0).sum())
+    w = torch.linspace(-1, 1, out.numel()).reshape(out.shape)
+    (out * w).sum().backward()
+    g["dvol_sample"], g["dvol_stats"] = sample(vol.grad), stats(vol.grad)
+    idx = ((geom - (i["bx"] - i["dx"] / 2.)) / i["dx"]).long().reshape(-1, 3)
+    g["idx_sample"] = idx[::101].numpy().astype(np.int32)
+    return g
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    gl2 = golden_lss()
+    path = os.path.join(OUT, "reference_lss.npz")
+    np.savez_compressed(path, **gl2)
+    print("lss ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
     ge = golden_eval()
     path = os.path.join(OUT, "reference_eval.npz")
     np.savez_compressed(path, **ge)

@@ -280,3 +280,49 @@ def reference_evaluation_semantic(pred, gt, eval_type, visible_mask=None, empty_
         _eval_ns = dict(torch=torch, F=F, np=_NP(), copy=copy)
         exec(compile(src, _RENDER_FILE, "exec"), _eval_ns)
     return _eval_ns["evaluation_semantic"](types.SimpleNamespace(empty_idx=empty_idx), pred, gt, eval_type, visible_mask)
+
+
+_LSSV_FILE = os.path.join(_PLUGIN, "coocc", "image2bev", "ViewTransformerLSSVoxel.py")
+_LSSB_FILE = os.path.join(_PLUGIN, "coocc", "image2bev", "ViewTransformerLSSBEVDepth.py")
+_VP_LINES = (100, 123)        # `def voxel_pooling(self, geom_feats, x):` ... `return final`
+_GG_LINES = (117, 150)        # `def get_geometry(self, rots, ...):` ... `return points`
+_lss_ns = None
+
+
+def _cpu_bev_pool(feats, coords, B, D, H, W):
+    """The CUDA-only op `bev_pool` (M/ops/bev_pool/bev_pool.py:80-97, src/bev_pool_cuda.cu:20-46) restated for
+    the CPU: sort by voxel rank, sum every run, scatter to out[b][z][x][y][:], return [B,C,D,H,W]."""
+    B, D, H, W = int(B), int(D), int(H), int(W)
+    ranks = coords[:, 0] * (W * D * B) + coords[:, 1] * (D * B) + coords[:, 2] * B + coords[:, 3]
+    idx = ranks.argsort()
+    feats, coords = feats[idx], coords[idx]
+    out = torch.zeros(B, D, H, W, feats.shape[1], dtype=feats.dtype)
+    out.index_put_((coords[:, 3], coords[:, 2], coords[:, 0], coords[:, 1]), feats, accumulate=True)
+    return out.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def _lss_namespace():
+    global _lss_ns
+    import textwrap
+    if _lss_ns is None:
+        ns = dict(torch=torch, bev_pool=_cpu_bev_pool)
+        for path, (a, b), name in ((_LSSV_FILE, _VP_LINES, "voxel_pooling"), (_LSSB_FILE, _GG_LINES, "get_geometry")):
+            with open(path) as f:
+                lines = f.readlines()
+            src = textwrap.dedent("".join(lines[a - 1:b]))
+            assert src.lstrip().startswith("def %s(self" % name), "reference layout changed (%s)" % name
+            exec(compile(src, path, "exec"), ns)
+        _lss_ns = ns
+    return _lss_ns
+
+
+def reference_voxel_pooling(geom_feats, x, bx, dx, nx):
+    """ViewTransformerLiftSplatShootVoxel.voxel_pooling (ViewTransformerLSSVoxel.py:100-123) run as it is, with
+    `self` = (bx, dx, nx) and the CUDA op bev_pool replaced by its CPU restatement."""
+    return _lss_namespace()["voxel_pooling"](types.SimpleNamespace(bx=bx, dx=dx, nx=nx), geom_feats, x)
+
+
+def reference_get_geometry(frustum, rots, trans, intrins, post_rots, post_trans, bda):
+    """ViewTransformerLiftSplatShoot.get_geometry (ViewTransformerLSSBEVDepth.py:117-150) run as it is."""
+    return _lss_namespace()["get_geometry"](types.SimpleNamespace(frustum=frustum), rots, trans, intrins, post_rots,
+                                            post_trans, bda)
