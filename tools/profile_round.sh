@@ -9,13 +9,13 @@ tag=${1:-prof}
 out=gpurun_out
 mkdir -p $out
 SECT="--section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy"
-NONCONV='fps_kernel|modulate|pack_kernel|composite|rep_topk|gather_rows|ball_assign|box_gather|box_scatter|upsample_loss|scatter_rows|trilinear_mix|trilinear_bwd_axis|dilate2|sgemm_kernel'
+NONCONV='fps_kernel|modulate|pack_kernel|composite|rep_topk|gather_rows|ball_assign|box_gather|box_scatter|upsample_loss|scatter_rows|trilinear_mix|dilate2|sgemm_kernel|occ_stats|occ_bwd|radix_|lovasz_|label_mode'
 
-timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -s 1750 -c 900 --csv \
+timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -s 1800 -c 950 --csv \
     --log-file $out/${tag}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
 python tools/launch_summary.py $out/${tag}_launches.csv 60 > $out/${tag}_launches.summary.txt 2>&1
 
-timeout 300 ncu $SECT --clock-control none --profile-from-start off -k regex:"$NONCONV" -c 45 \
+timeout 300 ncu $SECT --clock-control none --profile-from-start off -k regex:"$NONCONV" -c 60 \
     -o $out/${tag}_step python tools/ncu_step.py > $out/${tag}_ncu_step.log 2>&1
 python tools/ncu_summary.py $out/${tag}_step.ncu-rep > $out/${tag}_step_kernels.summary.txt 2>&1
 rm -f $out/${tag}_step.ncu-rep
