@@ -59,8 +59,8 @@ _SIGS = {
     "coocc_gsf_scatter_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_bn_finalize": (c_int, [c_void_p, c_int, c_ll, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "coocc_bn_act_fwd": (c_int, [c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p]),
-    "coocc_bn_act_bwd_reduce": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
-    "coocc_bn_act_bwd_apply": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_bn_act_bwd_reduce": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "coocc_bn_act_bwd_apply": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_dilate2": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "coocc_trilinear_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),
     "coocc_trilinear_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p]),

@@ -37,6 +37,26 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, doubl
   }
 }
 
+// the BatchNorm affine map, one expression shared by forward and backward so that the backward can
+// recompute the ReLU mask (y > 0) from x bit-for-bit instead of re-reading the stored output
+__device__ __forceinline__ float bn_affine(float x, float m, float is, float g, float b) {
+  return (x - m) * is * g + b;
+}
+// dz = dout * [y > 0]: mask from the stored output `o` (use_out) or recomputed from x
+__device__ __forceinline__ float4 bn_mask(float4 d, bool use_out, float4 o, float4 xv, float4 m, float4 is, float4 g,
+                                          float4 b) {
+  if (use_out) {
+    d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
+    d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
+  } else {
+    d.x = bn_affine(xv.x, m.x, is.x, g.x, b.x) > 0.f ? d.x : 0.f;
+    d.y = bn_affine(xv.y, m.y, is.y, g.y, b.y) > 0.f ? d.y : 0.f;
+    d.z = bn_affine(xv.z, m.z, is.z, g.z, b.z) > 0.f ? d.z : 0.f;
+    d.w = bn_affine(xv.w, m.w, is.w, g.w, b.w) > 0.f ? d.w : 0.f;
+  }
+  return d;
+}
+
 // out = relu?( (x - mean) * invstd * gamma + beta (+ residual) )
 template <typename T>
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x, long long ldx,
@@ -57,10 +77,10 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x
     const float4 g = *reinterpret_cast<const float4*>(gamma + c);
     const float4 b = *reinterpret_cast<const float4*>(beta + c);
     float4 y;
-    y.x = (xv.x - m.x) * is.x * g.x + b.x;
-    y.y = (xv.y - m.y) * is.y * g.y + b.y;
-    y.z = (xv.z - m.z) * is.z * g.z + b.z;
-    y.w = (xv.w - m.w) * is.w * g.w + b.w;
+    y.x = bn_affine(xv.x, m.x, is.x, g.x, b.x);
+    y.y = bn_affine(xv.y, m.y, is.y, g.y, b.y);
+    y.z = bn_affine(xv.z, m.z, is.z, g.z, b.z);
+    y.w = bn_affine(xv.w, m.w, is.w, g.w, b.w);
     if (residual != nullptr) {
       const float4 rv = load4(residual + r * ldr + c);
       y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w;
@@ -72,28 +92,33 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x
   }
 }
 
-// sums[c] = sum_r dz, sums[C + c] = sum_r dz * xhat, dz = dout * [out > 0] (relu) or dout
+// sums[c] = sum_r dz, sums[C + c] = sum_r dz * xhat, dz = dout * [y > 0] (relu) or dout.  The mask is read
+// from the stored output when `out` is given (needed when a residual was added before the ReLU) and recomputed
+// from x otherwise -- one tensor less to read.
 // block = 32 x 8: threadIdx.x -> channel group (4 channels), threadIdx.y -> row lane.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
     const T* __restrict__ dout, long long ldd, const T* __restrict__ out, long long ldo,
     const T* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
-    int relu, int rows_per_block, float* __restrict__ sums) {
+    const float* __restrict__ gamma, const float* __restrict__ beta, int relu, int rows_per_block,
+    float* __restrict__ sums) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
   if (c < C) {
     const float4 m = *reinterpret_cast<const float4*>(mean_invstd + c);
     const float4 is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
+    const bool use_out = out != nullptr;
+    float4 g = m, b = m;
+    if (relu && !use_out) {
+      g = *reinterpret_cast<const float4*>(gamma + c);
+      b = *reinterpret_cast<const float4*>(beta + c);
+    }
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     const long long r1 = min(V, r0 + rows_per_block);
     for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
       float4 d = load4(dout + r * ldd + c);
-      if (relu) {
-        const float4 o = load4(out + r * ldo + c);
-        d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
-        d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
-      }
       const float4 xv = load4(x + r * ldx + c);
+      if (relu) d = bn_mask(d, use_out, use_out ? load4(out + r * ldo + c) : xv, xv, m, is, g, b);
       s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
       s2.x += d.x * (xv.x - m.x) * is.x; s2.y += d.y * (xv.y - m.y) * is.y;
       s2.z += d.z * (xv.z - m.z) * is.z; s2.w += d.w * (xv.w - m.w) * is.w;
@@ -121,24 +146,24 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const T* __restrict__ dout, long long ldd, const T* __restrict__ out, long long ldo,
     const T* __restrict__ x, long long ldx, long long V, int C, const float* __restrict__ mean_invstd,
-    const float* __restrict__ gamma, const float* __restrict__ sums, int relu, T* __restrict__ dx,
-    long long lddx, T* __restrict__ dres, long long lddr, float inv_n) {
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums, int relu,
+    T* __restrict__ dx, long long lddx, T* __restrict__ dres, long long lddr, float inv_n) {
   const int c4 = C >> 2;
   const long long total = V * c4;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const long long r = i / c4;
     const int c = (int)(i % c4) * 4;
     float4 d = load4(dout + r * ldd + c);
-    if (relu) {
-      const float4 o = load4(out + r * ldo + c);
-      d.x = o.x > 0.f ? d.x : 0.f; d.y = o.y > 0.f ? d.y : 0.f;
-      d.z = o.z > 0.f ? d.z : 0.f; d.w = o.w > 0.f ? d.w : 0.f;
-    }
-    if (dres != nullptr) store4(dres + r * lddr + c, d);
     const float4 xv = load4(x + r * ldx + c);
     const float4 m = *reinterpret_cast<const float4*>(mean_invstd + c);
     const float4 is = *reinterpret_cast<const float4*>(mean_invstd + C + c);
     const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    if (relu) {
+      const bool use_out = out != nullptr;
+      const float4 bt = use_out ? m : *reinterpret_cast<const float4*>(beta + c);
+      d = bn_mask(d, use_out, use_out ? load4(out + r * ldo + c) : xv, xv, m, is, g, bt);
+    }
+    if (dres != nullptr) store4(dres + r * lddr + c, d);
     const float4 a = *reinterpret_cast<const float4*>(sums + c);
     const float4 b = *reinterpret_cast<const float4*>(sums + C + c);
     float4 y;
@@ -209,6 +234,8 @@ extern "C" int coocc_bn_act_fwd(const void* x, long long ldx, long long V, int C
   return CK_LAUNCH();
 }
 
+// relu != 0: dz = dout * [y > 0]; the mask is read from `out` when it is given (required if a residual was added
+// before the ReLU) and recomputed from x, gamma, beta when out == NULL.
 // Backward in two stream-ordered halves so that SyncBatchNorm can all-reduce `sums` in between:
 //   reduce: sums (float[2*C], zeroed by the caller) += (sum dz, sum dz*xhat) over this rank's rows
 //   apply : dx = gamma*invstd*(dz - sums[0:C]/count - xhat*sums[C:2C]/count); dres = dz (optional)
@@ -216,9 +243,11 @@ extern "C" int coocc_bn_act_fwd(const void* x, long long ldx, long long V, int C
 // After the reduce, sums[0:C] = dbeta and sums[C:2C] = dgamma (of this rank / of all ranks).
 extern "C" int coocc_bn_act_bwd_reduce(const void* dout, long long ldd, const void* out, long long ldo,
                                        const void* x, long long ldx, long long V, int C, const float* mean_invstd,
-                                       int relu, float* sums, int act_bf16, void* stream) {
+                                       const float* gamma, const float* beta, int relu, float* sums, int act_bf16,
+                                       void* stream) {
   if (!dout || !x || !mean_invstd || !sums || (C & 3) || (ldd & 3) || (ldx & 3)) return COOCC_ERR_ARG;
-  if (relu && (!out || (ldo & 3))) return COOCC_ERR_ARG;
+  if (relu && out && (ldo & 3)) return COOCC_ERR_ARG;
+  if (relu && !out && (!gamma || !beta)) return COOCC_ERR_ARG;
   const int cgroups = (C / 4 + 31) / 32;
   int rows_per_block = 256;
   long long nby = (V + rows_per_block - 1) / rows_per_block;
@@ -230,32 +259,34 @@ extern "C" int coocc_bn_act_bwd_reduce(const void* dout, long long ldd, const vo
   if (act_bf16)
     bn_act_bwd_reduce_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)x, ldx, V, C,
-        mean_invstd, relu, rows_per_block, sums);
+        mean_invstd, gamma, beta, relu, rows_per_block, sums);
   else
     bn_act_bwd_reduce_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(
-        (const float*)dout, ldd, (const float*)out, ldo, (const float*)x, ldx, V, C, mean_invstd, relu,
+        (const float*)dout, ldd, (const float*)out, ldo, (const float*)x, ldx, V, C, mean_invstd, gamma, beta, relu,
         rows_per_block, sums);
   return CK_LAUNCH();
 }
 
 extern "C" int coocc_bn_act_bwd_apply(const void* dout, long long ldd, const void* out, long long ldo,
                                       const void* x, long long ldx, long long V, int C, const float* mean_invstd,
-                                      const float* gamma, int relu, const float* sums, long long count, void* dx,
-                                      long long lddx, int act_bf16, void* dres, long long lddr, void* stream) {
+                                      const float* gamma, const float* beta, int relu, const float* sums,
+                                      long long count, void* dx, long long lddx, int act_bf16, void* dres,
+                                      long long lddr, void* stream) {
   if (!dout || !x || !mean_invstd || !gamma || !sums || !dx || (C & 3) || (ldd & 3) || (ldx & 3) || (lddx & 3) ||
       count < 1)
     return COOCC_ERR_ARG;
-  if (relu && (!out || (ldo & 3))) return COOCC_ERR_ARG;
+  if (relu && out && (ldo & 3)) return COOCC_ERR_ARG;
+  if (relu && !out && !beta) return COOCC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int g = grid_for(V * (C >> 2));
   const float inv_n = (float)(1.0 / (double)count);
   if (act_bf16)
     bn_act_bwd_apply_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(
         (const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)x, ldx, V, C,
-        mean_invstd, gamma, sums, relu, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddr, inv_n);
+        mean_invstd, gamma, beta, sums, relu, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddr, inv_n);
   else
     bn_act_bwd_apply_kernel<float><<<g, 256, 0, st>>>((const float*)dout, ldd, (const float*)out, ldo, (const float*)x,
-                                                     ldx, V, C, mean_invstd, gamma, sums, relu, (float*)dx, lddx,
+                                                     ldx, V, C, mean_invstd, gamma, beta, sums, relu, (float*)dx, lddx,
                                                      (float*)dres, lddr, inv_n);
   return CK_LAUNCH();
 }

@@ -314,14 +314,16 @@ class _BNActFn(torch.autograd.Function):
         _lib.check(L.coocc_bn_act_fwd(_p(x), x.stride(0), V, C, _p(mi), _p(gamma), _p(beta), _p(residual),
                                       residual.stride(0) if residual is not None else 0, 1 if relu else 0,
                                       _p(out), out.stride(0), _is_bf16(x), _stream()), "bn_act_fwd")
-        ctx.save_for_backward(x, out if relu else None, mi, gamma)
+        # the backward needs the ReLU mask: with a residual it reads it from `out`, otherwise it recomputes
+        # y > 0 from x, gamma, beta (the forward's own expression) and `out` is not read again
+        ctx.save_for_backward(x, out if (relu and residual is not None) else None, mi, gamma, beta)
         ctx.meta = (relu, residual is not None, count, res_dtype)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
-        x, out, mi, gamma = ctx.saved_tensors
+        x, out, mi, gamma, beta = ctx.saved_tensors
         relu, has_res, count, res_dtype = ctx.meta
         V, C = x.shape
         dout = _as_rows(dout, x.dtype)
@@ -329,7 +331,8 @@ class _BNActFn(torch.autograd.Function):
         sums = torch.zeros(2, C, device=x.device, dtype=torch.float32)
         ldo = out.stride(0) if out is not None else 0
         _lib.check(L.coocc_bn_act_bwd_reduce(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C,
-                                             _p(mi), 1 if relu else 0, _p(sums), bf, _stream()), "bn_act_bwd_reduce")
+                                             _p(mi), _p(gamma), _p(beta), 1 if relu else 0, _p(sums), bf, _stream()),
+                   "bn_act_bwd_reduce")
         local = sums
         if count != V:                      # SyncBN: batch terms use the sums over all ranks
             dist = _sync_group()
@@ -338,8 +341,9 @@ class _BNActFn(torch.autograd.Function):
         dx = torch.empty(V, C, device=x.device, dtype=x.dtype)
         dres = torch.empty(V, C, device=x.device, dtype=x.dtype) if has_res else None
         _lib.check(L.coocc_bn_act_bwd_apply(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C, _p(mi),
-                                            _p(gamma), 1 if relu else 0, _p(sums), count, _p(dx), dx.stride(0), bf,
-                                            _p(dres), C if has_res else 0, _stream()), "bn_act_bwd_apply")
+                                            _p(gamma), _p(beta), 1 if relu else 0, _p(sums), count, _p(dx),
+                                            dx.stride(0), bf, _p(dres), C if has_res else 0, _stream()),
+                   "bn_act_bwd_apply")
         if has_res and dres.dtype != res_dtype:
             dres = dres.to(res_dtype)
         return dx, None, local[1], local[0], dres, None, None, None, None, None

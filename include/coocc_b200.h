@@ -247,16 +247,19 @@ int coocc_bn_act_fwd(const void* x, long long ldx, long long V, int C, const flo
                      const float* gamma, const float* beta, const void* residual, long long ldr, int relu,
                      void* out, long long ldo, int act_bf16, void* stream);
 /* backward of the above, in two stream-ordered halves (a SyncBatchNorm all-reduce of `sums` fits in
- * between).  reduce: sums (float[2*C], zeroed by the caller) += (sum dz, sum dz*xhat), dz = dout*[out>0];
+ * between).  reduce: sums (float[2*C], zeroed by the caller) += (sum dz, sum dz*xhat), dz = dout*[y>0];
  * afterwards sums[0:C] = dbeta, sums[C:2C] = dgamma.  apply: dx = gradient w.r.t. x with the batch
- * terms divided by `count` (rows the statistics were taken over); dres (optional) = dz. */
+ * terms divided by `count` (rows the statistics were taken over); dres (optional) = dz.
+ * ReLU mask: read from `out` (the forward's output) when it is given -- required when a residual was added --
+ * and recomputed from x, gamma, beta with the forward's own expression when out == NULL (one tensor less
+ * to read; gamma / beta may be NULL otherwise in the reduce call). */
 int coocc_bn_act_bwd_reduce(const void* dout, long long ldd, const void* out, long long ldo, const void* x,
-                            long long ldx, long long V, int C, const float* mean_invstd, int relu, float* sums,
-                            int act_bf16, void* stream);
+                            long long ldx, long long V, int C, const float* mean_invstd, const float* gamma,
+                            const float* beta, int relu, float* sums, int act_bf16, void* stream);
 int coocc_bn_act_bwd_apply(const void* dout, long long ldd, const void* out, long long ldo, const void* x,
-                           long long ldx, long long V, int C, const float* mean_invstd, const float* gamma, int relu,
-                           const float* sums, long long count, void* dx, long long lddx, int act_bf16, void* dres,
-                           long long lddr, void* stream);
+                           long long ldx, long long V, int C, const float* mean_invstd, const float* gamma,
+                           const float* beta, int relu, const float* sums, long long count, void* dx, long long lddx,
+                           int act_bf16, void* dres, long long lddr, void* stream);
 /* dst[(2x,2y,2z)] = src[(x,y,z)], zero elsewhere (dst extent X,Y,Z; src extent oX,oY,oZ) */
 int coocc_dilate2(const void* src, long long lds, int oX, int oY, int oZ, int C, void* dst, long long ldd,
                   int X, int Y, int Z, int is_bf16, void* stream);
