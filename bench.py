@@ -379,6 +379,22 @@ def run_ours(args, cfg):
                               peak_source=peak_src,
                               traffic_note=NCU_TRAFFIC["note"],
                               note="tf32 math has half the nominal bf16 rate" if args.precision == "tf32" else ""))
+    if gstep.capture_error is not None:
+        line["config"]["launch"] = "eager (CUDA-graph capture failed: %s)" % gstep.capture_error
+    if world == 1 and args.precision != "fp32":
+        # the same step in the parity arithmetic (3xTF32 split = fp32-accurate convolutions, fp32 storage), the mode
+        # tests/test_gpu_parity.py holds to the 1e-3 bound; reported next to the bf16 headline, eager launches
+        try:
+            coocc_b200.set_precision("fp32")
+            for _ in range(2):
+                eager_step(resident)
+            ms32 = timed(lambda: eager_step(resident), 3) / 3
+            line["parity_mode"] = dict(precision="fp32 (3xTF32 split, fp32 activations)", ms_per_step=ms32,
+                                       value=nvox / (ms32 / 1e3), unit=UNIT)
+        except Exception as e:  # noqa: BLE001
+            line["parity_mode"] = dict(error=str(e).splitlines()[0][:200])
+        finally:
+            coocc_b200.set_precision(args.precision)
     line["parity"] = dict(mode=args.precision,
                           note="fp32 mode (3xTF32 split) matches the oracle to 3e-5 on logits; tf32 ~1e-2; bf16 ~5e-2 "
                                "(tests/test_gpu_parity.py, profiles/r01_gpu_parity_*.log); indices bit-exact in every mode")

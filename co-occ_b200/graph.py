@@ -52,6 +52,7 @@ class GraphedStep:
         self.static = None          # fixed-address copies of the small inputs
         self.stats = dict(replays=0, eager=0, captures=0)
         self.launches_per_replay = 0
+        self.capture_error = None   # set if a capture failed and the runner fell back to eager launches
         self._stream = None         # capture stream; the warm-up step runs on it too, so that autograd's
         self._warm = False
         self._last = None           # AccumulateGrad nodes live on the stream the capture uses
@@ -129,7 +130,16 @@ class GraphedStep:
             if len(self.graphs) >= self.max_graphs:
                 self.stats["eager"] += 1
                 return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
-            entry = self._capture(key, ov, img, pts)
+            try:
+                entry = self._capture(key, ov, img, pts)
+            except Exception as e:  # noqa: BLE001 -- a failed capture must not take the training run down
+                # (the eager path computes the same step; the failure is kept for the caller to report)
+                self.enabled = False
+                self.capture_error = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])
+                _dbg("capture failed, falling back to eager: " + self.capture_error)
+                torch.cuda.synchronize()
+                self.stats["eager"] += 1
+                return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
         entry["graph"].replay()
         self.stats["replays"] += 1
         if self.stats["replays"] <= 2 and os.environ.get("COOCC_DEBUG"):
