@@ -135,7 +135,7 @@ class GraphedStep:
             except Exception as e:  # noqa: BLE001 -- a failed capture must not take the training run down
                 # (the eager path computes the same step; the failure is kept for the caller to report)
                 self.enabled = False
-                self.capture_error = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])
+                self.capture_error = "%s: %s" % (type(e).__name__, (str(e).splitlines() or [""])[0][:200])
                 _dbg("capture failed, falling back to eager: " + self.capture_error)
                 torch.cuda.synchronize()
                 self.stats["eager"] += 1
