@@ -236,6 +236,63 @@ def golden_lss():
     return g
 
 
+FINE_GRID = (20, 20, 4)
+
+
+def fine_inputs(seed=1):
+    """Seeded inputs of the fine-stage golden case (coarse grid 20x20x4, 6 cameras, 16x44 image features)."""
+    gen = torch.Generator().manual_seed(seed)
+    feats = torch.randn(1, 128, *FINE_GRID, generator=gen)
+    occ = torch.randn(1, 17, *FINE_GRID, generator=gen)
+    occ[:, 0] += 1.0
+    rig = S.make_camera_rig(6, 0)
+    img_feats = torch.randn(1, 6, 512, 16, 44, generator=gen) * 0.5
+    transform = (rig["rots"], rig["trans"], rig["intrins"], rig["post_rots"], rig["post_trans"], rig["bda"],
+                 None, None, None, None, None, None, (torch.tensor([256]), torch.tensor([704])))
+    return feats, occ, img_feats, transform
+
+
+def fine_head_params(seed=0):
+    """State-dict entries of the fine stage (occ_head.py:58-82) with the reference layer shapes."""
+    g = torch.Generator().manual_seed(seed + 71)
+    r = lambda *s: torch.randn(*s, generator=g)
+    p = {"img_mlp_0.0.weight": r(128, 512, 1, 1) * 0.04, "img_mlp_0.0.bias": r(128) * 0.1,
+         "img_mlp_0.1.weight": 1 + 0.1 * r(128), "img_mlp_0.1.bias": 0.1 * r(128),
+         "img_mlp.0.weight": r(64, 128) * 0.09, "img_mlp.0.bias": r(64) * 0.1,
+         "img_mlp.1.weight": 1 + 0.1 * r(64), "img_mlp.1.bias": 0.1 * r(64),
+         "fine_mlp.0.weight": r(64, 192) * 0.07, "fine_mlp.0.bias": r(64) * 0.1,
+         "fine_mlp.1.weight": 1 + 0.1 * r(64), "fine_mlp.1.bias": 0.1 * r(64),
+         "fine_mlp.3.weight": r(17, 64) * 0.12, "fine_mlp.3.bias": r(17) * 0.1}
+    return p
+
+
+def golden_fine(ns):
+    """Reference OccHead fine / cascade stage (occ_head.py:182-237) + loss_point (:295-312), run as they are: the
+    coarse half is fed in directly (forward_coarse_voxel replaced by the seeded tensors), fine_topk small enough
+    to exercise the random-subset branch (coordinate_transform.py:19-21) under torch.manual_seed(123)."""
+    feats, occ, img_feats, transform = fine_inputs()
+    head = ns.OccHead(norm_cfg=dict(type="SyncBN", requires_grad=True), soft_weights=True, cascade_ratio=2,
+                      sample_from_voxel=True, sample_from_img=True, final_occ_size=[2 * s for s in FINE_GRID],
+                      fine_topk=150, empty_idx=0, num_level=4, in_channels=[256] * 4, out_channel=17,
+                      point_cloud_range=[-10.0, -10.0, -5.0, 10.0, 10.0, 3.0])
+    head.train()
+    head.load_state_dict(fine_head_params(), strict=False)
+    f = feats.clone().requires_grad_(True)
+    head.forward_coarse_voxel = lambda vf: {"out_voxel_feats": [f], "occ": [occ]}
+    torch.manual_seed(123)
+    res = head(voxel_feats=[None] * 4, img_feats=[img_feats], transform=transform)
+    fc, fo = res["output_coords_fine"][0], res["output_voxels_fine"][0]
+    gt = S.make_gt_occ(FINE_GRID, 2, 3)
+    ld = head.loss_point(fc, fo, gt, "fine")
+    names = ["loss_voxel_ce_fine", "loss_voxel_sem_scal_fine", "loss_voxel_geo_scal_fine", "loss_voxel_lovasz_fine"]
+    g = dict(fine_coord=fc.numpy().astype(np.int32), fine_output=fo.detach().numpy().astype(np.float32),
+             losses=np.array([ld[k].item() for k in names], dtype=np.float64))
+    sum(ld.values()).backward()
+    g["dfeats_sample"], g["dfeats_stats"] = sample(f.grad), stats(f.grad)
+    g["dw_fine3"] = head.fine_mlp[3].weight.grad.numpy().astype(np.float32)
+    return g
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gl2 = golden_lss()
@@ -247,6 +304,10 @@ def main():
     np.savez_compressed(path, **ge)
     print("eval ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
     ns = refshim.load_reference()
+    gf = golden_fine(ns)
+    path = os.path.join(OUT, "reference_fine.npz")
+    np.savez_compressed(path, **gf)
+    print("fine ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
     gl = golden_losses(ns)
     path = os.path.join(OUT, "reference_losses.npz")
     np.savez_compressed(path, **gl)
