@@ -85,6 +85,13 @@ _SIGS = {
     "coocc_lss_sort": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "coocc_lss_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_lss_pool_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
+    "coocc_fine_sample3d_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_fine_sample3d_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_fine_project": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "coocc_fine_sample2d_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_fine_sample2d_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_groupnorm_fwd": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_ll, c_void_p]),
+    "coocc_groupnorm_bwd": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -955,3 +955,137 @@ def eval_confusion(logits2d, dims, gt, visible_mask=None, empty_idx=0, ignore=25
                                       int(empty_idx), int(ignore), _p(h_ssc), _p(h_vis), _p(h_sc), _stream()),
                "eval_confusion")
     return h_ssc, h_vis, h_sc
+
+
+# ----------------------------------------------------------------------------------------
+# OccHead fine / cascade stage (occ_head.py:182-237) -- csrc/fine_stage.cu.
+# Arithmetic verified on the CPU (tests/test_fine_emul.py); not yet run on a B200.
+# ----------------------------------------------------------------------------------------
+class _Sample3dFn(torch.autograd.Function):
+    """feats [V,C] fp32 NDHWC rows, coords int32 [3,M] fine voxel indices -> [M,C] trilinear samples (:212-221)."""
+
+    @staticmethod
+    def forward(ctx, feats, dims, coords, final_size):
+        L = _lib.lib()
+        _require_cuda(feats, coords)
+        feats = _as_rows(feats.float() if feats.dtype != torch.float32 else feats)
+        C = feats.shape[1]
+        coords = coords.to(torch.int32).contiguous()
+        M = coords.shape[1]
+        out = torch.empty(M, C, device=feats.device, dtype=torch.float32)
+        _lib.check(L.coocc_fine_sample3d_fwd(_p(feats), feats.stride(0), dims[0], dims[1], dims[2], C, _p(coords), M,
+                                             int(final_size[0]), int(final_size[1]), int(final_size[2]), _p(out), C,
+                                             _stream()), "fine_sample3d_fwd")
+        ctx.save_for_backward(coords)
+        ctx.meta = (tuple(dims), C, M, tuple(int(v) for v in final_size), feats.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        (coords,) = ctx.saved_tensors
+        dims, C, M, fs, V = ctx.meta
+        g = _as_rows(g.float())
+        d = torch.zeros(V, C, device=g.device, dtype=torch.float32)
+        _lib.check(L.coocc_fine_sample3d_bwd(_p(g), g.stride(0), dims[0], dims[1], dims[2], C, _p(coords), M, fs[0],
+                                             fs[1], fs[2], _p(d), C, _stream()), "fine_sample3d_bwd")
+        return d, None, None, None
+
+
+def fine_sample_voxels(feats2d, dims, coords, final_size):
+    return _Sample3dFn.apply(feats2d, tuple(dims), coords, final_size)
+
+
+def fine_project(coords, rots, trans, intrins, post_rots, post_trans, bda, pts_range, W_img, H_img, grid_fine):
+    """project_points_on_img (coordinate_transform.py:29-70, nuScenes): coords int [3,M]; rots/intrins/post_rots
+    [n,3,3], trans/post_trans [n,3], bda [3,3] -> (uv [n,M,2] fp32, mask uint8 [M,n]).  No gradient (the
+    reference computes it under no_grad)."""
+    L = _lib.lib()
+    _require_cuda(coords, rots)
+    with torch.no_grad():
+        n = rots.shape[0]
+        pr = pts_range.detach().float().cpu()
+        vs = (pr[3:] - pr[:3]) / torch.tensor([grid_fine[0] - 1, grid_fine[1] - 1, grid_fine[2] - 1])      # :33
+        cam = torch.cat([rots.inverse().reshape(n, 9), trans.reshape(n, 3), intrins.reshape(n, 9),
+                         post_rots[:, :2, :2].reshape(n, 4), post_trans[:, :2].reshape(n, 2)], 1).float().contiguous()
+        inv_bda = bda.inverse().float().contiguous()
+        coords = coords.to(torch.int32).contiguous()
+        M = coords.shape[1]
+        uv = torch.empty(n, M, 2, device=coords.device, dtype=torch.float32)
+        mask = torch.empty(M, n, device=coords.device, dtype=torch.uint8)
+        f3 = lambda t: (ctypes.c_float * 3)(*[float(v) for v in t.tolist()])
+        _lib.check(L.coocc_fine_project(_p(coords), M, n, f3(vs), f3(pr[:3]), _p(inv_bda), _p(cam), float(W_img),
+                                        float(H_img), _p(uv), _p(mask), _stream()), "fine_project")
+    return uv, mask
+
+
+class _Sample2dFn(torch.autograd.Function):
+    """img [n*H*W, C] NHWC rows, uv [n,M,2], mask [M,n] -> [M,C]: masked sum over cameras of bilinear samples (:231-233)."""
+
+    @staticmethod
+    def forward(ctx, img, n, H, W, uv, mask):
+        L = _lib.lib()
+        img = _as_rows(img.float() if img.dtype != torch.float32 else img)
+        C = img.shape[1]
+        M = uv.shape[1]
+        out = torch.empty(M, C, device=img.device, dtype=torch.float32)
+        _lib.check(L.coocc_fine_sample2d_fwd(_p(img), img.stride(0), n, H, W, C, _p(uv), _p(mask), M, _p(out), C,
+                                             _stream()), "fine_sample2d_fwd")
+        ctx.save_for_backward(uv, mask)
+        ctx.meta = (n, H, W, C, M)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        uv, mask = ctx.saved_tensors
+        n, H, W, C, M = ctx.meta
+        g = _as_rows(g.float())
+        d = torch.zeros(n * H * W, C, device=g.device, dtype=torch.float32)
+        _lib.check(L.coocc_fine_sample2d_bwd(_p(g), g.stride(0), n, H, W, C, _p(uv), _p(mask), M, _p(d), C, _stream()),
+                   "fine_sample2d_bwd")
+        return d, None, None, None, None, None
+
+
+def fine_sample_images(img_rows, n, H, W, uv, mask):
+    return _Sample2dFn.apply(img_rows, n, H, W, uv, mask)
+
+
+class _GroupNormFn(torch.autograd.Function):
+    """nn.GroupNorm(G) (+ ReLU) on rows [R, C]; `span` consecutive rows are one sample (1 = point rows, H*W = a map)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, G, span, eps, relu):
+        L = _lib.lib()
+        _require_cuda(x)
+        x = _as_rows(x.float() if x.dtype != torch.float32 else x)
+        R, C = x.shape
+        gamma, beta = gamma.float().contiguous(), beta.float().contiguous()
+        stats = torch.empty(max(R // span, 1) * G * 2, device=x.device, dtype=torch.float32)
+        y = torch.empty(R, C, device=x.device, dtype=torch.float32)
+        _lib.check(L.coocc_groupnorm_fwd(_p(x), x.stride(0), R, C, G, span, _p(gamma), _p(beta), float(eps),
+                                         1 if relu else 0, _p(stats), _p(y), C, _stream()), "groupnorm_fwd")
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.meta = (G, span, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x, gamma, beta, stats = ctx.saved_tensors
+        G, span, relu = ctx.meta
+        R, C = x.shape
+        dy = _as_rows(dy.float())
+        sums = torch.empty_like(stats)
+        dx = torch.empty(R, C, device=x.device, dtype=torch.float32)
+        dg = torch.zeros(C, device=x.device, dtype=torch.float32)
+        db = torch.zeros(C, device=x.device, dtype=torch.float32)
+        _lib.check(L.coocc_groupnorm_bwd(_p(x), x.stride(0), R, C, G, span, _p(gamma), _p(beta), 1 if relu else 0,
+                                         _p(stats), _p(dy), dy.stride(0), _p(sums), _p(dx), C, _p(dg), _p(db), _stream()),
+                   "groupnorm_bwd")
+        return dx, dg, db, None, None, None, None
+
+
+def group_norm_rows(x2d, gn, span=1, relu=True):
+    """x2d [R,C] rows through the nn.GroupNorm parameter container `gn` (+ ReLU)."""
+    return _GroupNormFn.apply(x2d, gn.weight, gn.bias, gn.num_groups, span, gn.eps, relu)

@@ -25,6 +25,11 @@ NUSC_CLASS_FREQUENCIES = [2242961742295, 25985376, 1561108, 28862014, 196106643,
                           1724391378]
 
 
+# The fine / cascade stage of OccHead is implemented (csrc/fine_stage.cu) and its arithmetic is checked on the CPU,
+# but it has not run on a B200 yet: it only executes when this switch is turned on.
+FINE_STAGE = {"enabled": False}
+
+
 def _norm_layer(norm_cfg, c):
     cfg = dict(norm_cfg or dict(type="BN3d"))
     typ = cfg.pop("type")
@@ -278,6 +283,17 @@ class OccHead(nn.Module):
         self.occ_pred_conv = nn.Sequential(nn.Conv3d(mid, mid // 2, 1, bias=bias), _norm_layer(norm_cfg, mid // 2),
                                            nn.ReLU(inplace=True), nn.Conv3d(mid // 2, out_channel, 1, bias=bias))
         self.num_point_sampling_feat = num_level
+        # fine / cascade stage (occ_head.py:58-82): parameter containers with the reference's names and shapes
+        self.point_cloud_range = torch.tensor(point_cloud_range).float()
+        self.fine_stage = cascade_ratio != 1 and (sample_from_voxel or sample_from_img)
+        if self.fine_stage:
+            fine_in = 128 if sample_from_voxel else 0
+            if sample_from_img:
+                self.img_mlp_0 = nn.Sequential(nn.Conv2d(512, 128, 1, 1, 0), nn.GroupNorm(16, 128), nn.ReLU(inplace=True))
+                self.img_mlp = nn.Sequential(nn.Linear(128, 64), nn.GroupNorm(16, 64), nn.ReLU(inplace=True))
+                fine_in += 64
+            self.fine_mlp = nn.Sequential(nn.Linear(fine_in, 64), nn.GroupNorm(16, 64), nn.ReLU(inplace=True),
+                                          nn.Linear(64, out_channel))
         if soft_weights:
             self.voxel_soft_weights = nn.Sequential(
                 nn.Conv3d(mid, mid // 2, 1, bias=bias), _norm_layer(norm_cfg, mid // 2), nn.ReLU(inplace=True),
@@ -320,23 +336,86 @@ class OccHead(nn.Module):
                 'loss_voxel_geo_scal_{}'.format(tag): self.loss_voxel_geo_scal_weight * l4[2],
                 'loss_voxel_lovasz_{}'.format(tag): self.loss_voxel_lovasz_weight * l4[3]}
 
+    def loss_point(self, fine_coord, fine_output, target_voxels, tag):
+        """occ_head.py:295-312: the four voxel losses on the sampled points (CE without class weights, :305)."""
+        gt = target_voxels[:, fine_coord[0, :], fine_coord[1, :], fine_coord[2, :]].long()[0]
+        l4 = CF.occ_voxel_losses(fine_output, gt.to(torch.int32).contiguous(), None, 255, self.empty_idx)
+        return {'loss_voxel_ce_{}'.format(tag): self.loss_voxel_ce_weight * l4[0],
+                'loss_voxel_sem_scal_{}'.format(tag): self.loss_voxel_sem_scal_weight * l4[1],
+                'loss_voxel_geo_scal_{}'.format(tag): self.loss_voxel_geo_scal_weight * l4[2],
+                'loss_voxel_lovasz_{}'.format(tag): self.loss_voxel_lovasz_weight * l4[3]}
+
     def loss(self, output_voxels=None, output_coords_fine=None, output_voxels_fine=None, target_voxels=None,
              target_points=None, img_metas=None, visible_mask=None, **kwargs):
-        """occ_head.py:314-337 (coarse levels; the fine/cascade stage and lidarseg are not on the path)."""
+        """occ_head.py:314-337 (lidarseg is not on the path)."""
         loss_dict = {}
         for index, output_voxel in enumerate(output_voxels):
             loss_dict.update(self.loss_voxel(output_voxel, target_voxels, tag='c_{}'.format(index)))
-        if output_voxels_fine is not None or target_points:
-            raise NotImplementedError("OccHead fine stage / lidarseg losses are outside the hot path (SURVEY §8f)")
+        if self.cascade_ratio != 1 and output_voxels_fine is not None:          # :320-331
+            acc = {}
+            for fine_coord, fine_output in zip(output_coords_fine, output_voxels_fine):
+                for k, v in self.loss_point(fine_coord, fine_output, target_voxels, tag='fine').items():
+                    acc[k] = v if k not in acc else acc[k] + v
+            for k, v in acc.items():
+                loss_dict[k] = v / len(output_coords_fine)
+        if target_points:
+            raise NotImplementedError("OccHead lidarseg losses are outside the hot path (SURVEY §8f)")
         return loss_dict
+
+    def forward_fine(self, out_voxel_feats, coarse_occ, img_feats, transform):
+        """occ_head.py:182-237 for B = 1: occupied coarse voxels -> their cascade_ratio^3 children (a random subset of
+        fine_topk parents in training, coordinate_transform.py:19-21) -> trilinear sample of out_voxel_feats,
+        camera projection + bilinear sample of the image features (img_mlp_0, masked camera sum, img_mlp),
+        fine_mlp -> per-point logits.  Sampling / projection / GroupNorm run in csrc/fine_stage.cu, the Linear
+        layers on the tensor-core conv kernel.  Returns (fine_coord [3,M] int64, fine_output [M, out_channel])."""
+        if not FINE_STAGE["enabled"]:
+            raise NotImplementedError(
+                "OccHead fine / cascade stage: kernels written and checked on the CPU (tests/test_fine_emul.py) but not "
+                "yet validated on a B200; set coocc_b200.modules.FINE_STAGE['enabled'] = True to run them (DESIGN.md §6g)")
+        x2d, dims = CF.to_cl2d(out_voxel_feats)
+        mask = coarse_occ.argmax(1) != self.empty_idx                                           # :183
+        if int(mask.sum()) == 0:
+            raise AssertionError('no foreground in coarse voxel')                               # :184
+        coarse = torch.nonzero(mask[0]).t().contiguous()                                        # [3,N], (x,y,z) lexicographic
+        r = self.cascade_ratio
+        topk = self.fine_topk if self.training else 30000
+        off = torch.stack(torch.meshgrid(*([torch.arange(r, device=coarse.device)] * 3), indexing='ij'), 3).reshape(-1, 3)
+        fine = coarse[None] * r + off[:, :, None]                                               # [r^3,3,N]
+        if fine.shape[-1] >= topk:
+            fine = fine[:, :, torch.randperm(fine.shape[-1])[:topk].to(fine.device)]            # CPU generator like the reference
+        fine = fine.permute(1, 0, 2).reshape(3, -1)
+        feats = []
+        if self.sample_from_voxel:
+            feats.append(CF.fine_sample_voxels(x2d, dims, fine, self.final_occ_size))
+        if self.sample_from_img and img_feats is not None:
+            f = img_feats[0]                                                                    # [1,n,512,Hf,Wf]
+            _, n, Ci, Hf, Wf = f.shape
+            rows = f[0].permute(0, 2, 3, 1).reshape(n * Hf * Wf, Ci)
+            c0 = self.img_mlp_0[0]
+            rows = CF.linear(rows, c0.weight.reshape(c0.out_channels, Ci), c0.bias)
+            rows = CF.group_norm_rows(rows, self.img_mlp_0[1], span=Hf * Wf, relu=True)
+            X, Y, Z = dims
+            uv, m = CF.fine_project(fine, transform[0][0], transform[1][0], transform[2][0], transform[3][0],
+                                    transform[4][0], transform[5][0], self.point_cloud_range,
+                                    float(transform[-1][1][0]), float(transform[-1][0][0]), (X * r, Y * r, Z * r))
+            s = CF.fine_sample_images(rows, n, Hf, Wf, uv, m)
+            s = CF.linear(s, self.img_mlp[0].weight, self.img_mlp[0].bias)
+            feats.append(CF.group_norm_rows(s, self.img_mlp[1], span=1, relu=True))
+        h = torch.cat(feats, 1)
+        h = CF.linear(h, self.fine_mlp[0].weight, self.fine_mlp[0].bias)
+        h = CF.group_norm_rows(h, self.fine_mlp[1], span=1, relu=True)
+        return fine, CF.linear(h, self.fine_mlp[3].weight, self.fine_mlp[3].bias)
 
     def forward(self, voxel_feats, img_feats=None, img_metas=None, pts_feats=None, target_points=None,
                 transform=None, **kwargs):
         assert type(voxel_feats) is list and len(voxel_feats) == self.num_level
         out = self.forward_coarse_voxel(voxel_feats)
-        if self.cascade_ratio != 1 and (self.sample_from_img or self.sample_from_voxel):
-            raise NotImplementedError("OccHead fine/cascade stage is outside the hot path (SURVEY §8f rank 1)")
-        return {"output_voxels": out["occ"], "output_voxels_fine": None, "output_coords_fine": None,
+        fine_output = fine_coord = None
+        if self.fine_stage:
+            assert out["occ"][0].shape[0] == 1, "batch 1 like the rest of the path"
+            c, o = self.forward_fine(out["out_voxel_feats"][0], out["occ"][0], img_feats, transform)
+            fine_coord, fine_output = [c], [o]
+        return {"output_voxels": out["occ"], "output_voxels_fine": fine_output, "output_coords_fine": fine_coord,
                 "output_points": None}
 
 

@@ -229,6 +229,39 @@ int coocc_lss_pool_bwd(const unsigned int* point_keys, long long npts, int V, in
                        float* dfeat, long long lddf, float* ddepth, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * OccHead fine / cascade stage (csrc/fine_stage.cu, bodies in csrc/fine_stage.cuh) -- SURVEY §8f rank 1, second half.
+ * Replaces, in P/coocc/dense_heads/occ_head.py:182-237, the 5-D F.grid_sample of out_voxel_feats (:219), the
+ * camera projection project_points_on_img (P/utils/coordinate_transform.py:29-70), the 4-D F.grid_sample of the
+ * image features with the masked camera sum (:231-233) and nn.GroupNorm(16) + ReLU of img_mlp_0 / img_mlp /
+ * fine_mlp (:58-78).  All fp32.  NOT YET RUN ON A GPU: arithmetic verified on the CPU through
+ * tests/emul/fine_emul.cpp only.
+ * ------------------------------------------------------------------------------------------ */
+/* feats [X*Y*Z][ld] NDHWC rows; coords int32 [3][M] fine voxel indices; S* = final_occ_size; out [M][ldo]:
+ * trilinear sample at grid = (c/(S-1) - 0.5)*2, zeros padding, align_corners=False. */
+int coocc_fine_sample3d_fwd(const float* feats, long long ld, int X, int Y, int Z, int C, const int* coords, int M,
+                            int SX, int SY, int SZ, float* out, long long ldo, void* stream);
+/* dfeats [X*Y*Z][ldd] += scatter of gout [M][ldg] (atomics; zeroed by the caller) */
+int coocc_fine_sample3d_bwd(const float* gout, long long ldg, int X, int Y, int Z, int C, const int* coords, int M,
+                            int SX, int SY, int SZ, float* dfeats, long long ldd, void* stream);
+/* vs3 / lo3: HOST float[3] voxel size and lower corner; inv_bda float[9]; cam27 [ncam][27] = inverse(rots)(9) |
+ * trans(3) | intrins(9) | post_rots[:2,:2](4) | post_trans[:2](2); uv [ncam][M][2], mask uint8 [M][ncam]. */
+int coocc_fine_project(const int* coords, int M, int ncam, const float* vs3, const float* lo3, const float* inv_bda,
+                       const float* cam27, float W_img, float H_img, float* uv, unsigned char* mask, void* stream);
+/* img [ncam*H*W][ld] NHWC rows; out [M][ldo] = sum over cameras with mask of the bilinear sample (align_corners=True) */
+int coocc_fine_sample2d_fwd(const float* img, long long ld, int ncam, int H, int W, int C, const float* uv,
+                            const unsigned char* mask, int M, float* out, long long ldo, void* stream);
+int coocc_fine_sample2d_bwd(const float* gout, long long ldg, int ncam, int H, int W, int C, const float* uv,
+                            const unsigned char* mask, int M, float* dimg, long long ldd, void* stream);
+/* GroupNorm(G) (+ ReLU) over rows [rows][ldx]; `span` consecutive rows form one sample (1: point rows, H*W: an
+ * NHWC feature map).  stats float[rows/span][G][2] (mean, rstd) is written by fwd and read by bwd. */
+int coocc_groupnorm_fwd(const float* x, long long ldx, long long rows, int C, int G, int span, const float* gamma,
+                        const float* beta, float eps, int relu, float* stats, float* y, long long ldy, void* stream);
+/* sums: scratch float[rows/span][G][2]; dgamma / dbeta float[C] accumulated with atomics (zeroed by the caller) */
+int coocc_groupnorm_bwd(const float* x, long long ldx, long long rows, int C, int G, int span, const float* gamma,
+                        const float* beta, int relu, const float* stats, const float* dy, long long lddy, float* sums,
+                        float* dx, long long lddx, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * BatchNorm3d (training mode) + ReLU + residual, and x2 zero insertion (csrc/elementwise.cu).
  * Replaces torch.nn.BatchNorm3d / SyncBatchNorm + nn.ReLU (+ `out += residual`) at
  * P/coocc/fuser/bifuser_n.py:25-29, P/coocc/backbones/resnet3d.py:46-62, P/coocc/necks/fpn3d.py:48-67,
