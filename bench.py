@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--workload", default="northstar")
     ap.add_argument("--precision", default=os.environ.get("COOCC_PRECISION", "bf16"), choices=["tf32", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default=os.environ.get("COOCC_OPTIMIZER", "torch"), choices=["torch", "coocc"],
+                    help="torch: torch.optim.AdamW(fused=True); coocc: co-occ_b200/optim.py FusedAdamW (one multi-tensor "
+                         "kernel that also writes the bf16 weight operands) -- CPU-verified, not yet validated on a B200")
     ap.add_argument("--parity-mode", action="store_true",
                     help="also time the step in the fp32-accurate (3xTF32) arithmetic of the parity tests and report it "
                          "as `parity_mode` next to the headline")
@@ -150,6 +153,7 @@ def workload_config(args, cfg):
                      "Lovasz) + render losses, backward, grad all-reduce, AdamW",
                 l2="inputs (%.0f MB/step) exceed the 126 MB L2" % (2 * X * Y * Z * cfg["C"] * 4 / 1e6),
                 parallelism="dp%d (replicas only)" % args.gpus, precision=args.precision,
+                optimizer="torch.optim.AdamW(fused)" if args.optimizer == "torch" else "coocc FusedAdamW + bf16 shadow",
                 launch="cuda_graph (whole step, co-occ_b200/graph.py)" if args.launch == "graph" else "eager")
 
 
@@ -236,7 +240,11 @@ def run_ours(args, cfg):
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
     reducer = GradReducer(params)
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True, capturable=(args.launch == "graph"))
+    if args.optimizer == "coocc":
+        from coocc_b200.optim import FusedAdamW
+        opt = FusedAdamW(params, lr=1e-4, weight_decay=0.01, shadow=(args.precision == "bf16"))
+    else:
+        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True, capturable=(args.launch == "graph"))
     LOSS_KEYS = ["loss_voxel_ce_c_0", "loss_voxel_sem_scal_c_0", "loss_voxel_geo_scal_c_0", "loss_voxel_lovasz_c_0",
                  "loss_depth_render", "loss_rgb"]
     gstep = coocc_b200.GraphedStep(model, opt, reducer, LOSS_KEYS, enabled=(args.launch == "graph"))

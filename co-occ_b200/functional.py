@@ -147,6 +147,17 @@ def weight_rows(w5d):
     return w.reshape(w5d.shape[0], -1)
 
 
+def weight_operand(w5d, dtype):
+    """weight_rows(w5d) in the storage type of `dtype`.  In bf16 mode a parameter that carries an up-to-date bf16
+    shadow (written by optim.FusedAdamW in the same pass as the update) is used as is instead of being converted."""
+    if dtype == DT_BF16:
+        sh = getattr(w5d, "_coocc_bf16", None)
+        if sh is not None and getattr(w5d, "_coocc_bf16_version", None) == w5d._version \
+                and w5d.permute(0, 2, 3, 4, 1).is_contiguous() and (sh.numel() // w5d.shape[0]) % 8 == 0:
+            return sh.view(w5d.shape[0], -1)
+    return _operand(weight_rows(w5d), dtype)
+
+
 def out_dim(n, k, s):
     return (n + 2 * (k // 2) - k) // s + 1
 
@@ -208,7 +219,7 @@ class _Conv3dFn(torch.autograd.Function):
         out_bf16 = bool(out_bf16) and dtype == DT_BF16
         # operands in their storage type (bf16 mode: converted once here and kept for backward)
         xo = _operand(_as_rows(x2d), dtype)
-        wo = _operand(weight_rows(w5d), dtype)
+        wo = weight_operand(w5d, dtype)
         stats = torch.zeros(2, cout, device=x2d.device, dtype=torch.float32) if want_stats else None
         y, odims = conv_fwd_raw(xo, wo, dims, cin, cout, k, s, bias, relu, stats=stats, dtype=dtype,
                                 out_bf16=out_bf16)

@@ -1,0 +1,101 @@
+"""AdamW for the hot-path parameters as ONE multi-tensor kernel (csrc/adamw.cu) that also refreshes the bf16 operand
+copy ("shadow") of every parameter, so that the bf16 mode no longer converts 148 M weights per step in separate
+passes.  Update rule = torch.optim.AdamW (the reference trains with AdamW, coocc_multi_r50_256x704.py:283-290).
+
+STATUS: the kernel body is verified on the CPU against torch.optim.AdamW (tests/test_adamw_emul.py); it has not run
+on a B200 yet, so bench.py keeps torch's fused AdamW unless `--optimizer coocc` is passed.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+CHUNK = 16384      # elements per scheduling chunk (multiple of 4)
+
+
+def build_tables(sizes, chunk=CHUNK):
+    """(chunk_tensor, chunk_index) int32 lists covering tensors of the given element counts."""
+    ct, ci = [], []
+    for t, n in enumerate(sizes):
+        for c in range((n + chunk - 1) // chunk):
+            ct.append(t)
+            ci.append(c)
+    return ct, ci
+
+
+def _dense(t):
+    """flat view of a dense tensor in its own memory order (contiguous or channels_last_3d)."""
+    if t.is_contiguous():
+        return t.view(-1)
+    if t.dim() == 5 and t.permute(0, 2, 3, 4, 1).is_contiguous():
+        return t.permute(0, 2, 3, 4, 1).reshape(-1)
+    raise ValueError("FusedAdamW needs dense parameters")
+
+
+class FusedAdamW:
+    """step() / zero_grad() like a torch optimizer for a fixed list of fp32 CUDA parameters.
+
+    shadow=True keeps `p._coocc_bf16` (a flat bf16 buffer in p's memory order) equal to bf16(p) after every step;
+    functional._operand uses it instead of converting.  Gradients must exist for every parameter at step()."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, shadow=True):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        dev = self.params[0].device
+        self.m = [torch.zeros_like(_dense(p)) for p in self.params]
+        self.v = [torch.zeros_like(_dense(p)) for p in self.params]
+        self.step_t = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.shadow = shadow
+        if shadow:
+            for p in self.params:
+                p._coocc_bf16 = _dense(p.detach()).to(torch.bfloat16)
+                p._coocc_bf16_version = p._version
+        ct, ci = build_tables([p.numel() for p in self.params])
+        self.chunk_tensor = torch.tensor(ct, device=dev, dtype=torch.int32)
+        self.chunk_index = torch.tensor(ci, device=dev, dtype=torch.int32)
+        self._table = torch.empty(len(self.params) * 6, dtype=torch.int64).pin_memory()
+        self._table_dev = torch.empty(len(self.params) * 6, device=dev, dtype=torch.int64)
+        self._grad_ptrs = None
+        self.state = {"initialised": True}      # torch-optimizer-like attribute (graph.GraphedStep checks it is non-empty)
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def _refresh_table(self):
+        ptrs = []
+        for p in self.params:
+            if p.grad is None:
+                raise RuntimeError("FusedAdamW.step(): a parameter has no gradient")
+            ptrs.append(_dense(p.grad).data_ptr())
+        if ptrs == self._grad_ptrs:
+            return
+        rows = []
+        for p, g, m, v in zip(self.params, ptrs, self.m, self.v):
+            sh = p._coocc_bf16.data_ptr() if self.shadow else 0
+            rows += [_dense(p.detach()).data_ptr(), g, m.data_ptr(), v.data_ptr(), sh, p.numel()]
+        self._table.copy_(torch.tensor(rows, dtype=torch.int64))
+        self._table_dev.copy_(self._table, non_blocking=True)
+        self._grad_ptrs = ptrs
+
+    @torch.no_grad()
+    def step(self):
+        L = _lib.lib()
+        self._refresh_table()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(L.coocc_adamw_step(ctypes.c_void_p(self._table_dev.data_ptr()), len(self.params),
+                                      ctypes.c_void_p(self.chunk_tensor.data_ptr()),
+                                      ctypes.c_void_p(self.chunk_index.data_ptr()), self.chunk_tensor.numel(), CHUNK,
+                                      float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                      float(self.weight_decay), ctypes.c_void_p(self.step_t.data_ptr()), 0, st),
+                   "adamw_step")
+        # the shadow was rewritten in the same pass as p: mark it valid for p's current version (the raw-pointer update
+        # does not move the autograd version counter; any later in-place change of p does, and invalidates it)
+        if self.shadow:
+            for p in self.params:
+                p._coocc_bf16_version = p._version

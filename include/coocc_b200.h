@@ -262,6 +262,20 @@ int coocc_groupnorm_bwd(const float* x, long long ldx, long long rows, int C, in
                         float* dx, long long lddx, float* dgamma, float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-tensor AdamW step that also writes the bf16 operand copy of every parameter (csrc/adamw.cu, body in
+ * csrc/adamw.cuh).  Replaces torch.optim.AdamW (the reference's optimizer, coocc_multi_r50_256x704.py:283-290) plus
+ * the per-step fp32 -> bf16 weight conversions of the bf16 mode.  NOT YET RUN ON A GPU; arithmetic
+ * verified on the CPU against torch.optim.AdamW (tests/test_adamw_emul.py).
+ * tensors: device array of ntensors 48-byte entries {float* p; float* g; float* m; float* v; uint16_t* bf16_shadow
+ * (or NULL); long long n}.  chunk_tensor / chunk_index: device int[nchunks], the tensor id and the chunk number of
+ * every chunk of chunk_elems (multiple of 4) elements.  step: device float, incremented by the call (t = 1 for the
+ * first update).  zero_grad != 0 clears the gradients after they have been consumed.
+ * ------------------------------------------------------------------------------------------ */
+int coocc_adamw_step(const void* tensors, int ntensors, const int* chunk_tensor, const int* chunk_index, int nchunks,
+                     int chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
+                     int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * BatchNorm3d (training mode) + ReLU + residual, and x2 zero insertion (csrc/elementwise.cu).
  * Replaces torch.nn.BatchNorm3d / SyncBatchNorm + nn.ReLU (+ `out += residual`) at
  * P/coocc/fuser/bifuser_n.py:25-29, P/coocc/backbones/resnet3d.py:46-62, P/coocc/necks/fpn3d.py:48-67,
