@@ -79,7 +79,6 @@ def cpu_sample_inputs(cfg, seed=0):
 
 def cpu_step_fn(cfg, seed=0):
     """fwd+bwd of the reference algorithm (oracle restatement) on the bounded sample."""
-    import torch.nn.functional as F
     from coocc_b200 import synthetic as S
     from oracle import oracle as O
     from oracle import losses as OL

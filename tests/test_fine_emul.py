@@ -7,12 +7,10 @@ import ctypes
 import os
 import subprocess
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
-from coocc_b200 import synthetic as S
 from oracle import finestage as OF
 from oracle.make_golden import FINE_GRID, fine_head_params, fine_inputs
 
