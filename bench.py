@@ -105,6 +105,38 @@ def cpu_step_fn(cfg, seed=0):
     return step, grid[0] * grid[1] * grid[2]
 
 
+def cpu_stage_seconds(cfg, seed=0):
+    """Forward-pass seconds of each stage of the CPU reference on the bounded sample."""
+    from coocc_b200 import synthetic as S
+    from oracle import oracle as O
+    from oracle import losses as OL
+    inp, grid = cpu_sample_inputs(cfg, seed)
+    C, K = cfg["C"], cfg["K"]
+    planes = [C, 2 * C, 4 * C, 8 * C]
+    P = dict(occ_fuser=S.fuser_params(C, K), semantic_encoder=S.resnet3d_params(C, planes),
+             semantic_neck=S.fpn3d_params(planes, 2 * C), pts_bbox_head=S.occhead_params([2 * C] * 4),
+             render=S.render_params(C))
+    out = {}
+    with torch.no_grad():
+        t = time.perf_counter()
+        fused = O.bifuser_forward(P["occ_fuser"], inp["img_voxel_feats"], inp["pts_voxel_feats"], K, tie="canonical")
+        out["occ_fuser"] = time.perf_counter() - t
+        t = time.perf_counter()
+        mid = O.resnet3d_forward(P["semantic_encoder"], fused)
+        out["semantic_encoder"] = time.perf_counter() - t
+        t = time.perf_counter()
+        neck = O.fpn3d_forward(P["semantic_neck"], mid)
+        out["semantic_neck"] = time.perf_counter() - t
+        t = time.perf_counter()
+        _, occ = O.occhead_coarse_forward(P["pts_bbox_head"], neck)
+        OL.loss_voxel(occ, inp["gt_occ"])
+        out["occ_head+loss"] = time.perf_counter() - t
+        t = time.perf_counter()
+        O.render_forward(P["render"], fused, inp["geom"], inp["gt_depth"], inp["gt_img"])
+        out["render"] = time.perf_counter() - t
+    return out
+
+
 def cpu_baseline(cfg, warm=1, steps=2):
     step, nvox = cpu_step_fn(cfg)
     for _ in range(warm):
@@ -118,7 +150,7 @@ def cpu_baseline(cfg, warm=1, steps=2):
                        "K=%d, %d cams x %d rays x %d samples, %d timed steps of %.2f s"
                        % (os.cpu_count() or 1, *CPU_SAMPLE_GRID, cfg["C"], cfg["K"], cfg["cams"], cfg["fH"] * cfg["fW"],
                           cfg["D"], steps, dt),
-                seconds_per_step=dt)
+                seconds_per_step=dt, forward_stage_seconds=cpu_stage_seconds(cfg))
 
 
 def run_reference(args, cfg):
@@ -389,6 +421,11 @@ def run_ours(args, cfg):
                               peak_source=peak_src,
                               traffic_note=NCU_TRAFFIC["note"],
                               note="tf32 math has half the nominal bf16 rate" if args.precision == "tf32" else ""))
+    if world == 1:      # (with more ranks SyncBN's all-reduces would need every rank to take part)
+        try:
+            line["forward_stage_ms"] = gpu_stage_ms(model, resident)
+        except Exception as e:  # noqa: BLE001 -- informational only
+            line["forward_stage_ms"] = dict(error=(str(e).splitlines() or [type(e).__name__])[0][:200])
     if gstep.capture_error is not None:
         line["config"]["launch"] = "eager (CUDA-graph capture failed: %s)" % gstep.capture_error
     if world == 1 and args.precision != "fp32" and args.parity_mode:
@@ -412,6 +449,36 @@ def run_ours(args, cfg):
         line["cpu_baseline"] = cpu_baseline(cfg)
     print(json.dumps(line), flush=True)
     shutdown()
+
+
+def gpu_stage_ms(model, d):
+    """Forward-pass milliseconds of each stage (eager launches, CUDA events on the current stream), the GPU
+    counterpart of cpu_baseline.forward_stage_seconds."""
+    from coocc_b200.modules import render_fn
+    marks = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        marks.append((name, e))
+
+    with torch.no_grad():
+        for _ in range(2):                      # second pass is the timed one (first warms allocator / caches)
+            marks.clear()
+            mark("start")
+            fused = model.occ_fuser(d["img"], d["pts"])
+            mark("occ_fuser")
+            mid = model.semantic_encoder(fused)
+            mark("semantic_encoder")
+            neck = model.semantic_neck(mid)
+            mark("semantic_neck")
+            outs = model.pts_bbox_head(voxel_feats=neck)
+            model.pts_bbox_head.loss(output_voxels=outs["output_voxels"], target_voxels=d["gt_occ"])
+            mark("occ_head+loss")
+            render_fn(fused, d["geom"], model.sigma_head, model.rgb_head, d["gt_depth"], d["gt_img"])
+            mark("render")
+        torch.cuda.synchronize()
+    return {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
 
 
 def main():
