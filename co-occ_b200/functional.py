@@ -979,6 +979,7 @@ class _Sample3dFn(torch.autograd.Function):
     def forward(ctx, feats, dims, coords, final_size):
         L = _lib.lib()
         _require_cuda(feats, coords)
+        ctx.in_dtype = feats.dtype
         feats = _as_rows(feats.float() if feats.dtype != torch.float32 else feats)
         C = feats.shape[1]
         coords = coords.to(torch.int32).contiguous()
@@ -1000,7 +1001,7 @@ class _Sample3dFn(torch.autograd.Function):
         d = torch.zeros(V, C, device=g.device, dtype=torch.float32)
         _lib.check(L.coocc_fine_sample3d_bwd(_p(g), g.stride(0), dims[0], dims[1], dims[2], C, _p(coords), M, fs[0],
                                              fs[1], fs[2], _p(d), C, _stream()), "fine_sample3d_bwd")
-        return d, None, None, None
+        return d.to(ctx.in_dtype), None, None, None
 
 
 def fine_sample_voxels(feats2d, dims, coords, final_size):
@@ -1036,6 +1037,7 @@ class _Sample2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, n, H, W, uv, mask):
         L = _lib.lib()
+        ctx.in_dtype = img.dtype
         img = _as_rows(img.float() if img.dtype != torch.float32 else img)
         C = img.shape[1]
         M = uv.shape[1]
@@ -1055,7 +1057,7 @@ class _Sample2dFn(torch.autograd.Function):
         d = torch.zeros(n * H * W, C, device=g.device, dtype=torch.float32)
         _lib.check(L.coocc_fine_sample2d_bwd(_p(g), g.stride(0), n, H, W, C, _p(uv), _p(mask), M, _p(d), C, _stream()),
                    "fine_sample2d_bwd")
-        return d, None, None, None, None, None
+        return d.to(ctx.in_dtype), None, None, None, None, None
 
 
 def fine_sample_images(img_rows, n, H, W, uv, mask):
@@ -1069,6 +1071,7 @@ class _GroupNormFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, G, span, eps, relu):
         L = _lib.lib()
         _require_cuda(x)
+        ctx.in_dtype = x.dtype
         x = _as_rows(x.float() if x.dtype != torch.float32 else x)
         R, C = x.shape
         gamma, beta = gamma.float().contiguous(), beta.float().contiguous()
@@ -1094,7 +1097,7 @@ class _GroupNormFn(torch.autograd.Function):
         _lib.check(L.coocc_groupnorm_bwd(_p(x), x.stride(0), R, C, G, span, _p(gamma), _p(beta), 1 if relu else 0,
                                          _p(stats), _p(dy), dy.stride(0), _p(sums), _p(dx), C, _p(dg), _p(db), _stream()),
                    "groupnorm_bwd")
-        return dx, dg, db, None, None, None, None
+        return dx.to(ctx.in_dtype), dg, db, None, None, None, None
 
 
 def group_norm_rows(x2d, gn, span=1, relu=True):
