@@ -1,6 +1,6 @@
 // adamw.cu -- CUDA launcher of the multi-tensor AdamW + bf16-shadow step (body in adamw.cuh).
-// STATUS: arithmetic verified on the CPU against torch.optim.AdamW (tests/test_adamw_emul.py); not yet run or timed
-// on a B200 -- bench.py keeps torch's fused AdamW unless --optimizer coocc is given.
+// Arithmetic verified on the CPU against torch.optim.AdamW (tests/test_adamw_emul.py) and on the GPU
+// (tests/test_gpu_adamw.py).
 #include <cuda_runtime.h>
 
 #include "../../include/coocc_b200.h"

@@ -64,6 +64,32 @@ COOCC_HD void adamw_item(const AdamWP& a, long long id) {
   const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
   const float decay = 1.f - a.lr * a.weight_decay;
   const int cnt = (t.n - base) < 4 ? (int)(t.n - base) : 4;
+  const uintptr_t al = (uintptr_t)(t.p + base) | (uintptr_t)(t.g + base) | (uintptr_t)(t.m + base) | (uintptr_t)(t.v + base);
+  if (cnt == 4 && (al & 15) == 0 && (!t.shadow || ((uintptr_t)(t.shadow + base) & 7) == 0)) {
+    // 16-byte accesses: one quad per work item, consecutive items touch consecutive quads (coalesced)
+    struct alignas(16) F4 { float x[4]; };
+    struct alignas(8) H4 { uint16_t x[4]; };
+    const F4 g4 = *reinterpret_cast<const F4*>(t.g + base);
+    F4 p4 = *reinterpret_cast<const F4*>(t.p + base);
+    F4 m4 = *reinterpret_cast<const F4*>(t.m + base);
+    F4 v4 = *reinterpret_cast<const F4*>(t.v + base);
+    H4 h4;
+    for (int k = 0; k < 4; ++k) {
+      const float g = g4.x[k];
+      float p = p4.x[k] * decay;
+      const float m = m4.x[k] + (g - m4.x[k]) * (1.f - a.beta1);
+      const float v = a.beta2 * v4.x[k] + (1.f - a.beta2) * g * g;
+      p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+      p4.x[k] = p; m4.x[k] = m; v4.x[k] = v;
+      h4.x[k] = f32_to_bf16_rn(p);
+    }
+    *reinterpret_cast<F4*>(t.p + base) = p4;
+    *reinterpret_cast<F4*>(t.m + base) = m4;
+    *reinterpret_cast<F4*>(t.v + base) = v4;
+    if (t.shadow) *reinterpret_cast<H4*>(t.shadow + base) = h4;
+    if (a.zero_grad) { F4 z; z.x[0] = z.x[1] = z.x[2] = z.x[3] = 0.f; *reinterpret_cast<F4*>(t.g + base) = z; }
+    return;
+  }
   for (int k = 0; k < cnt; ++k) {
     const long long i = base + k;
     const float g = t.g[i];

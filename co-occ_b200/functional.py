@@ -153,6 +153,7 @@ def weight_operand(w5d, dtype):
     if dtype == DT_BF16:
         sh = getattr(w5d, "_coocc_bf16", None)
         if sh is not None and getattr(w5d, "_coocc_bf16_version", None) == w5d._version \
+                and getattr(w5d, "_coocc_bf16_layout", None) == (w5d.data_ptr(), tuple(w5d.stride())) \
                 and w5d.permute(0, 2, 3, 4, 1).is_contiguous() and (sh.numel() // w5d.shape[0]) % 8 == 0:
             return sh.view(w5d.shape[0], -1)
     return _operand(weight_rows(w5d), dtype)

@@ -25,11 +25,6 @@ NUSC_CLASS_FREQUENCIES = [2242961742295, 25985376, 1561108, 28862014, 196106643,
                           1724391378]
 
 
-# The fine / cascade stage of OccHead is implemented (csrc/fine_stage.cu) and its arithmetic is checked on the CPU,
-# but it has not run on a B200 yet: it only executes when this switch is turned on.
-FINE_STAGE = {"enabled": False}
-
-
 def _norm_layer(norm_cfg, c):
     cfg = dict(norm_cfg or dict(type="BN3d"))
     typ = cfg.pop("type")
@@ -45,6 +40,15 @@ def _cl3d_(conv):
     if w.dim() == 5 and not w.permute(0, 2, 3, 4, 1).is_contiguous():
         w.data = w.data.contiguous(memory_format=torch.channels_last_3d)
     return w
+
+
+def _cl3d_all(module):
+    """Relayout every Conv3d weight of `module` to [Cout,kx,ky,kz,Cin] at construction, so that optimizers and
+    bf16 shadows built before the first forward see the final memory order (load_state_dict copies in place and
+    .to(device) preserves strides)."""
+    for m in module.modules():
+        if isinstance(m, nn.Conv3d):
+            _cl3d_(m)
 
 
 def batch_norm2d(x2d, bn):
@@ -110,6 +114,7 @@ class BiFuser_N(nn.Module):
             nn.Conv3d(in_channels * 2, out_channels, 3, padding=1, bias=False),
             nn.BatchNorm3d(out_channels), nn.ReLU(True))
         self.knn_enc = nn.Sequential(nn.Linear(in_channels * knum, out_channels), nn.ReLU())
+        _cl3d_all(self)
 
     def forward(self, img_voxel_feats, pts_voxel_feats):
         dims = tuple(img_voxel_feats.shape[2:])
@@ -169,6 +174,7 @@ class CustomResNet3D(nn.Module):
             elif isinstance(m, nn.BatchNorm3d):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
+        _cl3d_all(self)
 
     def _make_layer(self, planes, blocks, stride, norm_cfg):
         downsample = None
@@ -219,6 +225,7 @@ class FPN3D(nn.Module):
         for i in range(self.num_out):
             self.lateral_convs.append(nn.Sequential(_ConvModule(in_channels[i], out_channels, 1, norm_cfg)))
             self.fpn_convs.append(nn.Sequential(_ConvModule(out_channels, out_channels, 3, norm_cfg)))
+        _cl3d_all(self)
 
     def forward(self, inputs):
         assert len(inputs) == len(self.in_channels)
@@ -298,6 +305,7 @@ class OccHead(nn.Module):
             self.voxel_soft_weights = nn.Sequential(
                 nn.Conv3d(mid, mid // 2, 1, bias=bias), _norm_layer(norm_cfg, mid // 2), nn.ReLU(inplace=True),
                 nn.Conv3d(mid // 2, num_level, 1, bias=bias))
+        _cl3d_all(self)
 
     def forward_coarse_voxel(self, voxel_feats):
         occs, dims = [], []
@@ -368,10 +376,6 @@ class OccHead(nn.Module):
         camera projection + bilinear sample of the image features (img_mlp_0, masked camera sum, img_mlp),
         fine_mlp -> per-point logits.  Sampling / projection / GroupNorm run in csrc/fine_stage.cu, the Linear
         layers on the tensor-core conv kernel.  Returns (fine_coord [3,M] int64, fine_output [M, out_channel])."""
-        if not FINE_STAGE["enabled"]:
-            raise NotImplementedError(
-                "OccHead fine / cascade stage: kernels written and checked on the CPU (tests/test_fine_emul.py) but not "
-                "yet validated on a B200; set coocc_b200.modules.FINE_STAGE['enabled'] = True to run them (DESIGN.md §6g)")
         x2d, dims = CF.to_cl2d(out_voxel_feats)
         mask = coarse_occ.argmax(1) != self.empty_idx                                           # :183
         if int(mask.sum()) == 0:

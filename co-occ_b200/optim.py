@@ -2,8 +2,8 @@
 copy ("shadow") of every parameter, so that the bf16 mode no longer converts 148 M weights per step in separate
 passes.  Update rule = torch.optim.AdamW (the reference trains with AdamW, coocc_multi_r50_256x704.py:283-290).
 
-STATUS: the kernel body is verified on the CPU against torch.optim.AdamW (tests/test_adamw_emul.py); it has not run
-on a B200 yet, so bench.py keeps torch's fused AdamW unless `--optimizer coocc` is passed.
+Verified on the CPU against torch.optim.AdamW (tests/test_adamw_emul.py, kernel body compiled for the host) and on
+the GPU (tests/test_gpu_adamw.py: eager, under several CUDA graphs and with an eager step in between).
 """
 import ctypes
 
@@ -52,12 +52,17 @@ class FusedAdamW:
             for p in self.params:
                 p._coocc_bf16 = _dense(p.detach()).to(torch.bfloat16)
                 p._coocc_bf16_version = p._version
+                # the shadow is a flat copy in p's memory order *now*: a later relayout (p.data = ...) keeps the
+                # version counter, so the storage address and strides are part of the validity key
+                p._coocc_bf16_layout = (p.data_ptr(), tuple(p.stride()))
         ct, ci = build_tables([p.numel() for p in self.params])
         self.chunk_tensor = torch.tensor(ct, device=dev, dtype=torch.int32)
         self.chunk_index = torch.tensor(ci, device=dev, dtype=torch.int32)
-        self._table = torch.empty(len(self.params) * 6, dtype=torch.int64).pin_memory()
-        self._table_dev = torch.empty(len(self.params) * 6, device=dev, dtype=torch.int64)
-        self._grad_ptrs = None
+        # one (pinned host, device) pointer table per distinct set of gradient addresses.  A table is written once
+        # and never changed afterwards: the upload of a table first seen during a CUDA-graph capture becomes a
+        # memcpy node that re-reads its own pinned buffer on every replay, so the buffer must stay intact while
+        # other captures / eager steps (different gradient addresses) create their own tables.
+        self._tables = {}
         self.state = {"initialised": True}      # torch-optimizer-like attribute (graph.GraphedStep checks it is non-empty)
 
     def zero_grad(self, set_to_none=True):
@@ -73,22 +78,28 @@ class FusedAdamW:
             if p.grad is None:
                 raise RuntimeError("FusedAdamW.step(): a parameter has no gradient")
             ptrs.append(_dense(p.grad).data_ptr())
-        if ptrs == self._grad_ptrs:
-            return
+        key = tuple(ptrs)
+        hit = self._tables.get(key)
+        if hit is not None:
+            return hit[1]
         rows = []
         for p, g, m, v in zip(self.params, ptrs, self.m, self.v):
             sh = p._coocc_bf16.data_ptr() if self.shadow else 0
             rows += [_dense(p.detach()).data_ptr(), g, m.data_ptr(), v.data_ptr(), sh, p.numel()]
-        self._table.copy_(torch.tensor(rows, dtype=torch.int64))
-        self._table_dev.copy_(self._table, non_blocking=True)
-        self._grad_ptrs = ptrs
+        host = torch.tensor(rows, dtype=torch.int64).pin_memory()
+        devt = torch.empty(len(rows), device=self.params[0].device, dtype=torch.int64)
+        devt.copy_(host, non_blocking=True)
+        if len(self._tables) >= 64:          # gradient buffers keep moving (no graph, caching allocator churn)
+            self._tables.pop(next(iter(self._tables)))
+        self._tables[key] = (host, devt)
+        return devt
 
     @torch.no_grad()
     def step(self):
         L = _lib.lib()
-        self._refresh_table()
+        table = self._refresh_table()
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(L.coocc_adamw_step(ctypes.c_void_p(self._table_dev.data_ptr()), len(self.params),
+        _lib.check(L.coocc_adamw_step(ctypes.c_void_p(table.data_ptr()), len(self.params),
                                       ctypes.c_void_p(self.chunk_tensor.data_ptr()),
                                       ctypes.c_void_p(self.chunk_index.data_ptr()), self.chunk_tensor.numel(), CHUNK,
                                       float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),

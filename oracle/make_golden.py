@@ -42,7 +42,9 @@ def sub(prefix, p):
     return {k[len(prefix):]: v for k, v in p.items() if k.startswith(prefix)}
 
 
-def golden_for(name, ns):
+def golden_for(name, ns, full_indices=True):
+    """full_indices=False (the r50-size fixture, K=2 -- the benchmarked configuration): the [K,N] neighbour tables
+    are stored whole as well (they compress well), large float tensors as strided samples + sums."""
     cfg = S.CONFIGS[name]
     C, K = cfg["C"], cfg["K"]
     inp = S.make_inputs(name)
@@ -293,8 +295,20 @@ def golden_fine(ns):
     return g
 
 
+GOLDEN_CONFIGS = ("c1", "c1k1", "r50")      # r50: 100x100x8, C=128, K=2 = the reference's own working grid and knum
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
+    if only:                                 # e.g. `python -m oracle.make_golden r50`
+        ns = refshim.load_reference()
+        for name in only:
+            g = golden_for(name, ns)
+            path = os.path.join(OUT, "reference_%s.npz" % name)
+            np.savez_compressed(path, **g)
+            print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+        return
     gl2 = golden_lss()
     path = os.path.join(OUT, "reference_lss.npz")
     np.savez_compressed(path, **gl2)
@@ -312,7 +326,7 @@ def main():
     path = os.path.join(OUT, "reference_losses.npz")
     np.savez_compressed(path, **gl)
     print("losses ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
-    for name in ("c1", "c1k1"):
+    for name in GOLDEN_CONFIGS:
         g = golden_for(name, ns)
         path = os.path.join(OUT, "reference_%s.npz" % name)
         np.savez_compressed(path, **g)

@@ -43,10 +43,13 @@ def occupied_indices(feats):
 
 def _int_d2(a, b):
     """squared distances between integer coordinate sets a [M,3], b [N,3] -> int64 [M,N]."""
-    a = a.astype(np.int64)
-    b = b.astype(np.int64)
-    d = a[:, None, :] - b[None, :, :]
-    return (d * d).sum(-1)
+    a = a.astype(np.int32)          # voxel coordinates < 2^15: the squares fit int32, widened on return
+    b = b.astype(np.int32)
+    out = np.zeros((a.shape[0], b.shape[0]), dtype=np.int64)
+    for c in range(a.shape[1]):
+        d = a[:, None, c] - b[None, :, c]
+        out += d * d
+    return out
 
 
 def topk_canonical(d2, k):
@@ -93,18 +96,27 @@ def fps_nn_fast(query, key, num, fps_num=FPS_NUM, radius=BALL_RADIUS,
     qf = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32))[None]
     rep_idx = ops.furthest_point_sample(qf, fps_num)[0].numpy().astype(np.int64)   # :63 / :97
     rep = q[rep_idx]                                                               # :64 / :98
-    d2 = _int_d2(rep, k)                                                           # :67 / :101
-    if tie == "canonical":
-        sel, idx = topk_canonical(d2, num)
-        val = np.sqrt(sel.astype(np.float32))
-    else:
-        dist = torch.from_numpy(np.sqrt(d2.astype(np.float32)))
-        if num == 1:
-            v, i = dist.min(-1)                                                    # :68
-            val, idx = v[:, None].numpy(), i[:, None].numpy()
+    # :67 / :101 -- the reference materialises the whole [2048, Nk] distance matrix; the restatement walks it in
+    # row blocks (same values; ~64 M elements at a time so the north-star grid, Nk ~ 4e5, fits in memory)
+    rows = max(1, min(len(rep), (64 << 20) // max(len(k), 1)))
+    vals, idxs = [], []
+    for r0 in range(0, len(rep), rows):
+        d2 = _int_d2(rep[r0:r0 + rows], k)
+        if tie == "canonical":
+            sel, ix = topk_canonical(d2, num)
+            vals.append(np.sqrt(sel.astype(np.float32)))
+            idxs.append(ix)
         else:
-            v, i = torch.topk(dist, num, dim=-1, largest=False)                    # :103
-            val, idx = v.numpy(), i.numpy()
+            dist = torch.from_numpy(np.sqrt(d2.astype(np.float32)))
+            if num == 1:
+                v, i = dist.min(-1)                                                # :68
+                vals.append(v[:, None].numpy())
+                idxs.append(i[:, None].numpy())
+            else:
+                v, i = torch.topk(dist, num, dim=-1, largest=False)                # :103
+                vals.append(v.numpy())
+                idxs.append(i.numpy())
+    val, idx = np.concatenate(vals), np.concatenate(idxs)
     valid = val < thr                                                              # :69 / :107
     repf = torch.from_numpy(np.ascontiguousarray(rep, dtype=np.float32))[None]
     group = ops.ball_query(0, radius, max_cluster_samples, qf, repf)[0].numpy().astype(np.int64)  # :71 / :109

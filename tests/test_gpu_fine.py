@@ -1,24 +1,15 @@
-"""OccHead fine / cascade stage on the GPU (csrc/fine_stage.cu) against the pinned oracle and the reference fixture.
-
-NOT PART OF THE ROUND-1 GREEN SET: the kernels were written after the round's GPU budget was spent; their arithmetic
-is verified on the CPU (tests/test_fine_emul.py) but these launches have not run on a B200 yet, so the module is
-skipped unless COOCC_RUN_UNVERIFIED=1 (first thing to run next round)."""
-import os
-
+"""OccHead fine / cascade stage on the GPU (csrc/fine_stage.cu) against the pinned oracle and the reference fixture."""
 import numpy as np
 import pytest
 import torch
 
 import coocc_b200
-from coocc_b200 import modules as CM
 from coocc_b200 import synthetic as S
 from helpers import rel_l2
 from oracle import finestage as OF
 from oracle.make_golden import FINE_GRID, fine_head_params, fine_inputs
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("COOCC_RUN_UNVERIFIED") != "1",
-                                 reason="fine stage not yet validated on a B200; set COOCC_RUN_UNVERIFIED=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 PCR = [-10.0, -10.0, -5.0, 10.0, 10.0, 3.0]
 
@@ -35,7 +26,6 @@ def _head():
 def test_fine_stage_matches_reference_fixture_and_oracle(golden):
     g = golden("fine")
     coocc_b200.set_precision("fp32")
-    CM.FINE_STAGE["enabled"] = True
     try:
         feats, occ, img_feats, transform = fine_inputs()
         head = _head()
@@ -63,5 +53,4 @@ def test_fine_stage_matches_reference_fixture_and_oracle(golden):
         assert rel_l2(head.fine_mlp[3].weight.grad, p["fine_mlp.3.weight"].grad) < 1e-3
         assert rel_l2(head.img_mlp_0[0].weight.grad.reshape(128, 512), p["img_mlp_0.0.weight"].grad.reshape(128, 512)) < 1e-2
     finally:
-        CM.FINE_STAGE["enabled"] = False
         coocc_b200.set_precision("tf32")
