@@ -28,9 +28,13 @@ OUT = os.path.join(ROOT, "tests", "golden")
 STRIDE = 97      # sample stride for large float tensors
 
 
-def sample(t):
+def sample(t, stride=None):
     f = t.detach().reshape(-1)
-    return f[::STRIDE].numpy().astype(np.float32)
+    return f[::(stride or SAMPLE_STRIDE["cur"])].numpy().astype(np.float32)
+
+
+SAMPLE_STRIDE = {"cur": STRIDE}
+BIG_STRIDE = 1009       # r50-size tensors (10^7 elements): every 1009th element + the three sums
 
 
 def stats(t):
@@ -42,15 +46,18 @@ def sub(prefix, p):
     return {k[len(prefix):]: v for k, v in p.items() if k.startswith(prefix)}
 
 
-def golden_for(name, ns, full_indices=True):
-    """full_indices=False (the r50-size fixture, K=2 -- the benchmarked configuration): the [K,N] neighbour tables
-    are stored whole as well (they compress well), large float tensors as strided samples + sums."""
+def golden_for(name, ns):
+    """Fixture of one synthetic configuration.  The [K,N] neighbour tables are stored whole (also for the r50-size
+    fixture, K=2 -- the benchmarked configuration); large float tensors as strided samples + sums, the stride is
+    recorded under `stride`."""
     cfg = S.CONFIGS[name]
+    X, Y, Z = cfg["grid"]
+    SAMPLE_STRIDE["cur"] = BIG_STRIDE if X * Y * Z * cfg["C"] > (1 << 22) else STRIDE
     C, K = cfg["C"], cfg["K"]
     inp = S.make_inputs(name)
     P = S.make_params(name)
     torch.use_deterministic_algorithms(True)
-    g = {}
+    g = {"stride": np.int64(SAMPLE_STRIDE["cur"])}
     nc = dict(type="SyncBN", requires_grad=True)
 
     # ---- GSFusion (reference BiFuser_N, torch tie order) -----------------------------------

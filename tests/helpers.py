@@ -5,8 +5,10 @@ import torch
 STRIDE = 97   # must match oracle/make_golden.py
 
 
-def sample(t):
-    return t.detach().float().cpu().reshape(-1)[::STRIDE].numpy()
+def sample(t, g=None):
+    """strided sample of a tensor; `g` = the fixture it is compared with (its `stride` entry, default STRIDE)."""
+    stride = int(g["stride"]) if (g is not None and "stride" in getattr(g, "files", g)) else STRIDE
+    return t.detach().float().cpu().reshape(-1)[::stride].numpy()
 
 
 def stats(t):
