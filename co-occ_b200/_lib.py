@@ -92,6 +92,11 @@ _SIGS = {
     "coocc_fine_sample2d_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_groupnorm_fwd": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_ll, c_void_p]),
     "coocc_groupnorm_bwd": (c_int, [c_void_p, c_ll, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
+    "coocc_fine_select_workspace": (c_ll, [c_int]),
+    "coocc_fine_select": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "coocc_fine_gather_labels": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p]),
     "coocc_adamw_step": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p, c_int, c_void_p]),
 }
 

@@ -63,6 +63,8 @@ def _raise_if_set(flag, exc):
 
 
 def _timed(tag, flops, fn, info=""):
+    """Run one C-ABI launch; when bench.py has set PROFILE, bracket it with CUDA events.  `flops` is the launch's
+    algorithmic work: FLOPs for the tensor-core kernels, BYTES for tags starting with "hbm:"."""
     if PROFILE is None:
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -323,9 +325,12 @@ class _BNActFn(torch.autograd.Function):
         if residual is not None:
             res_dtype = residual.dtype
             residual = _as_rows(residual, x.dtype)
-        _lib.check(L.coocc_bn_act_fwd(_p(x), x.stride(0), V, C, _p(mi), _p(gamma), _p(beta), _p(residual),
-                                      residual.stride(0) if residual is not None else 0, 1 if relu else 0,
-                                      _p(out), out.stride(0), _is_bf16(x), _stream()), "bn_act_fwd")
+        e = x.element_size()
+        _lib.check(_timed("hbm:bn_act_fwd", float(e * V * C * (3 if residual is not None else 2)),
+                          lambda: L.coocc_bn_act_fwd(_p(x), x.stride(0), V, C, _p(mi), _p(gamma), _p(beta), _p(residual),
+                                                     residual.stride(0) if residual is not None else 0,
+                                                     1 if relu else 0, _p(out), out.stride(0), _is_bf16(x), _stream())),
+                   "bn_act_fwd")
         # the backward needs the ReLU mask: with a residual it reads it from `out`, otherwise it recomputes
         # y > 0 from x, gamma, beta (the forward's own expression) and `out` is not read again
         ctx.save_for_backward(x, out if (relu and residual is not None) else None, mi, gamma, beta)
@@ -342,9 +347,11 @@ class _BNActFn(torch.autograd.Function):
         bf = _is_bf16(x)
         sums = torch.zeros(2, C, device=x.device, dtype=torch.float32)
         ldo = out.stride(0) if out is not None else 0
-        _lib.check(L.coocc_bn_act_bwd_reduce(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C,
-                                             _p(mi), _p(gamma), _p(beta), 1 if relu else 0, _p(sums), bf, _stream()),
-                   "bn_act_bwd_reduce")
+        e = x.element_size()
+        _lib.check(_timed("hbm:bn_act_bwd_reduce", float(e * V * C * (3 if out is not None else 2)),
+                          lambda: L.coocc_bn_act_bwd_reduce(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V,
+                                                            C, _p(mi), _p(gamma), _p(beta), 1 if relu else 0, _p(sums),
+                                                            bf, _stream())), "bn_act_bwd_reduce")
         local = sums
         if count != V:                      # SyncBN: batch terms use the sums over all ranks
             dist = _sync_group()
@@ -352,10 +359,11 @@ class _BNActFn(torch.autograd.Function):
             dist.all_reduce(sums)
         dx = torch.empty(V, C, device=x.device, dtype=x.dtype)
         dres = torch.empty(V, C, device=x.device, dtype=x.dtype) if has_res else None
-        _lib.check(L.coocc_bn_act_bwd_apply(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C, _p(mi),
-                                            _p(gamma), _p(beta), 1 if relu else 0, _p(sums), count, _p(dx),
-                                            dx.stride(0), bf, _p(dres), C if has_res else 0, _stream()),
-                   "bn_act_bwd_apply")
+        _lib.check(_timed("hbm:bn_act_bwd_apply", float(e * V * C * (5 if has_res else 3)),
+                          lambda: L.coocc_bn_act_bwd_apply(_p(dout), dout.stride(0), _p(out), ldo, _p(x), x.stride(0), V, C,
+                                                           _p(mi), _p(gamma), _p(beta), 1 if relu else 0, _p(sums), count,
+                                                           _p(dx), dx.stride(0), bf, _p(dres), C if has_res else 0,
+                                                           _stream())), "bn_act_bwd_apply")
         if has_res and dres.dtype != res_dtype:
             dres = dres.to(res_dtype)
         return dx, None, local[1], local[0], dres, None, None, None, None, None
@@ -572,8 +580,10 @@ def gsf_prologue(img5d, pts5d, out=None):
     cat, flags, lists, ranks, counts, ws = (out[k] for k in ("cat", "flags", "lists", "ranks", "counts", "ws"))
     for i, t in enumerate((img5d, pts5d)):
         sB, sC, sX, sY, sZ = t.stride()
-        _lib.check(L.coocc_gsf_pack(_p(t), sC, sX, sY, sZ, C, X, Y, Z, _pb(cat, i * C * 4), 4 * C,
-                                    _p(flags[i]), st), "gsf_pack")
+        _lib.check(_timed("hbm:gsf_pack", float(8 * V * C + V),
+                          lambda t=t, i=i, sC=sC, sX=sX, sY=sY, sZ=sZ: L.coocc_gsf_pack(
+                              _p(t), sC, sX, sY, sZ, C, X, Y, Z, _pb(cat, i * C * 4), 4 * C, _p(flags[i]), st)),
+                   "gsf_pack")
         _lib.check(L.coocc_gsf_compact(_p(flags[i]), V, _p(lists[i]), _p(ranks[i]), _pb(counts, 4 * i),
                                        _p(ws), st), "gsf_compact")
     return out
@@ -970,9 +980,52 @@ def eval_confusion(logits2d, dims, gt, visible_mask=None, empty_idx=0, ignore=25
 
 
 # ----------------------------------------------------------------------------------------
-# OccHead fine / cascade stage (occ_head.py:182-237) -- csrc/fine_stage.cu.
-# Arithmetic verified on the CPU (tests/test_fine_emul.py); not yet run on a B200.
+# OccHead fine / cascade stage (occ_head.py:182-237) -- csrc/fine_stage.cu, csrc/fine_select.cu.
 # ----------------------------------------------------------------------------------------
+def fine_select(logits2d, dims, empty_idx, ratio, topk, state):
+    """Device-side replacement of `argmax != empty` -> nonzero -> random subset of `topk` parents -> ratio^3 children
+    (occ_head.py:183-205, coordinate_transform.py:3-21) with no host synchronisation (csrc/fine_select.cu).
+    logits2d [V,C] fp32 rows of the coarse prediction; state int64[2] on the device (seed, draw counter).
+    Returns (coords int32 [3, ratio^3*topk], nsel int32 [2] = (N occupied, P = min(N, topk))); child slot o*topk + j
+    belongs to parent slot j, slots j >= P are padding (coordinates 0)."""
+    L = _lib.lib()
+    _require_cuda(logits2d, state)
+    x = _as_rows(logits2d.float() if logits2d.dtype != torch.float32 else logits2d)
+    V, C = x.shape
+    X, Y, Z = dims
+    assert V == X * Y * Z and state.dtype == torch.int64 and state.numel() == 2
+    M = ratio ** 3 * int(topk)
+    coords = torch.empty(3, M, device=x.device, dtype=torch.int32)
+    nsel = torch.empty(2, device=x.device, dtype=torch.int32)
+    ws = torch.empty(int(L.coocc_fine_select_workspace(V)), device=x.device, dtype=torch.uint8)
+    _lib.check(L.coocc_fine_select(_p(x), x.stride(0), X, Y, Z, C, int(empty_idx), int(ratio), int(topk), _p(state),
+                                   _p(coords), _p(nsel), _p(ws), _stream()), "fine_select")
+    return coords, nsel
+
+
+def fine_gather_labels(coords, topk, nsel, target_voxels, ignore=255):
+    """target_voxels[:, c0, c1, c2] (occ_head.py:298) as int32 [M]; padding slots of fine_select get `ignore`."""
+    L = _lib.lib()
+    _require_cuda(coords, target_voxels)
+    assert coords.dtype == torch.int32 and coords.is_contiguous() and target_voxels.shape[0] == 1
+    if target_voxels.dtype not in (torch.uint8, torch.int32, torch.int64):
+        target_voxels = target_voxels.long()
+    g = target_voxels.contiguous()
+    M = coords.shape[1]
+    labels = torch.empty(M, device=coords.device, dtype=torch.int32)
+    _lib.check(L.coocc_fine_gather_labels(_p(coords), M, int(topk), _p(nsel), _p(g), g.element_size(), g.shape[1],
+                                          g.shape[2], g.shape[3], int(ignore), _p(labels), _stream()),
+               "fine_gather_labels")
+    return labels
+
+
+def _inv3x3(m):
+    """closed-form inverse of [...,3,3] matrices from elementwise ops (torch.inverse goes through a solver library
+    that may synchronise; this form can be captured in a CUDA graph)."""
+    a, b, c = m[..., 0, :], m[..., 1, :], m[..., 2, :]
+    r0, r1, r2 = torch.linalg.cross(b, c), torch.linalg.cross(c, a), torch.linalg.cross(a, b)
+    det = (a * r0).sum(-1)
+    return torch.stack([r0, r1, r2], -1) / det[..., None, None]
 class _Sample3dFn(torch.autograd.Function):
     """feats [V,C] fp32 NDHWC rows, coords int32 [3,M] fine voxel indices -> [M,C] trilinear samples (:212-221)."""
 
@@ -1019,9 +1072,10 @@ def fine_project(coords, rots, trans, intrins, post_rots, post_trans, bda, pts_r
         n = rots.shape[0]
         pr = pts_range.detach().float().cpu()
         vs = (pr[3:] - pr[:3]) / torch.tensor([grid_fine[0] - 1, grid_fine[1] - 1, grid_fine[2] - 1])      # :33
-        cam = torch.cat([rots.inverse().reshape(n, 9), trans.reshape(n, 3), intrins.reshape(n, 9),
+        inv = _inv3x3 if torch.cuda.is_current_stream_capturing() else torch.inverse
+        cam = torch.cat([inv(rots.float()).reshape(n, 9), trans.reshape(n, 3), intrins.reshape(n, 9),
                          post_rots[:, :2, :2].reshape(n, 4), post_trans[:, :2].reshape(n, 2)], 1).float().contiguous()
-        inv_bda = bda.inverse().float().contiguous()
+        inv_bda = inv(bda.float()).contiguous()
         coords = coords.to(torch.int32).contiguous()
         M = coords.shape[1]
         uv = torch.empty(n, M, 2, device=coords.device, dtype=torch.float32)

@@ -56,18 +56,19 @@ class GraphedStep:
         self._stream = None         # capture stream; the warm-up step runs on it too, so that autograd's
         self._warm = False
         self._last = None           # AccumulateGrad nodes live on the stream the capture uses
+        self._tr_fixed, self._tr_len = None, 0
 
     # ------------------------------------------------------------------------------------
     def _loss(self, losses):
         keys = self.loss_keys if self.loss_keys is not None else list(losses)
         return sum(losses[k] for k in keys)
 
-    def _eager(self, img, pts, geom, gt_depth, gt_img, gt_occ):
+    def _eager(self, img, pts, geom, gt_depth, gt_img, gt_occ, img_feats=None, transform=None):
         if self.opt is not None:
             self.opt.zero_grad(set_to_none=True)
         else:
             self.model.zero_grad(set_to_none=True)
-        losses, _, _ = self.model.forward_train(img, pts, geom, gt_depth, gt_img, gt_occ)
+        losses, _, _ = self.model.forward_train(img, pts, geom, gt_depth, gt_img, gt_occ, img_feats, transform)
         loss = self._loss(losses)
         loss.backward()
         if self.reducer is not None:
@@ -79,8 +80,21 @@ class GraphedStep:
     def _round(self, n, cap):
         return min(cap, (n + self.bucket - 1) // self.bucket * self.bucket)
 
-    def _bind_static(self, geom, gt_depth, gt_img, gt_occ):
-        new = dict(geom=geom, gt_depth=gt_depth, gt_img=gt_img, gt_occ=gt_occ)
+    def _bind_static(self, geom, gt_depth, gt_img, gt_occ, img_feats=None, transform=None):
+        new = dict(geom=geom, gt_depth=gt_depth, gt_img=gt_img, gt_occ=gt_occ, img_feats=img_feats)
+        # transform = img_inputs[1:]: the calibration tensors get fixed-address copies, everything else (None
+        # placeholders, the (H, W) image size -- read on the host) is passed through as python values
+        tr_fixed = None
+        if transform is not None:
+            for i, t in enumerate(transform):
+                if torch.is_tensor(t) and t.is_cuda:
+                    new["tr%d" % i] = t
+            size = transform[-1]
+            tr_fixed = tuple(float(v[0]) if hasattr(v, "__getitem__") else float(v) for v in size)
+        if self.static is not None and self._tr_fixed != tr_fixed:
+            raise RuntimeError("GraphedStep: image size changed; build a new GraphedStep")
+        self._tr_fixed = tr_fixed
+        self._tr_len = len(transform) if transform is not None else 0
         if self.static is None:
             self.static = {k: (v.clone() if v is not None else None) for k, v in new.items()}
             return
@@ -92,10 +106,18 @@ class GraphedStep:
                 s.copy_(v, non_blocking=True)
 
     # ------------------------------------------------------------------------------------
-    def __call__(self, img, pts, geom, gt_depth, gt_img, gt_occ=None):
+    def _static_transform(self):
+        if not self._tr_len:
+            return None
+        tr = [self.static.get("tr%d" % i) for i in range(self._tr_len)]
+        tr[-1] = self._tr_fixed
+        return tuple(tr)
+
+    def __call__(self, img, pts, geom, gt_depth, gt_img, gt_occ=None, img_feats=None, transform=None):
+        args = (img, pts, geom, gt_depth, gt_img, gt_occ, img_feats, transform)
         if not self.enabled:
             self.stats["eager"] += 1
-            return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+            return self._eager(*args)
         K = self.model.occ_fuser.knum
         # optimizer state must exist before a capture (lazy state init allocates and syncs)
         if self._stream is None:
@@ -109,7 +131,7 @@ class GraphedStep:
             cur = torch.cuda.current_stream()
             self._stream.wait_stream(cur)
             with torch.cuda.stream(self._stream):
-                loss = self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+                loss = self._eager(*args)
             cur.wait_stream(self._stream)
             return loss
         self.prologue = CF.gsf_prologue(img, pts, out=self.prologue)
@@ -120,16 +142,16 @@ class GraphedStep:
                    and (K > 1 or self.model.occ_fuser.fix_k1_fps))
         if not covered:
             self.stats["eager"] += 1
-            return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+            return self._eager(*args)
         nb_img, nb_pts = self._round(n_img, V), self._round(n_pts, V)
         key = (nb_img, nb_pts)
-        self._bind_static(geom, gt_depth, gt_img, gt_occ)
+        self._bind_static(geom, gt_depth, gt_img, gt_occ, img_feats, transform)
         ov = dict(prologue=self.prologue, n_img=n_img, n_pts=n_pts, nb_img=nb_img, nb_pts=nb_pts)
         entry = self.graphs.get(key)
         if entry is None:
             if len(self.graphs) >= self.max_graphs:
                 self.stats["eager"] += 1
-                return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+                return self._eager(*args)
             try:
                 entry = self._capture(key, ov, img, pts)
             except Exception as e:  # noqa: BLE001 -- a failed capture must not take the training run down
@@ -139,7 +161,7 @@ class GraphedStep:
                 _dbg("capture failed, falling back to eager: " + self.capture_error)
                 torch.cuda.synchronize()
                 self.stats["eager"] += 1
-                return self._eager(img, pts, geom, gt_depth, gt_img, gt_occ)
+                return self._eager(*args)
         entry["graph"].replay()
         self.stats["replays"] += 1
         if self.stats["replays"] <= 2 and os.environ.get("COOCC_DEBUG"):
@@ -173,7 +195,8 @@ class GraphedStep:
             _dbg("capture begin key=%s" % (key,))
             # thread_local: NCCL's watchdog / heartbeat threads query events while this thread captures
             with torch.cuda.graph(g, stream=self._stream, capture_error_mode="thread_local"):
-                losses, _, _ = self.model.forward_train(img, pts, s["geom"], s["gt_depth"], s["gt_img"], s["gt_occ"])
+                losses, _, _ = self.model.forward_train(img, pts, s["geom"], s["gt_depth"], s["gt_img"], s["gt_occ"],
+                                                        s["img_feats"], self._static_transform())
                 loss = self._loss(losses)
                 loss.backward()
                 if self.reducer is not None:

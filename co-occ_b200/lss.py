@@ -166,6 +166,17 @@ def get_geometry(frustum, rots, trans, intrins, post_rots, post_trans, bda):
     return geom
 
 
+def create_frustum(input_size, dbound, downsample=16):
+    """ViewTransformerLSSBEVDepth.py:103-115 / get_frustum of coocc_ray.py:738-748: [D, fH, fW, 3] (u, v, depth)."""
+    ogfH, ogfW = input_size
+    fH, fW = ogfH // downsample, ogfW // downsample
+    ds = torch.arange(*dbound, dtype=torch.float).view(-1, 1, 1).expand(-1, fH, fW)
+    D = ds.shape[0]
+    xs = torch.linspace(0, ogfW - 1, fW, dtype=torch.float).view(1, 1, fW).expand(D, fH, fW)
+    ys = torch.linspace(0, ogfH - 1, fH, dtype=torch.float).view(1, fH, 1).expand(D, fH, fW)
+    return torch.stack((xs, ys, ds), -1)
+
+
 class LSSVoxelPool(nn.Module):
     """The geometry / splat half of ViewTransformerLiftSplatShootVoxel: same grid_config / data_config /
     downsample constructor fields, buffers dx / bx / nx / frustum, and the methods create_frustum,
@@ -183,13 +194,8 @@ class LSSVoxelPool(nn.Module):
         self.spec = GridSpec(dx=dx, bx=bx, nx=nx)
 
     def create_frustum(self):          # ViewTransformerLSSBEVDepth.py:103-115
-        ogfH, ogfW = self.data_config['input_size']
-        fH, fW = ogfH // self.downsample, ogfW // self.downsample
-        ds = torch.arange(*self.grid_config['dbound'], dtype=torch.float).view(-1, 1, 1).expand(-1, fH, fW)
-        D = ds.shape[0]
-        xs = torch.linspace(0, ogfW - 1, fW, dtype=torch.float).view(1, 1, fW).expand(D, fH, fW)
-        ys = torch.linspace(0, ogfH - 1, fH, dtype=torch.float).view(1, fH, 1).expand(D, fH, fW)
-        return nn.Parameter(torch.stack((xs, ys, ds), -1), requires_grad=False)
+        return nn.Parameter(create_frustum(self.data_config['input_size'], self.grid_config['dbound'], self.downsample),
+                            requires_grad=False)
 
     def get_geometry(self, rots, trans, intrins, post_rots, post_trans, bda):
         return get_geometry(self.frustum, rots, trans, intrins, post_rots, post_trans, bda)

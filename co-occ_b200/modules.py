@@ -293,6 +293,9 @@ class OccHead(nn.Module):
         # fine / cascade stage (occ_head.py:58-82): parameter containers with the reference's names and shapes
         self.point_cloud_range = torch.tensor(point_cloud_range).float()
         self.fine_stage = cascade_ratio != 1 and (sample_from_voxel or sample_from_img)
+        self.fine_select = "auto"          # see forward_fine
+        # (seed, draw counter) of the device-side subset selection; not part of the reference's state_dict
+        self.register_buffer("fine_rng_state", torch.tensor([0x5EED5EED, 0], dtype=torch.int64), persistent=False)
         if self.fine_stage:
             fine_in = 128 if sample_from_voxel else 0
             if sample_from_img:
@@ -345,9 +348,16 @@ class OccHead(nn.Module):
                 'loss_voxel_lovasz_{}'.format(tag): self.loss_voxel_lovasz_weight * l4[3]}
 
     def loss_point(self, fine_coord, fine_output, target_voxels, tag):
-        """occ_head.py:295-312: the four voxel losses on the sampled points (CE without class weights, :305)."""
-        gt = target_voxels[:, fine_coord[0, :], fine_coord[1, :], fine_coord[2, :]].long()[0]
-        l4 = CF.occ_voxel_losses(fine_output, gt.to(torch.int32).contiguous(), None, 255, self.empty_idx)
+        """occ_head.py:295-312: the four voxel losses on the sampled points (CE without class weights, :305).
+        Coordinates from the device-side selection carry their padding count (`_coocc_nsel`): padding slots get
+        label 255, which all four losses ignore."""
+        nsel = getattr(fine_coord, "_coocc_nsel", None)
+        if nsel is not None:
+            gt = CF.fine_gather_labels(fine_coord, fine_coord._coocc_topk, nsel, target_voxels, 255)
+        else:
+            gt = target_voxels[:, fine_coord[0, :], fine_coord[1, :], fine_coord[2, :]].long()[0]
+            gt = gt.to(torch.int32).contiguous()
+        l4 = CF.occ_voxel_losses(fine_output, gt, None, 255, self.empty_idx)
         return {'loss_voxel_ce_{}'.format(tag): self.loss_voxel_ce_weight * l4[0],
                 'loss_voxel_sem_scal_{}'.format(tag): self.loss_voxel_sem_scal_weight * l4[1],
                 'loss_voxel_geo_scal_{}'.format(tag): self.loss_voxel_geo_scal_weight * l4[2],
@@ -370,13 +380,8 @@ class OccHead(nn.Module):
             raise NotImplementedError("OccHead lidarseg losses are outside the hot path (SURVEY §8f)")
         return loss_dict
 
-    def forward_fine(self, out_voxel_feats, coarse_occ, img_feats, transform):
-        """occ_head.py:182-237 for B = 1: occupied coarse voxels -> their cascade_ratio^3 children (a random subset of
-        fine_topk parents in training, coordinate_transform.py:19-21) -> trilinear sample of out_voxel_feats,
-        camera projection + bilinear sample of the image features (img_mlp_0, masked camera sum, img_mlp),
-        fine_mlp -> per-point logits.  Sampling / projection / GroupNorm run in csrc/fine_stage.cu, the Linear
-        layers on the tensor-core conv kernel.  Returns (fine_coord [3,M] int64, fine_output [M, out_channel])."""
-        x2d, dims = CF.to_cl2d(out_voxel_feats)
+    def _select_host(self, coarse_occ):
+        """occ_head.py:183-205 as written: host synchronisation (nonzero) and torch's CPU generator (randperm)."""
         mask = coarse_occ.argmax(1) != self.empty_idx                                           # :183
         if int(mask.sum()) == 0:
             raise AssertionError('no foreground in coarse voxel')                               # :184
@@ -387,7 +392,37 @@ class OccHead(nn.Module):
         fine = coarse[None] * r + off[:, :, None]                                               # [r^3,3,N]
         if fine.shape[-1] >= topk:
             fine = fine[:, :, torch.randperm(fine.shape[-1])[:topk].to(fine.device)]            # CPU generator like the reference
-        fine = fine.permute(1, 0, 2).reshape(3, -1)
+        return fine.permute(1, 0, 2).reshape(3, -1)
+
+    def _select_device(self, coarse_occ):
+        """Same selection without leaving the device (csrc/fine_select.cu): fixed-capacity buffers of fine_topk
+        parents, a keyed pseudo-random subset instead of torch.randperm, padding slots flagged through `_coocc_nsel`."""
+        x2d, dims = CF.to_cl2d(coarse_occ)
+        topk = self.fine_topk if self.training else 30000
+        topk = min(int(topk), dims[0] * dims[1] * dims[2])
+        if self.fine_rng_state.device != x2d.device:
+            self.fine_rng_state = self.fine_rng_state.to(x2d.device)
+        coords, nsel = CF.fine_select(x2d, dims, self.empty_idx, self.cascade_ratio, topk, self.fine_rng_state)
+        coords._coocc_nsel, coords._coocc_topk = nsel, topk
+        return coords
+
+    def forward_fine(self, out_voxel_feats, coarse_occ, img_feats, transform):
+        """occ_head.py:182-237 for B = 1: occupied coarse voxels -> their cascade_ratio^3 children (a random subset of
+        fine_topk parents in training, coordinate_transform.py:19-21) -> trilinear sample of out_voxel_feats,
+        camera projection + bilinear sample of the image features (img_mlp_0, masked camera sum, img_mlp),
+        fine_mlp -> per-point logits.  Sampling / projection / GroupNorm run in csrc/fine_stage.cu, the Linear
+        layers on the tensor-core conv kernel.  Returns (fine_coord [3,M], fine_output [M, out_channel]).
+
+        `self.fine_select`: "host" = the reference's own draw (nonzero + torch.randperm: one host synchronisation, the
+        coordinates are bit-identical to the reference's under the same torch seed); "device" = csrc/fine_select.cu
+        (no synchronisation, CUDA-graph capturable, a different but equally distributed subset); "auto" = device
+        while a CUDA graph is being captured or replayed by GraphedStep, host otherwise."""
+        x2d, dims = CF.to_cl2d(out_voxel_feats)
+        r = self.cascade_ratio
+        mode = self.fine_select
+        if mode == "auto":
+            mode = "device" if (CF.GSF_OVERRIDE is not None or torch.cuda.is_current_stream_capturing()) else "host"
+        fine = self._select_device(coarse_occ) if mode == "device" else self._select_host(coarse_occ)
         feats = []
         if self.sample_from_voxel:
             feats.append(CF.fine_sample_voxels(x2d, dims, fine, self.final_occ_size))
@@ -399,9 +434,12 @@ class OccHead(nn.Module):
             rows = CF.linear(rows, c0.weight.reshape(c0.out_channels, Ci), c0.bias)
             rows = CF.group_norm_rows(rows, self.img_mlp_0[1], span=Hf * Wf, relu=True)
             X, Y, Z = dims
+            W_img, H_img = transform[-1][1], transform[-1][0]        # img_size = (H, W), per-sample entries
+            W_img = float(W_img[0]) if hasattr(W_img, "__getitem__") else float(W_img)
+            H_img = float(H_img[0]) if hasattr(H_img, "__getitem__") else float(H_img)
             uv, m = CF.fine_project(fine, transform[0][0], transform[1][0], transform[2][0], transform[3][0],
                                     transform[4][0], transform[5][0], self.point_cloud_range,
-                                    float(transform[-1][1][0]), float(transform[-1][0][0]), (X * r, Y * r, Z * r))
+                                    W_img, H_img, (X * r, Y * r, Z * r))
             s = CF.fine_sample_images(rows, n, Hf, Wf, uv, m)
             s = CF.linear(s, self.img_mlp[0].weight, self.img_mlp[0].bias)
             feats.append(CF.group_norm_rows(s, self.img_mlp[1], span=1, relu=True))
@@ -463,19 +501,41 @@ class MLP(nn.Module):
 
 
 def render_fn(voxel_feats, gemo, sigma_head, rgb_head, gt_depth, gt_img):
-    """The inline render block of COOCC_Ray.forward_train (coocc_ray.py:358-433).
+    """The inline render block of COOCC_Ray.forward_train (coocc_ray.py:358-433) and its test-time copy (:562-637).
 
     voxel_feats [1,C,X,Y,Z] (fuser output), gemo [1,N,D,H,W,3], gt_depth = img_inputs[7] [1,N,16H,16W],
-    gt_img = img_inputs[0] [1,N,3,16H,16W].  Returns (rgbs [N,16H,16W,3], depths [N,16H,16W], losses dict).
+    gt_img = img_inputs[0] [1,N,3,16H,16W] (both None at test time: maps only, empty loss dict).
+    Returns (rgbs [N,16H,16W,3], depths [N,16H,16W], losses dict).
     The heads run once per voxel of the render box, not once per sample (identical values).
+    rgb_head None = the LiDAR-only detector (coocc_ray.py:435-494): density head only, colour columns zero.
     """
     B, N, D, H, W, _ = gemo.shape
     assert B == 1
     x2d, dims = CF.to_cl2d(voxel_feats)
     rows = CF.box_rows(x2d.float(), dims)       # (bf16 activations: the render box is gathered in fp32)
-    rgb_raw = rgb_head.forward_rows(rows)                       # [T,3]
     sigma = sigma_head.forward_rows(rows, relu_out=True)        # [T,1] = relu(sigma_head(f))
+    if rgb_head is not None:
+        rgb_raw = rgb_head.forward_rows(rows)                   # [T,3]
+    else:
+        rgb_raw = torch.zeros(sigma.shape[0], 3, device=sigma.device, dtype=sigma.dtype)
     tab = torch.cat([rgb_raw, sigma], dim=1)                    # [T,4]
     rgb_map, depth_map = CF.composite(tab, gemo[0], dims)
+    want_loss = gt_depth is not None
+    if gt_depth is None:
+        gt_depth = torch.zeros(1, N, 16 * H, 16 * W, device=tab.device)
+    if gt_img is None:
+        gt_img = torch.zeros(1, N, 3, 16 * H, 16 * W, device=tab.device)
     losses2, rgbs, depths = CF.upsample_losses(rgb_map, depth_map, gt_img[0], gt_depth[0], D)
-    return rgbs, depths, {"loss_depth_render": losses2[0], "loss_rgb": losses2[1]}
+    losses = {}
+    if want_loss:
+        losses["loss_depth_render"] = losses2[0]
+        if rgb_head is not None:
+            losses["loss_rgb"] = losses2[1]
+    return rgbs, depths, losses
+
+
+def render_depth_fn(voxel_feats, gemo, sigma_head, gt_depth):
+    """LiDAR-only render branch (coocc_ray.py:435-494, COOCC_Ray_L): depth maps and loss_depth_render from the
+    density head alone.  Returns (depths [N,16H,16W], {"loss_depth_render": ...})."""
+    _, depths, losses = render_fn(voxel_feats, gemo, sigma_head, None, gt_depth, None)
+    return depths, losses

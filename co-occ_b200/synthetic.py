@@ -148,6 +148,22 @@ def make_camera_rig(cams=6, seed=0, in_h=256, in_w=704):
     return dict(rots=st(rots), trans=st(trans), intrins=st(intr), post_rots=st(prot), post_trans=st(ptr), bda=bda[None])
 
 
+def make_img_feats(cams, fH, fW, seed=0, channels=512):
+    """img_feats[0] of extract_img_feat (coocc_ray.py:164-197): the SECONDFPN output [1,N,512,fH,fW] the OccHead fine
+    stage samples (occ_head.py:199-203)."""
+    g = _gen(seed + 1299709)
+    return torch.randn(1, cams, channels, fH, fW, generator=g) * 0.5
+
+
+def make_transform(cams, fH, fW, seed=0):
+    """`transform = img_inputs[1:]` (coocc_ray.py:348): (rots, trans, intrins, post_rots, post_trans, bda, gt_depths,
+    sensor2sensors, denorm_imgs, aabb, intrin_nerf, c2ws, img_size) -- the head reads entries 0-5 and the last one
+    (img_size = (H, W) per sample, occ_head.py:222-227); the others are placeholders here."""
+    rig = make_camera_rig(cams, seed, in_h=16 * fH, in_w=16 * fW)
+    return (rig["rots"], rig["trans"], rig["intrins"], rig["post_rots"], rig["post_trans"], rig["bda"],
+            None, None, None, None, None, None, (torch.tensor([16 * fH]), torch.tensor([16 * fW])))
+
+
 def make_inputs(name, seed=0, with_render=True):
     cfg = CONFIGS[name]
     img, pts = make_voxel_feats(cfg["grid"], cfg["C"], cfg["p_img"], cfg["p_pts"], seed,
@@ -257,6 +273,20 @@ def render_params(C, width=256, seed=0):
     for h in ("sigma_head", "rgb_head"):
         p[h + ".posi_encoder.scales"] = torch.tensor([2 ** i for i in range(10)])   # nerf_mlp.py:188-190 (Q8)
     return p
+
+
+def fine_head_params(seed=0):
+    """State-dict entries of the OccHead fine / cascade stage (occ_head.py:58-82) with the reference's hard-wired
+    layer shapes (512 -> 128 image conv, 128 -> 64, 192 -> 64 -> 17)."""
+    g = torch.Generator().manual_seed(seed + 71)
+    r = lambda *s: torch.randn(*s, generator=g)
+    return {"img_mlp_0.0.weight": r(128, 512, 1, 1) * 0.04, "img_mlp_0.0.bias": r(128) * 0.1,
+            "img_mlp_0.1.weight": 1 + 0.1 * r(128), "img_mlp_0.1.bias": 0.1 * r(128),
+            "img_mlp.0.weight": r(64, 128) * 0.09, "img_mlp.0.bias": r(64) * 0.1,
+            "img_mlp.1.weight": 1 + 0.1 * r(64), "img_mlp.1.bias": 0.1 * r(64),
+            "fine_mlp.0.weight": r(64, 192) * 0.07, "fine_mlp.0.bias": r(64) * 0.1,
+            "fine_mlp.1.weight": 1 + 0.1 * r(64), "fine_mlp.1.bias": 0.1 * r(64),
+            "fine_mlp.3.weight": r(17, 64) * 0.12, "fine_mlp.3.bias": r(17) * 0.1}
 
 
 def make_params(name, seed=0):

@@ -233,8 +233,8 @@ int coocc_lss_pool_bwd(const unsigned int* point_keys, long long npts, int V, in
  * Replaces, in P/coocc/dense_heads/occ_head.py:182-237, the 5-D F.grid_sample of out_voxel_feats (:219), the
  * camera projection project_points_on_img (P/utils/coordinate_transform.py:29-70), the 4-D F.grid_sample of the
  * image features with the masked camera sum (:231-233) and nn.GroupNorm(16) + ReLU of img_mlp_0 / img_mlp /
- * fine_mlp (:58-78).  All fp32.  NOT YET RUN ON A GPU: arithmetic verified on the CPU through
- * tests/emul/fine_emul.cpp only.
+ * fine_mlp (:58-78).  All fp32.  Verified on the CPU (tests/emul/fine_emul.cpp) and on a B200 against the reference
+ * fixture (tests/test_gpu_fine.py).
  * ------------------------------------------------------------------------------------------ */
 /* feats [X*Y*Z][ld] NDHWC rows; coords int32 [3][M] fine voxel indices; S* = final_occ_size; out [M][ldo]:
  * trilinear sample at grid = (c/(S-1) - 0.5)*2, zeros padding, align_corners=False. */
@@ -261,11 +261,25 @@ int coocc_groupnorm_bwd(const float* x, long long ldx, long long rows, int C, in
                         const float* beta, int relu, const float* stats, const float* dy, long long lddy, float* sums,
                         float* dx, long long lddx, float* dgamma, float* dbeta, void* stream);
 
+/* Device-side point selection (csrc/fine_select.cu), replacing `argmax != empty` + torch.nonzero + the host
+ * torch.randperm subset of coarse_to_fine_coordinates (occ_head.py:183-205, P/utils/coordinate_transform.py:3-21)
+ * without a host round trip (CUDA-graph capturable).  logits [X*Y*Z][ld] fp32 coarse prediction; state = device
+ * uint64[2] (seed, draw counter; the call increments the counter); coords int32 [3][ratio^3 * topk], child slot
+ * o * topk + j of parent slot j; nsel = device int32[2] <- (N occupied, P = min(N, topk)); slots j >= P are padding
+ * (coordinates 0).  workspace: coocc_fine_select_workspace(X*Y*Z) bytes. */
+long long coocc_fine_select_workspace(int V);
+int coocc_fine_select(const float* logits, long long ld, int X, int Y, int Z, int C, int empty_idx, int ratio,
+                      int topk, unsigned long long* state, int* coords, int* nsel, void* workspace, void* stream);
+/* labels[i] = gt[coords[:, i]] (gt = [GX][GY][GZ] integers of gt_bytes = 1, 4 or 8 bytes: occ_head.py:298), `ignore`
+ * for the padding slots (parent slot i % topk >= nsel[1]); nsel == NULL: every slot valid. */
+int coocc_fine_gather_labels(const int* coords, long long M, int topk, const int* nsel, const void* gt, int gt_bytes,
+                             int GX, int GY, int GZ, int ignore, int* labels, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Multi-tensor AdamW step that also writes the bf16 operand copy of every parameter (csrc/adamw.cu, body in
  * csrc/adamw.cuh).  Replaces torch.optim.AdamW (the reference's optimizer, coocc_multi_r50_256x704.py:283-290) plus
- * the per-step fp32 -> bf16 weight conversions of the bf16 mode.  NOT YET RUN ON A GPU; arithmetic
- * verified on the CPU against torch.optim.AdamW (tests/test_adamw_emul.py).
+ * the per-step fp32 -> bf16 weight conversions of the bf16 mode.  Verified against torch.optim.AdamW on the CPU
+ * (tests/test_adamw_emul.py) and on a B200 (tests/test_gpu_adamw.py).
  * tensors: device array of ntensors 48-byte entries {float* p; float* g; float* m; float* v; uint16_t* bf16_shadow
  * (or NULL); long long n}.  chunk_tensor / chunk_index: device int[nchunks], the tensor id and the chunk number of
  * every chunk of chunk_elems (multiple of 4) elements.  step: device float, incremented by the call (t = 1 for the

@@ -1,7 +1,7 @@
 """oracle.finestage -- TEST INFRASTRUCTURE ONLY (parity checker; never imported by the product).
 
-CPU restatement of the occupancy head's fine / cascade stage, the part of SURVEY §8f rank 1 that the
-product does not implement yet (prepared so that the kernels can be written against a pinned oracle):
+CPU restatement of the occupancy head's fine / cascade stage (second half; the product's
+counterpart is csrc/fine_stage.cu + csrc/fine_select.cu behind modules.OccHead.forward_fine):
     OccHead.forward, fine branch      P/coocc/dense_heads/occ_head.py:182-237 (layers :58-82)
     coarse_to_fine_coordinates        P/utils/coordinate_transform.py:3-25
     project_points_on_img (nuScenes)  P/utils/coordinate_transform.py:29-70

@@ -261,18 +261,7 @@ def fine_inputs(seed=1):
     return feats, occ, img_feats, transform
 
 
-def fine_head_params(seed=0):
-    """State-dict entries of the fine stage (occ_head.py:58-82) with the reference layer shapes."""
-    g = torch.Generator().manual_seed(seed + 71)
-    r = lambda *s: torch.randn(*s, generator=g)
-    p = {"img_mlp_0.0.weight": r(128, 512, 1, 1) * 0.04, "img_mlp_0.0.bias": r(128) * 0.1,
-         "img_mlp_0.1.weight": 1 + 0.1 * r(128), "img_mlp_0.1.bias": 0.1 * r(128),
-         "img_mlp.0.weight": r(64, 128) * 0.09, "img_mlp.0.bias": r(64) * 0.1,
-         "img_mlp.1.weight": 1 + 0.1 * r(64), "img_mlp.1.bias": 0.1 * r(64),
-         "fine_mlp.0.weight": r(64, 192) * 0.07, "fine_mlp.0.bias": r(64) * 0.1,
-         "fine_mlp.1.weight": 1 + 0.1 * r(64), "fine_mlp.1.bias": 0.1 * r(64),
-         "fine_mlp.3.weight": r(17, 64) * 0.12, "fine_mlp.3.bias": r(17) * 0.1}
-    return p
+fine_head_params = S.fine_head_params      # (moved to coocc_b200.synthetic; same seeded values)
 
 
 def golden_fine(ns):

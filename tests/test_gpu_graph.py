@@ -108,7 +108,7 @@ def test_graph_training_steps_track_eager():
         for a, b in zip(le, lg):
             assert abs(a - b) <= 1e-3 * abs(a), (le, lg)
         for (k, b), c in zip(m_e.named_buffers(), m_g.buffers()):
-            if not b.dtype.is_floating_point:
+            if not b.dtype.is_floating_point and not k.endswith("fine_rng_state"):
                 assert torch.equal(b, c) and (k.endswith("scales") or int(b) == n), k   # num_batches_tracked
         dot = ne = ng = 0.0
         for (k, p), q in zip(m_e.named_parameters(), m_g.parameters()):

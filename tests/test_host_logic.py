@@ -28,6 +28,8 @@ def test_weight_shadow_is_used_only_while_valid():
     assert a.dtype == torch.bfloat16 and torch.equal(a, rows.detach().to(torch.bfloat16))
     w._coocc_bf16 = rows.detach().reshape(-1).to(torch.bfloat16) + 1                # a recognisable shadow
     w._coocc_bf16_version = w._version
+    assert CF.weight_operand(w, CF.DT_BF16).data_ptr() != w._coocc_bf16.data_ptr()  # no layout key: not trusted
+    w._coocc_bf16_layout = (w.data_ptr(), tuple(w.stride()))
     b = CF.weight_operand(w, CF.DT_BF16)
     assert b.data_ptr() == w._coocc_bf16.data_ptr()                                 # used as is
     assert CF.weight_operand(w, CF.DT_TF32).dtype == torch.float32                  # fp32 modes never use it
@@ -36,6 +38,12 @@ def test_weight_shadow_is_used_only_while_valid():
     c = CF.weight_operand(w, CF.DT_BF16)
     assert c.data_ptr() != w._coocc_bf16.data_ptr()
     assert torch.equal(c, CF.weight_rows(w).detach().to(torch.bfloat16))
+    # a relayout through `.data =` keeps the version counter: the storage address / strides invalidate it
+    w._coocc_bf16_version = w._version
+    assert CF.weight_operand(w, CF.DT_BF16).data_ptr() == w._coocc_bf16.data_ptr()
+    w.data = w.data.clone()
+    assert w._version == w._coocc_bf16_version
+    assert CF.weight_operand(w, CF.DT_BF16).data_ptr() != w._coocc_bf16.data_ptr()
 
 
 def test_graph_bucket_keys():
