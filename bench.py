@@ -189,13 +189,23 @@ def run_reference(args, cfg):
         return
     fine = not args.no_fine and cfg["C"] == 128
     step, nvox = cpu_step_fn(cfg, fine)
-    for _ in range(args.warmup):
+    # a step on the reference's working grid costs 10-30 s of CPU: the requested W + K steps run as long as they fit a
+    # wall-clock budget (COOCC_CPU_BUDGET_S, default 300 s); `steps` / `warmup` below are the counts actually run
+    budget = float(os.environ.get("COOCC_CPU_BUDGET_S", "300"))
+    t_start = time.perf_counter()
+    n_warm = 0
+    while n_warm < args.warmup and (n_warm == 0 or time.perf_counter() - t_start < 0.15 * budget):
         step()
+        n_warm += 1
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    n_steps = 0
+    while n_steps < args.steps and (n_steps == 0 or (time.perf_counter() - t_start) * (1 + 1.0 / (n_steps + n_warm)) < budget):
         step()
-    dt = (time.perf_counter() - t0) / args.steps
+        n_steps += 1
+    dt = (time.perf_counter() - t0) / n_steps
     val = nvox / dt
+    requested = dict(steps=args.steps, warmup=args.warmup)
+    args.steps, args.warmup = n_steps, n_warm
     conf = workload_config(args, cfg, fine)
     # what actually ran: the CPU arm's grid, not the GPU arm's
     conf["workload"] = ("CPU arm of %s: %dx%dx%d working grid (the reference's own, 1/%d of the GPU arm's voxels per step), "
@@ -208,7 +218,7 @@ def run_reference(args, cfg):
     conf["parallelism"] = "1 CPU process (rank 0 only), %d threads" % (os.cpu_count() or 1)
     line = dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=args.gpus, gpus_used=0, steps=args.steps,
                 warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", config=conf,
+                dtype="f32", data="synthetic", config=conf, requested=requested,
                 cpu_baseline=dict(value=val, unit=UNIT, cores=os.cpu_count() or 1, kind="port", grid=list(CPU_GRID),
                                   sample=cpu_sample_text(cfg, fine, dt, args.steps)),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))

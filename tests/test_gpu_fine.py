@@ -54,3 +54,39 @@ def test_fine_stage_matches_reference_fixture_and_oracle(golden):
         assert rel_l2(head.img_mlp_0[0].weight.grad.reshape(128, 512), p["img_mlp_0.0.weight"].grad.reshape(128, 512)) < 1e-2
     finally:
         coocc_b200.set_precision("tf32")
+
+
+@pytest.mark.parametrize("case", [(5000, 64, 16, 1), (3001, 128, 16, 1), (6 * 77, 128, 16, 77), (2 * 640, 64, 16, 640),
+                                  (300, 48, 16, 1)])
+def test_groupnorm_kernels_match_torch(case):
+    """nn.GroupNorm(16) + ReLU on point rows (span 1: the fused one-thread-per-(row, group) kernels) and on NHWC feature
+    maps (span = H*W: one block per (sample, group)) against F.group_norm, forward and all three gradients."""
+    import torch.nn.functional as F
+    import torch.nn as nn
+    from coocc_b200 import functional as CF
+    rows, C, G, span = case
+    gen = torch.Generator().manual_seed(rows + C)
+    x0 = torch.randn(rows, C, generator=gen) * 1.5 + 0.3
+    gn = nn.GroupNorm(G, C)
+    with torch.no_grad():
+        gn.weight.copy_(torch.rand(C, generator=gen) + 0.5)
+        gn.bias.copy_(torch.randn(C, generator=gen) * 0.2)
+    w = torch.randn(rows, C, generator=gen)
+    xr = x0.clone().requires_grad_(True)
+    if span == 1:
+        ref = F.relu(F.group_norm(xr, G, gn.weight, gn.bias, gn.eps))
+    else:
+        n = rows // span
+        ref = F.relu(F.group_norm(xr.reshape(n, span, C).permute(0, 2, 1), G, gn.weight, gn.bias, gn.eps)).permute(0, 2, 1).reshape(rows, C)
+    (ref * w).sum().backward()
+    ref_dg, ref_db = gn.weight.grad.clone(), gn.bias.grad.clone()
+    gn.zero_grad()
+    gd = nn.GroupNorm(G, C).to(DEV)
+    gd.load_state_dict(gn.state_dict())
+    x = x0.to(DEV).requires_grad_(True)
+    y = CF.group_norm_rows(x, gd, span=span, relu=True)
+    (y * w.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_l2(y, ref) < 1e-5
+    assert rel_l2(x.grad, xr.grad) < 1e-4
+    assert rel_l2(gd.weight.grad, ref_dg) < 1e-4 and rel_l2(gd.bias.grad, ref_db) < 1e-4

@@ -1,33 +1,49 @@
-"""One warmed-up forward+backward of the hot path between cudaProfilerStart/Stop, for
-`ncu --profile-from-start off -k regex:<kernels>` captures of the non-conv kernels."""
+"""One warmed-up training step of the hot path (forward + backward + AdamW, eager launches) between
+cudaProfilerStart/Stop, for `ncu --profile-from-start off` captures: the launch list of exactly one step
+(`--metrics gpu__time_duration.sum`) or sections of selected kernels (`-k regex:<kernels>`)."""
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import coocc_b200
 from coocc_b200 import synthetic as S
+from coocc_b200.optim import FusedAdamW
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="northstar")
 ap.add_argument("--precision", default="bf16")
+ap.add_argument("--no-fine", action="store_true")
+ap.add_argument("--select", default="device", choices=["device", "host"])
+ap.add_argument("--no-opt", action="store_true")
 a = ap.parse_args()
 cfg = S.CONFIGS[a.workload]
 C, K = cfg["C"], cfg["K"]
 dev = "cuda"
 coocc_b200.set_precision(a.precision)
 torch.manual_seed(0)
-model = coocc_b200.HotPath(coocc_b200.model_cfg(C, K), C).to(dev).train()
+fine = not a.no_fine and C == 128
+model = coocc_b200.HotPath(coocc_b200.model_cfg(C, K, fine=fine, grid=cfg["grid"]), C).to(dev).train()
+model.pts_bbox_head.fine_select = a.select
 inp = S.make_inputs(a.workload)
 d = {k: v.to(dev) for k, v in inp.items()}
-X, Y, Z = cfg["grid"]
 occ = S.make_gt_occ(cfg["grid"], 2, 0).to(dev)
+img_feats = tr = None
+if fine:
+    img_feats = S.make_img_feats(cfg["cams"], cfg["fH"], cfg["fW"], 0).to(dev)
+    tr = tuple(t.to(dev) if torch.is_tensor(t) else t for t in S.make_transform(cfg["cams"], cfg["fH"], cfg["fW"], 0))
+params = [p for p in model.parameters() if p.requires_grad]
+opt = None if a.no_opt else FusedAdamW(params, lr=1e-4, weight_decay=0.01, shadow=(a.precision == "bf16"))
 
 
 def step():
     model.zero_grad(set_to_none=True)
-    losses, _, _ = model.forward_train(d["img_voxel_feats"], d["pts_voxel_feats"], d["geom"], d["gt_depth"], d["gt_img"], occ)
+    losses, _, _ = model.forward_train(d["img_voxel_feats"], d["pts_voxel_feats"], d["geom"], d["gt_depth"], d["gt_img"], occ,
+                                       img_feats, tr)
     sum(losses.values()).backward()
+    if opt is not None:
+        opt.step()
 
 
+step()
 step()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
