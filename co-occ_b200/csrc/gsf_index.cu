@@ -236,10 +236,13 @@ struct FpsJob {
   int* out;          // [m] sampled indices into list
 };
 
-// --- one-hop cluster exchange -------------------------------------------------------------
-// Every warp sends its candidate straight into the inbox of every CTA of the cluster with
-// st.async (remote shared-memory store that completes bytes on the *receiver's* mbarrier); a
-// round is then a single wait on the local mbarrier -- no __syncthreads, no barrier.cluster.
+// --- cluster exchange ---------------------------------------------------------------------
+// Two levels per round: the 16 warps of a CTA reduce their candidates through shared memory (one
+// block barrier), then warp 0 sends the CTA's candidate into the inbox of every CTA of the cluster
+// with st.async (remote shared-memory store that completes bytes on the *receiver's* mbarrier) and
+// every warp waits on the local mbarrier -- no barrier.cluster.  (Round 1 sent every warp's
+// candidate to every CTA: 16 x CS messages and mbarrier transactions per CTA and round, which is
+// what bounded the round at 2.4 us; now CS messages.)
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
@@ -262,11 +265,14 @@ __device__ __forceinline__ void fps_mbar_arm(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+// Default (.acquire.cta) semantics on purpose: the payload arrives through st.async, whose bytes are made visible by
+// the transaction count of this very mbarrier; an .acquire.cluster wait makes ptxas emit CCTL.IVALL (L1 invalidate)
+// after every wait -- measured at 65 % of all stall samples of the kernel (profiles/r02_fps_ncu.txt).
 __device__ __forceinline__ void fps_mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "FPS_WAIT:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra FPS_DONE;\n\t"
       "bra FPS_WAIT;\n\t"
       "FPS_DONE:\n\t}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
@@ -275,6 +281,15 @@ __device__ __forceinline__ void fps_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 constexpr int kFpsWarps = kFpsThreads / 32;
+
+// Optional phase trace (tools/fps_trace.py): clock64 of CTA 0 / warp 0 at six points of rounds 1024..1087 of job 0.
+#ifdef COOCC_FPS_TRACE
+__device__ long long g_fps_trace[16 * 64 * 8];
+#define FPS_T(slot) do { if (blockIdx.y == 0 && tid == 0 && j >= 1024 && j < 1088) \
+                           g_fps_trace[(rank * 64 + (j - 1024)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define FPS_T(slot) do { } while (0)
+#endif
 
 // Points are dealt to the warps of a CTA in groups ("slots") of 32 consecutive list entries, round
 // robin: slot s of warp w holds entries base + (s*16 + w)*32 + lane.  The list is sorted by voxel id,
@@ -301,10 +316,11 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
   uint32_t* sd = bhi + kFpsWarps * S;                    // [16][S] slot best distance
   uint32_t* stie = sd + kFpsWarps * S;                   // [16][S] slot best tie key
   uint32_t* sc = stie + kFpsWarps * S;                   // [16][S] slot best coordinate
-  __shared__ __align__(16) FpsCand inbox[2][16 * kFpsWarps];    // [parity][sender cta * warps + warp]
+  __shared__ __align__(16) FpsCand inbox[2][16];               // [parity][sender cta]
+  __shared__ __align__(16) FpsCand wcand[2][kFpsWarps];        // [parity][warp] candidates of this CTA's warps
   __shared__ __align__(8) uint64_t mbar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t nmsg = CS * kFpsWarps;
+  const uint32_t nmsg = CS;
 
   // block-size rule of the reference launcher (opt_n_threads): 2^floor(log2 n), capped at 1024
   int log2bs = 0;
@@ -314,11 +330,17 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
     while ((2 << log2bs) <= n && log2bs < 10) ++log2bs;
   }
   const uint32_t bsmask = (1u << log2bs) - 1u;
-  const int cta_base = rank * (S * kFpsThreads);
+  // slot g = (sl * 16 + warp) * CS + rank holds list entries 32 g .. 32 g + 31: consecutive slots go to consecutive
+  // CTAs, then warps.  The slots a new sample can reach are neighbours in space, i.e. short runs of consecutive
+  // slots a few grid rows apart; dealt this way they spread over all CTAs and warps of the cluster (with one
+  // contiguous range per CTA they all landed in one CTA, whose warps updated 3-6 slots each while the other 15
+  // CTAs waited: 2400 of the 4000 cycles of a round, profiles/r02_fps_trace.txt).
+  const int slot_stride = (int)CS * 32;
+  const int slot_base = (int)rank * 32;
 
   // ---- load points, build slot bounding boxes ---------------------------------------------
   for (int sl = 0; sl < S; ++sl) {
-    const int k = cta_base + (sl * kFpsWarps + warp) * 32 + lane;
+    const int k = (sl * kFpsWarps + warp) * slot_stride + slot_base + lane;
     uint32_t c = 0u;
     int xl = 1 << 20, yl = 1 << 20, zl = 1 << 20, xh = -1, yh = -1, zh = -1;
     if (k < n) {
@@ -353,7 +375,7 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
   uint32_t r_slot[2] = {0, 0}, r_bar[2] = {0, 0};
   if (lane < CS) {
     for (int p2 = 0; p2 < 2; ++p2) {
-      r_slot[p2] = mapa_u32((uint32_t)__cvta_generic_to_shared(&inbox[p2][rank * kFpsWarps + warp]), lane);
+      r_slot[p2] = mapa_u32((uint32_t)__cvta_generic_to_shared(&inbox[p2][rank]), lane);
       r_bar[p2] = mapa_u32((uint32_t)__cvta_generic_to_shared(&mbar[p2]), lane);
     }
   }
@@ -364,6 +386,7 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
     const int par = j & 1;
     const int px = cur & 1023u, py = (cur >> 10) & 1023u, pz = cur >> 20;
     bool changed = false;
+    FPS_T(0);
     for (int s0 = 0; s0 < S; s0 += 32) {
       // 1. which of this warp's slots can the new sample reach?
       const int sl = s0 + lane;
@@ -382,23 +405,38 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
       while (todo) {
         const int u = s0 + __ffs(todo) - 1;
         todo &= todo - 1;
-        const int k = cta_base + (u * kFpsWarps + warp) * 32 + lane;
+        const int k0 = (u * kFpsWarps + warp) * slot_stride + slot_base;
+        const int k = k0 + lane;
         uint32_t bd = 0u, bt = 0xffffffffu, bc = 0u;
         if (k < n) {
           const uint32_t c = coords[u * kFpsThreads + tid];
           const uint32_t d = min((uint32_t)d2_packed(c, cur), dist[u * kFpsThreads + tid]);
           dist[u * kFpsThreads + tid] = d;
           bd = d;
-          bt = (__brev((uint32_t)k & bsmask) >> (32 - log2bs) << 22) | ((uint32_t)k >> log2bs);
           bc = c;
         }
-        warp_best(bd, bt, bc);
+        if (log2bs >= 5) {
+          // The 32 entries of a slot differ only in the low five bits of k, which the bit reversal turns into the
+          // top five bits of the tie key: inside a slot the tie order is bitrev5(lane).  One packed max-reduction
+          // yields the slot's best distance and the winning lane.
+          const uint32_t key = (bd << 5) | (31u - (__brev((uint32_t)lane) >> 27));
+          const uint32_t mk = __reduce_max_sync(0xffffffffu, k < n ? key : 0u);
+          const uint32_t wl = __brev(31u - (mk & 31u)) >> 27;
+          bd = mk >> 5;
+          bc = __shfl_sync(0xffffffffu, bc, wl);
+          const uint32_t kw = (uint32_t)k0 + wl;
+          bt = (__brev(kw & bsmask) >> (32 - log2bs) << 22) | (kw >> log2bs);
+        } else {
+          if (k < n) bt = (log2bs ? (__brev((uint32_t)k & bsmask) >> (32 - log2bs) << 22) : 0u) | ((uint32_t)k >> log2bs);
+          warp_best(bd, bt, bc);
+        }
         if (lane == 0) {
           sd[warp * S + u] = bd; stie[warp * S + u] = bt; sc[warp * S + u] = bc;
         }
         changed = true;
       }
     }
+    FPS_T(1);
     // 3. warp candidate = best slot maximum (only when a slot changed)
     if (changed) {
       __syncwarp();
@@ -410,21 +448,46 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
       warp_best(bd, bt, bc);
       wd = bd; wt = bt; wc = bc;
     }
-    // lane i -> CTA i: this warp's candidate, completing 16 bytes on the receiver's mbarrier
-    if (lane < CS) st_async_v4(r_slot[par], r_bar[par], wd, wt, wc, 0u);
+    FPS_T(2);
+    // level 1: the CTA's best candidate (warp candidates through shared memory, one block barrier)
+    if (lane == 0) {
+      FpsCand w;
+      w.d = wd; w.t = wt; w.c = wc; w.pad = 0u;
+      wcand[par][warp] = w;
+    }
+    __syncthreads();
+    FPS_T(3);
+    if (warp == 0) {
+      uint32_t bd = 0u, bt = 0xffffffffu, bc = 0u;
+      if (lane < kFpsWarps) {
+        const FpsCand cnd = wcand[par][lane];
+        bd = cnd.d; bt = cnd.t; bc = cnd.c;
+      }
+      warp_best(bd, bt, bc);
+      FPS_T(6);
+      // level 2: lane i -> CTA i, completing 16 bytes on the receiver's mbarrier
+      if (lane < CS) st_async_v4(r_slot[par], r_bar[par], bd, bt, bc, 0u);
+    }
+    FPS_T(4);
     fps_mbar_wait(&mbar[par], ((j - 1) >> 1) & 1);
+    FPS_T(5);
     uint32_t bd = 0u, bt = 0xffffffffu, bc = 0u;
-    for (uint32_t e = lane; e < nmsg; e += 32) {
-      const FpsCand cnd = inbox[par][e];
-      if (cnd.d > bd || (cnd.d == bd && cnd.t < bt)) { bd = cnd.d; bt = cnd.t; bc = cnd.c; }
+    if (lane < nmsg) {
+      const FpsCand cnd = inbox[par][lane];
+      bd = cnd.d; bt = cnd.t; bc = cnd.c;
     }
     warp_best(bd, bt, bc);
     cur = bc;
-    // No block barrier: inbox[par] is only overwritten by round j+2 messages, and a sender can reach
-    // round j+2 only after it received *every* warp's round j+1 message, which each warp of this CTA
-    // sends after the reads above (program order).  Re-arming for round j+2 happens here, before this
-    // thread's own round j+1 message, hence before any round j+2 byte can arrive; slower local warps
-    // still waiting on the completed phase are unaffected (parity wait).
+    FPS_T(7);
+    // Buffer reuse needs no further barrier.  wcand[par] is rewritten in round j+2; a warp gets there only
+    // through the block barrier of round j+1, which warp 0 reaches after its reads above.  inbox[par] is
+    // overwritten by round j+2 messages; a CTA sends those only after it received *every* CTA's round j+1
+    // message, and this CTA's is sent behind the round j+1 block barrier, i.e. after all its warps finished
+    // the reads above (program order).  Re-arming for round j+2 happens here, before that barrier, hence
+    // before any round j+2 byte can arrive; slower local warps still waiting on the completed phase are
+    // unaffected (parity wait).
+    // (Letting warp 0 alone run the exchange while the others park in a second block barrier was measured too:
+    // 2.86 ms instead of 2.75 ms on the 200x200x16 grid.)
     if (tid == 0) {
       if (j + 2 < m) fps_mbar_arm(&mbar[par], nmsg * 16);
       if (rank == 0) {
@@ -677,6 +740,12 @@ extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, con
 }
 
 // tuning hook (benchmarks only): force the cluster size (0 = automatic) and exchange variant flags
+#ifdef COOCC_FPS_TRACE
+extern "C" int coocc_gsf_fps_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_fps_trace, sizeof(long long) * 16 * 64 * 8) == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+#endif
+
 extern "C" int coocc_gsf_fps_tune(int cluster_size, int flags) {
   g_fps_cs = cluster_size;
   g_fps_flags = flags;
