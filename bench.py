@@ -235,7 +235,8 @@ def workload_config(args, cfg, fine):
                          "fine points") if fine else ("", "")),
                 l2="inputs (%.0f MB/step) exceed the 126 MB L2" % (2 * X * Y * Z * cfg["C"] * 4 / 1e6),
                 parallelism="dp%d (replicas only)" % args.gpus, precision=args.precision,
-                optimizer="torch.optim.AdamW(fused)" if args.optimizer == "torch" else "coocc FusedAdamW + bf16 shadow",
+                optimizer="torch.optim.AdamW(fused)" if args.optimizer == "torch" else
+                "coocc FusedAdamW (norm_decay_mult 0, grad_clip 5, bf16 shadow, gradient arena)",
                 launch="cuda_graph (whole step, co-occ_b200/graph.py)" if args.launch == "graph" else "eager",
                 setup_steps="2 untimed calls before the warm-up (lazy init, graph capture)")
 
@@ -323,12 +324,21 @@ def run_ours(args, cfg):
     model = coocc_b200.HotPath(coocc_b200.model_cfg(C, K, fine=fine, grid=cfg["grid"]), C).to(dev)
     model.train()
     params = [p for p in model.parameters() if p.requires_grad]
-    reducer = GradReducer(params)
+    # gradients live in one flat arena: the weight-gradient kernels accumulate into it, the all-reduce buckets are
+    # slices of it, AdamW reads and clears it (co-occ_b200/ddp.py)
+    arena = None
+    if args.optimizer == "coocc":
+        from coocc_b200.ddp import GradArena
+        arena = GradArena(params)
+    reducer = GradReducer(params, arena=arena)
 
     def make_opt():
+        # the reference's optimizer recipe (coocc_multi_r50_256x704.py:263-279): AdamW lr 1e-4, weight_decay 0.01,
+        # norm_decay_mult 0, grad_clip max_norm 5
         if args.optimizer == "coocc":
-            from coocc_b200.optim import FusedAdamW
-            return FusedAdamW(params, lr=1e-4, weight_decay=0.01, shadow=True)
+            from coocc_b200.optim import FusedAdamW, norm_decay_mults
+            return FusedAdamW(params, lr=1e-4, weight_decay=0.01, shadow=True, arena=arena,
+                              param_mults=norm_decay_mults(model, 0.0), max_norm=5.0)
         return torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True, capturable=(args.launch == "graph"))
 
     opt = make_opt()
@@ -372,6 +382,7 @@ def run_ours(args, cfg):
     def eager_step(d, optimizer=None):
         o = optimizer or opt
         o.zero_grad(set_to_none=True)
+        reducer.begin()
         losses, _, _ = call(model.forward_train, d)
         loss = sum(losses[k] for k in LOSS_KEYS)
         loss.backward()

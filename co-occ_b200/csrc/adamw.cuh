@@ -26,6 +26,8 @@ struct TensorEntry {
   float* v;
   uint16_t* shadow;  // bf16 copy of p in the same memory order, or nullptr
   long long n;
+  float wd_mult;     // parameter-group multipliers (mmcv paramwise_cfg: norm_decay_mult = 0 for the BatchNorm / GroupNorm
+  float lr_mult;     // weights and biases, coocc_multi_r50_256x704.py:263-276)
 };
 
 struct AdamWP {
@@ -36,6 +38,9 @@ struct AdamWP {
   float lr, beta1, beta2, eps, weight_decay;
   const float* step;             // device scalar t (already incremented for this update)
   int zero_grad;
+  // device float[2] or nullptr: {learning-rate multiplier (schedule), gradient scale (clip_grad_norm coefficient)} --
+  // read at run time, so a step replayed from a CUDA graph follows the schedule and the clip
+  const float* dyn;
 };
 
 COOCC_HD uint16_t f32_to_bf16_rn(float f) {
@@ -60,9 +65,11 @@ COOCC_HD void adamw_item(const AdamWP& a, long long id) {
   const float tstep = *a.step;
   const float bc1 = 1.f - powf(a.beta1, tstep);
   const float bc2 = 1.f - powf(a.beta2, tstep);
-  const float step_size = a.lr / bc1;
+  const float lr = a.lr * t.lr_mult * (a.dyn ? a.dyn[0] : 1.f);
+  const float gscale = a.dyn ? a.dyn[1] : 1.f;
+  const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
-  const float decay = 1.f - a.lr * a.weight_decay;
+  const float decay = 1.f - lr * a.weight_decay * t.wd_mult;
   const int cnt = (t.n - base) < 4 ? (int)(t.n - base) : 4;
   const uintptr_t al = (uintptr_t)(t.p + base) | (uintptr_t)(t.g + base) | (uintptr_t)(t.m + base) | (uintptr_t)(t.v + base);
   if (cnt == 4 && (al & 15) == 0 && (!t.shadow || ((uintptr_t)(t.shadow + base) & 7) == 0)) {
@@ -75,7 +82,7 @@ COOCC_HD void adamw_item(const AdamWP& a, long long id) {
     F4 v4 = *reinterpret_cast<const F4*>(t.v + base);
     H4 h4;
     for (int k = 0; k < 4; ++k) {
-      const float g = g4.x[k];
+      const float g = g4.x[k] * gscale;
       float p = p4.x[k] * decay;
       const float m = m4.x[k] + (g - m4.x[k]) * (1.f - a.beta1);
       const float v = a.beta2 * v4.x[k] + (1.f - a.beta2) * g * g;
@@ -92,7 +99,7 @@ COOCC_HD void adamw_item(const AdamWP& a, long long id) {
   }
   for (int k = 0; k < cnt; ++k) {
     const long long i = base + k;
-    const float g = t.g[i];
+    const float g = t.g[i] * gscale;
     float p = t.p[i] * decay;
     const float m = t.m[i] + (g - t.m[i]) * (1.f - a.beta1);
     const float v = a.beta2 * t.v[i] + (1.f - a.beta2) * g * g;

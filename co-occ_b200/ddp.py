@@ -1,12 +1,20 @@
-"""Data-parallel gradient all-reduce for the hot path.
+"""Data-parallel gradient handling for the hot path: a flat gradient arena and the bucketed all-reduce over it.
 
 The reference wraps the detector in MMDistributedDataParallel(broadcast_buffers=False)
-(P/coocc/apis/mmdet_train.py:76-80): one process per GPU, replicas only (the voxel grid never
-shards, `assert B == 1` at coocc_ray.py:365), bucketed gradient all-reduce (mean) overlapped with
-backward.  GradReducer does the same over torch.distributed (NCCL over NVLink on the B200 box,
-gloo in the CPU tests): parameters are bucketed in reverse registration order (the order their
-gradients become ready), a bucket is flattened and all-reduced asynchronously as soon as its last
-gradient has been accumulated, and `finish()` waits and scatters the averaged values back.
+(P/coocc/apis/mmdet_train.py:76-80): one process per GPU, replicas only (the voxel grid never shards, `assert B == 1`
+at coocc_ray.py:365), bucketed gradient all-reduce (mean) overlapped with backward.
+
+GradArena    one flat fp32 buffer holding every parameter's gradient, laid out in reverse registration order (the order
+             in which backward produces them); `p.grad` is a view of it in the parameter's own memory order and stays
+             bound for the whole run.  The weight-gradient kernels accumulate straight into it (functional._Conv3dFn,
+             split-K `red.global.add`), so there is no per-step zero-filled scratch, no AccumulateGrad copy, and the
+             all-reduce buckets are plain slices of the buffer -- no flatten / copy-back (round 1 moved ~2.4 GB of
+             HBM traffic per step through torch.cat and copy_).  optim.FusedAdamW reads the gradients from the arena
+             and clears them in the same pass.
+GradReducer  buckets = contiguous arena ranges; a bucket is all-reduced (average) asynchronously as soon as its last
+             gradient is final, buckets are launched strictly in index order (same collective order on every rank);
+             `finish()` waits.  Works on any parameter list as well (legacy mode: flatten + copy back), which is what
+             the gloo CPU test exercises.
 """
 import torch
 import torch.distributed as dist
@@ -22,14 +30,62 @@ def _flat_view(t):
     return None
 
 
+class GradArena:
+    ALIGN = 64          # elements: every view starts on a 256-byte boundary
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev, dt = self.params[0].device, torch.float32
+        assert all(p.dtype == dt and p.device == dev for p in self.params)
+        self.order = list(reversed(self.params))
+        self.offsets = {}
+        off = 0
+        for p in self.order:
+            self.offsets[id(p)] = off
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flat = torch.zeros(off, device=dev, dtype=dt)
+        self.clean = True          # all zeros (nothing accumulated since the last clear)
+        for p in self.order:
+            o, n = self.offsets[id(p)], p.numel()
+            seg = self.flat[o:o + n]
+            if p.is_contiguous():
+                g = seg.view(p.shape)
+            elif p.dim() == 5 and p.permute(0, 2, 3, 4, 1).is_contiguous():
+                co, ci, k0, k1, k2 = p.shape
+                g = seg.view(co, k0, k1, k2, ci).permute(0, 4, 1, 2, 3)
+            else:
+                raise ValueError("GradArena needs dense parameters (contiguous or channels_last_3d)")
+            assert g.shape == p.shape and g.stride() == p.stride()
+            p._coocc_grad = g            # functional._Conv3dFn accumulates weight gradients here
+            p.grad = g
+
+    def bind(self):
+        """(re)attach the views, e.g. after something set p.grad = None"""
+        for p in self.params:
+            if p.grad is not p._coocc_grad:
+                p.grad = p._coocc_grad
+
+    def zero(self):
+        self.bind()
+        if not self.clean:
+            self.flat.zero_()
+            self.clean = True
+
+    def segment(self, p):
+        o = self.offsets[id(p)]
+        return o, o + p.numel()
+
+
 class GradReducer:
-    def __init__(self, params, bucket_bytes=64 << 20, process_group=None):
+    def __init__(self, params, bucket_bytes=64 << 20, process_group=None, arena=None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self.params = [p for p in params if p.requires_grad]
-        self.buckets = []          # list of lists of params
+        self.arena = arena
+        self.params = list(arena.order) if arena is not None else [p for p in reversed([q for q in params if q.requires_grad])]
+        self.buckets = []          # lists of params, in the order their gradients become ready
         cur, size = [], 0
-        for p in reversed(self.params):
+        for p in self.params:
             cur.append(p)
             size += p.numel() * p.element_size()
             if size >= bucket_bytes:
@@ -41,60 +97,90 @@ class GradReducer:
         for bi, b in enumerate(self.buckets):
             for p in b:
                 self._bucket_of[id(p)] = bi
-        self._ready = [0] * len(self.buckets)
-        self._inflight = []
+        if arena is not None:      # bucket = one contiguous slice of the arena (alignment padding included: zeros)
+            self._ranges = []
+            for b in self.buckets:
+                lo = arena.offsets[id(b[0])]
+                last = b[-1]
+                hi = arena.offsets[id(last)] + (last.numel() + arena.ALIGN - 1) // arena.ALIGN * arena.ALIGN
+                self._ranges.append((lo, hi))
+        backend = dist.get_backend(process_group) if dist.is_initialized() else None
+        self._avg = backend == "nccl"          # ReduceOp.AVG exists for NCCL only; otherwise SUM and divide
         self._hooks = []
+        self.begin()
         if self.world > 1:
             for p in self.params:
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+                self._hooks.append(p.register_post_accumulate_grad_hook(self.mark_ready))
+                p._coocc_on_grad = self.mark_ready      # for gradients written without an AccumulateGrad node
 
-    def _on_grad(self, p):
+    # ----------------------------------------------------------------------------------------------
+    def begin(self):
+        """start of a step: forget everything about the previous one (also after an exception in backward)"""
+        self._seen = [set() for _ in self.buckets]
+        self._launched = 0
+        self._inflight = []
+
+    def mark_ready(self, p):
+        if self.world == 1:
+            return
         bi = self._bucket_of[id(p)]
-        self._ready[bi] += 1
-        if self._ready[bi] == len(self.buckets[bi]):
-            self._launch(bi)
+        self._seen[bi].add(id(p))
+        # strictly in index order: a later bucket that completes first waits for its predecessors
+        while self._launched < len(self.buckets) and len(self._seen[self._launched]) == len(self.buckets[self._launched]):
+            self._launch(self._launched)
+            self._launched += 1
 
     def _launch(self, bi):
-        grads = [p.grad for p in self.buckets[bi]]
-        views = []
-        for g in grads:
-            v = _flat_view(g)
-            views.append(v if v is not None else g.contiguous().reshape(-1))
-        flat = torch.cat(views)
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        if self.arena is not None:
+            lo, hi = self._ranges[bi]
+            flat = self.arena.flat[lo:hi]
+        else:
+            views = []
+            for p in self.buckets[bi]:
+                g = p.grad
+                v = _flat_view(g)
+                views.append(v if v is not None else g.contiguous().reshape(-1))
+            flat = torch.cat(views)
+        work = dist.all_reduce(flat, op=op, group=self.group, async_op=True)
         self._inflight.append((bi, flat, work))
 
     def finish(self):
-        """Wait for all buckets and write the averaged gradients back.  Returns bytes reduced."""
+        """Wait for all buckets (launching the ones whose hooks did not all fire: unused parameters contribute
+        zeros) and leave the averaged gradients in p.grad.  Returns the bytes reduced."""
         if self.world == 1:
+            self.begin()
             return 0
-        # buckets whose hooks did not all fire (unused parameters) are reduced here
-        launched = {bi for bi, _, _ in self._inflight}
-        for bi, b in enumerate(self.buckets):
-            if bi not in launched:
-                for p in b:
+        while self._launched < len(self.buckets):
+            if self.arena is None:
+                for p in self.buckets[self._launched]:
                     if p.grad is None:
                         p.grad = torch.zeros_like(p)
-                self._launch(bi)
+            self._launch(self._launched)
+            self._launched += 1
         total = 0
         for bi, flat, work in self._inflight:
             work.wait()
-            flat.div_(self.world)
             total += flat.numel() * flat.element_size()
-            off = 0
-            for p in self.buckets[bi]:
-                n = p.numel()
-                v = _flat_view(p.grad)
-                if v is not None:
-                    v.copy_(flat[off:off + n])
-                else:
-                    p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
-        self._inflight = []
-        self._ready = [0] * len(self.buckets)
+            if not self._avg:
+                flat.div_(self.world)
+            if self.arena is None:
+                off = 0
+                for p in self.buckets[bi]:
+                    n = p.numel()
+                    v = _flat_view(p.grad)
+                    if v is not None:
+                        v.copy_(flat[off:off + n])
+                    else:
+                        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                    off += n
+        self.begin()
         return total
 
     def remove(self):
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for p in self.params:
+            if hasattr(p, "_coocc_on_grad"):
+                del p._coocc_on_grad

@@ -228,6 +228,7 @@ class _Conv3dFn(torch.autograd.Function):
                                 out_bf16=out_bf16)
         ctx.save_for_backward(xo, wo, y if relu else None)
         ctx.meta = (dims, odims, k, s, relu, bias is not None, dtype, cin, cout)
+        ctx.wparam = w5d if getattr(w5d, "_coocc_grad", None) is not None else None
         ctx.x_bf16 = x2d.dtype == torch.bfloat16
         if want_stats:
             ctx.mark_non_differentiable(stats)
@@ -246,14 +247,27 @@ class _Conv3dFn(torch.autograd.Function):
         dyo = _operand(dy, dtype)
         dx = dw = None
         if ctx.needs_input_grad[1]:
-            dw2d = torch.zeros(cout, k ** 3 * cin, device=dy.device, dtype=torch.float32)
+            # the kernel accumulates (split-K red.add).  With a gradient arena (ddp.GradArena) it adds straight into
+            # the parameter's slice of the arena -- no zero-filled scratch, no AccumulateGrad pass -- and the
+            # gradient is reported as None to autograd; otherwise into a fresh zero buffer that is returned.
+            sink = ctx.wparam._coocc_grad if ctx.wparam is not None else None
+            if sink is not None:
+                dw2d = sink.permute(0, 2, 3, 4, 1).reshape(cout, k ** 3 * cin)
+                assert dw2d.data_ptr() == sink.data_ptr()
+            else:
+                dw2d = torch.zeros(cout, k ** 3 * cin, device=dy.device, dtype=torch.float32)
             d = _conv_desc(dims, cin, cout, k, s, xo.stride(0), dyo.stride(0), dtype)
             flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
             _lib.check(_timed("wgrad", flops, lambda: L.coocc_conv3d_wgrad(ctypes.byref(d), _p(xo), _p(dyo), _p(dw2d),
                                                                           _stream()),
                               " %s %d->%d k%d s%d" % (dims, cin, cout, k, s)), "conv3d_wgrad")
-            # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
-            dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
+            if sink is not None:
+                cb = getattr(ctx.wparam, "_coocc_on_grad", None)      # ddp.GradReducer: this gradient is final
+                if cb is not None:
+                    cb(ctx.wparam)
+            else:
+                # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
+                dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
         if ctx.needs_input_grad[0]:
             if s != 1:
                 # scatter dy onto the input lattice (even positions), then a stride-1 dgrad

@@ -68,6 +68,8 @@ class GraphedStep:
             self.opt.zero_grad(set_to_none=True)
         else:
             self.model.zero_grad(set_to_none=True)
+        if self.reducer is not None:
+            self.reducer.begin()
         losses, _, _ = self.model.forward_train(img, pts, geom, gt_depth, gt_img, gt_occ, img_feats, transform)
         loss = self._loss(losses)
         loss.backward()
@@ -187,6 +189,8 @@ class GraphedStep:
             self.opt.zero_grad(set_to_none=True)
         else:
             self.model.zero_grad(set_to_none=True)
+        if self.reducer is not None:
+            self.reducer.begin()
         g = torch.cuda.CUDAGraph()
         n0 = _lib.CALLS["n"]
         CF.GSF_OVERRIDE = ov

@@ -280,14 +280,16 @@ int coocc_fine_gather_labels(const int* coords, long long M, int topk, const int
  * csrc/adamw.cuh).  Replaces torch.optim.AdamW (the reference's optimizer, coocc_multi_r50_256x704.py:283-290) plus
  * the per-step fp32 -> bf16 weight conversions of the bf16 mode.  Verified against torch.optim.AdamW on the CPU
  * (tests/test_adamw_emul.py) and on a B200 (tests/test_gpu_adamw.py).
- * tensors: device array of ntensors 48-byte entries {float* p; float* g; float* m; float* v; uint16_t* bf16_shadow
- * (or NULL); long long n}.  chunk_tensor / chunk_index: device int[nchunks], the tensor id and the chunk number of
+ * tensors: device array of ntensors 56-byte entries {float* p; float* g; float* m; float* v; uint16_t* bf16_shadow
+ * (or NULL); long long n; float wd_mult; float lr_mult} (the multipliers are mmcv's paramwise_cfg, e.g.
+ * norm_decay_mult = 0).  chunk_tensor / chunk_index: device int[nchunks], the tensor id and the chunk number of
  * every chunk of chunk_elems (multiple of 4) elements.  step: device float, incremented by the call (t = 1 for the
- * first update).  zero_grad != 0 clears the gradients after they have been consumed.
+ * first update).  zero_grad != 0 clears the gradients after they have been consumed.  dyn: device float[2]
+ * {learning-rate multiplier (lr schedule), gradient scale (clip_grad_norm coefficient)} read at run time, or NULL.
  * ------------------------------------------------------------------------------------------ */
 int coocc_adamw_step(const void* tensors, int ntensors, const int* chunk_tensor, const int* chunk_index, int nchunks,
                      int chunk_elems, float lr, float beta1, float beta2, float eps, float weight_decay, float* step,
-                     int zero_grad, void* stream);
+                     int zero_grad, const float* dyn, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * BatchNorm3d (training mode) + ReLU + residual, and x2 zero insertion (csrc/elementwise.cu).

@@ -52,14 +52,48 @@ def test_adamw_matches_torch_over_several_steps(E, wd):
         opt.step()
         rows = []
         for f, g, mm, vv, s in zip(flat, grads, m, v, sh):
-            rows += [f.data_ptr(), g.data_ptr(), mm.data_ptr(), vv.data_ptr(), s.data_ptr(), f.numel()]
+            rows += [f.data_ptr(), g.data_ptr(), mm.data_ptr(), vv.data_ptr(), s.data_ptr(), f.numel(), CO.pack_mults(1.0, 1.0)]
         table = torch.tensor(rows, dtype=torch.int64)
         E.emul_adamw_step(ctypes.c_void_p(table.data_ptr()), len(flat), ctypes.c_void_p(ctt.data_ptr()),
                           ctypes.c_void_p(cit.data_ptr()), len(ct), CO.CHUNK, ctypes.c_float(1e-2), ctypes.c_float(0.9),
                           ctypes.c_float(0.99), ctypes.c_float(1e-8), ctypes.c_float(wd),
-                          ctypes.c_void_p(step.data_ptr()), 1)
+                          ctypes.c_void_p(step.data_ptr()), 1, None)
         assert float(step) == it + 1
         for p, r, g, s in zip(ps, ref, grads, sh):
             assert torch.allclose(p.detach(), r.detach(), rtol=2e-5, atol=1e-7), it
             assert float(g.abs().max()) == 0.0                                        # zero_grad folded into the pass
             assert torch.equal(s.view(torch.bfloat16), p.detach().reshape(-1).to(torch.bfloat16))   # shadow = bf16(p), RNE
+
+
+def test_param_multipliers_lr_scale_and_grad_scale(E):
+    """wd_mult / lr_mult per tensor (mmcv paramwise_cfg), the device-side lr multiplier and gradient scale: equal to
+    torch.optim.AdamW with the corresponding param groups fed pre-scaled gradients."""
+    gen = torch.Generator().manual_seed(1)
+    ps = [torch.randn(n, generator=gen).requires_grad_(True) for n in (50, 300)]
+    ref = [p.detach().clone().requires_grad_(True) for p in ps]
+    lr, wd, lr_scale, gscale = 1e-2, 0.05, 0.1, 0.25
+    opt = torch.optim.AdamW([dict(params=[ref[0]], weight_decay=0.0, lr=lr * lr_scale),
+                             dict(params=[ref[1]], weight_decay=wd, lr=lr * lr_scale * 2.0)], betas=(0.9, 0.99))
+    mults = [(0.0, 1.0), (1.0, 2.0)]
+    flat = [p.detach().reshape(-1) for p in ps]
+    m = [torch.zeros_like(f) for f in flat]
+    v = [torch.zeros_like(f) for f in flat]
+    ct, ci = CO.build_tables([f.numel() for f in flat])
+    ctt, cit = torch.tensor(ct, dtype=torch.int32), torch.tensor(ci, dtype=torch.int32)
+    step = torch.zeros(1)
+    dyn = torch.tensor([lr_scale, gscale])
+    for it in range(3):
+        grads = [torch.randn(f.numel(), generator=gen) for f in flat]
+        for r, g in zip(ref, grads):
+            r.grad = (g * gscale).clone()
+        opt.step()
+        rows = []
+        for f, g, mm, vv, mu in zip(flat, grads, m, v, mults):
+            rows += [f.data_ptr(), g.data_ptr(), mm.data_ptr(), vv.data_ptr(), 0, f.numel(), CO.pack_mults(*mu)]
+        table = torch.tensor(rows, dtype=torch.int64)
+        E.emul_adamw_step(ctypes.c_void_p(table.data_ptr()), len(flat), ctypes.c_void_p(ctt.data_ptr()),
+                          ctypes.c_void_p(cit.data_ptr()), len(ct), CO.CHUNK, ctypes.c_float(lr), ctypes.c_float(0.9),
+                          ctypes.c_float(0.99), ctypes.c_float(1e-8), ctypes.c_float(wd),
+                          ctypes.c_void_p(step.data_ptr()), 0, ctypes.c_void_p(dyn.data_ptr()))
+        for p, r in zip(ps, ref):
+            assert torch.allclose(p.detach(), r.detach(), rtol=2e-5, atol=1e-7), it

@@ -35,6 +35,22 @@ def _worker(rank, world, port, q):
     nbytes = red.finish()
     grads = [p.grad.clone() for p in net.parameters()]
     ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(grads, ref))
+    red.remove()
+    # arena mode: p.grad are views of one flat buffer, buckets are slices of it (no flatten / copy back); a second
+    # backward before finish() accumulates (gradient accumulation) and a step that raised leaves no stale state
+    from coocc_b200.ddp import GradArena
+    net.zero_grad(set_to_none=True)
+    arena = GradArena(list(net.parameters()))
+    red2 = GradReducer(None, bucket_bytes=64, arena=arena)
+    ok = ok and len(red2.buckets) >= 2 and all(p.grad.data_ptr() == p._coocc_grad.data_ptr() for p in net.parameters())
+    ok = ok and net[0].weight.grad.stride() == net[0].weight.stride()
+    red2.mark_ready(net[2].bias)          # a step that died after one gradient ...
+    red2.begin()                          # ... is forgotten at the start of the next one
+    net(x).square().mean().backward()
+    nbytes2 = red2.finish()
+    ok = ok and all(torch.allclose(p.grad, b, atol=1e-6) for p, b in zip(net.parameters(), ref))
+    ok = ok and all(p.grad.data_ptr() == p._coocc_grad.data_ptr() for p in net.parameters())     # still the arena
+    ok = ok and nbytes2 >= nbytes
     q.put((rank, ok, nbytes))
     dist.barrier()
     dist.destroy_process_group()

@@ -95,3 +95,45 @@ def test_fused_adamw_two_graphs_and_an_eager_step_share_one_optimizer():
     torch.cuda.synchronize()
     for p, q in zip(pa, pb):
         assert torch.allclose(p, q, rtol=5e-6, atol=5e-7), (p - q).abs().max().item()
+
+
+def test_arena_norm_decay_and_grad_clip_match_torch():
+    """FusedAdamW on a ddp.GradArena (gradients accumulated in place, cleared by the kernel) with the reference's
+    optimizer recipe: norm_decay_mult = 0 for normalisation parameters (coocc_multi_r50_256x704.py:276), grad_clip
+    max_norm (:279), and an lr-schedule multiplier."""
+    import torch.nn as nn
+    from coocc_b200.ddp import GradArena
+    from coocc_b200.optim import norm_decay_mults
+
+    def build():
+        torch.manual_seed(3)
+        net = nn.Sequential(nn.Conv3d(4, 8, 3, padding=1, bias=False), nn.BatchNorm3d(8), nn.ReLU(),
+                            nn.Conv3d(8, 4, 1)).to(DEV)
+        net[0].weight.data = net[0].weight.data.contiguous(memory_format=torch.channels_last_3d)
+        return net
+
+    na, nb = build(), build()
+    arena = GradArena(list(na.parameters()))
+    oa = FusedAdamW(list(na.parameters()), lr=1e-2, weight_decay=0.1, shadow=False, arena=arena,
+                    param_mults=norm_decay_mults(na, 0.0), max_norm=0.5)
+    norm_p = [p for m in nb.modules() if isinstance(m, nn.BatchNorm3d) for p in m.parameters()]
+    rest = [p for p in nb.parameters() if all(p is not q for q in norm_p)]
+    ob = torch.optim.AdamW([dict(params=rest), dict(params=norm_p, weight_decay=0.0)], lr=1e-2, weight_decay=0.1)
+    for it in range(4):
+        if it == 2:
+            oa.set_lr_scale(0.1)
+            for g in ob.param_groups:
+                g["lr"] = 1e-3
+        x = torch.randn(2, 4, 6, 5, 4, generator=torch.Generator().manual_seed(it)).to(DEV)
+        oa.zero_grad()
+        ob.zero_grad()
+        (na(x).square().mean() * 50).backward()
+        (nb(x).square().mean() * 50).backward()
+        assert all(p.grad.data_ptr() == p._coocc_grad.data_ptr() for p in na.parameters())
+        total = torch.nn.utils.clip_grad_norm_(nb.parameters(), 0.5)
+        oa.step()
+        ob.step()
+        assert abs(float(oa.grad_norm) - float(total)) < 1e-4 * float(total)
+        assert float(arena.flat.abs().max()) == 0.0                   # cleared in the same pass
+    for p, q in zip(na.parameters(), nb.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (p - q).abs().max().item()

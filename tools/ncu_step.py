@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import coocc_b200
 from coocc_b200 import synthetic as S
-from coocc_b200.optim import FusedAdamW
+from coocc_b200.ddp import GradArena
+from coocc_b200.optim import FusedAdamW, norm_decay_mults
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="northstar")
@@ -31,11 +32,18 @@ if fine:
     img_feats = S.make_img_feats(cfg["cams"], cfg["fH"], cfg["fW"], 0).to(dev)
     tr = tuple(t.to(dev) if torch.is_tensor(t) else t for t in S.make_transform(cfg["cams"], cfg["fH"], cfg["fW"], 0))
 params = [p for p in model.parameters() if p.requires_grad]
-opt = None if a.no_opt else FusedAdamW(params, lr=1e-4, weight_decay=0.01, shadow=(a.precision == "bf16"))
+opt = None
+if not a.no_opt:
+    arena = GradArena(params)
+    opt = FusedAdamW(params, lr=1e-4, weight_decay=0.01, shadow=(a.precision == "bf16"), arena=arena,
+                     param_mults=norm_decay_mults(model, 0.0), max_norm=5.0)
 
 
 def step():
-    model.zero_grad(set_to_none=True)
+    if opt is not None:
+        opt.zero_grad()
+    else:
+        model.zero_grad(set_to_none=True)
     losses, _, _ = model.forward_train(d["img_voxel_feats"], d["pts_voxel_feats"], d["geom"], d["gt_depth"], d["gt_img"], occ,
                                        img_feats, tr)
     sum(losses.values()).backward()
