@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--optimizer", default=os.environ.get("COOCC_OPTIMIZER", "coocc"), choices=["torch", "coocc"],
                     help="coocc: co-occ_b200/optim.py FusedAdamW (one multi-tensor kernel that also writes the bf16 weight "
                          "operands); torch: torch.optim.AdamW(fused=True)")
+    ap.add_argument("--no-peer", action="store_true", help="SyncBN statistics through NCCL instead of the peer-memory kernel")
     ap.add_argument("--no-fine", action="store_true", help="coarse head only (cascade_ratio=1), the round-1 step")
     ap.add_argument("--launch", default=os.environ.get("COOCC_LAUNCH", "graph"), choices=["graph", "eager"],
                     help="graph: the step is replayed as one CUDA graph (co-occ_b200/graph.py); eager: one launch per kernel")
@@ -315,6 +316,16 @@ def run_ours(args, cfg):
             os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev)
     coocc_b200.set_precision(args.precision)
+    syncbn = "single process"
+    if world > 1:
+        syncbn = "NCCL all-reduce per BatchNorm"
+        if not args.no_peer:
+            try:
+                from coocc_b200.peer import PeerExchange
+                CF.PEER = PeerExchange()
+                syncbn = "peer-memory all-reduce kernel over NVLink (csrc/peer_reduce.cu)"
+            except Exception as e:  # noqa: BLE001 -- no peer access between the devices: NCCL carries the statistics
+                syncbn += " (peer exchange unavailable: %s)" % (str(e).splitlines() or [type(e).__name__])[0][:120]
     C, K = cfg["C"], cfg["K"]
     X, Y, Z = cfg["grid"]
     nvox = X * Y * Z
@@ -330,7 +341,7 @@ def run_ours(args, cfg):
     if args.optimizer == "coocc":
         from coocc_b200.ddp import GradArena
         arena = GradArena(params)
-    reducer = GradReducer(params, arena=arena)
+    reducer = GradReducer(params, arena=arena, bucket_bytes=int(os.environ.get("COOCC_BUCKET_MB", "16")) << 20)
 
     def make_opt():
         # the reference's optimizer recipe (coocc_multi_r50_256x704.py:263-279): AdamW lr 1e-4, weight_decay 0.01,
@@ -383,6 +394,7 @@ def run_ours(args, cfg):
         o = optimizer or opt
         o.zero_grad(set_to_none=True)
         reducer.begin()
+        CF.begin_step()
         losses, _, _ = call(model.forward_train, d)
         loss = sum(losses[k] for k in LOSS_KEYS)
         loss.backward()
@@ -521,7 +533,7 @@ def run_ours(args, cfg):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype={"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.precision], data="synthetic",
-                config=workload_config(args, cfg, fine), clocks=clk,
+                config=dict(workload_config(args, cfg, fine), sync_bn=syncbn), clocks=clk,
                 e2e=dict(value=e2e_val, unit=UNIT, ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=h2d_bytes,
                          d2h_bytes_per_step=4, loss=last.get("loss")),
                 gpu_launches=launches,

@@ -316,6 +316,23 @@ def _sync_group():
 # and one of the [2,C] backward sums.  Single process: plain BatchNorm3d.
 SYNC_BN = {"enabled": True}
 
+# peer.PeerExchange or None: when set (bench.py / the training harness, N > 1 on NVLink), the [2,C] statistics go
+# through the peer-memory all-reduce kernel (csrc/peer_reduce.cu) instead of an NCCL call each
+PEER = None
+
+
+def begin_step():
+    """start of a training step (eager or captured): resets the per-step call counter of the peer exchange"""
+    if PEER is not None:
+        PEER.begin_step()
+
+
+def _stats_all_reduce(dist, t):
+    if PEER is not None and PEER.fits(t):
+        PEER.all_reduce(t)
+    else:
+        dist.all_reduce(t)
+
 
 class _BNActFn(torch.autograd.Function):
     """out = relu?(batchnorm_train(x) (+ residual)) from the conv-epilogue statistics."""
@@ -328,7 +345,7 @@ class _BNActFn(torch.autograd.Function):
         count = V
         dist = _sync_group()
         if dist is not None:
-            dist.all_reduce(stats)
+            _stats_all_reduce(dist, stats)
             count = V * dist.get_world_size()
         mi = torch.empty(2, C, device=dev, dtype=torch.float32)
         _lib.check(L.coocc_bn_finalize(_p(stats), C, count, float(eps), float(momentum), _p(running_mean),
@@ -370,7 +387,7 @@ class _BNActFn(torch.autograd.Function):
         if count != V:                      # SyncBN: batch terms use the sums over all ranks
             dist = _sync_group()
             local = sums.clone()            # dgamma / dbeta stay per-rank (DDP averages them)
-            dist.all_reduce(sums)
+            _stats_all_reduce(dist, sums)
         dx = torch.empty(V, C, device=x.device, dtype=x.dtype)
         dres = torch.empty(V, C, device=x.device, dtype=x.dtype) if has_res else None
         _lib.check(_timed("hbm:bn_act_bwd_apply", float(e * V * C * (5 if has_res else 3)),

@@ -70,6 +70,7 @@ class GraphedStep:
             self.model.zero_grad(set_to_none=True)
         if self.reducer is not None:
             self.reducer.begin()
+        CF.begin_step()
         losses, _, _ = self.model.forward_train(img, pts, geom, gt_depth, gt_img, gt_occ, img_feats, transform)
         loss = self._loss(losses)
         loss.backward()
@@ -191,6 +192,7 @@ class GraphedStep:
             self.model.zero_grad(set_to_none=True)
         if self.reducer is not None:
             self.reducer.begin()
+        CF.begin_step()
         g = torch.cuda.CUDAGraph()
         n0 = _lib.CALLS["n"]
         CF.GSF_OVERRIDE = ov

@@ -276,6 +276,20 @@ int coocc_fine_gather_labels(const int* coords, long long M, int topk, const int
                              int GX, int GY, int GZ, int ignore, int* labels, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Small all-reduce over NVLink peer memory (csrc/peer_reduce.cu): the SyncBN statistics exchange of the data-parallel
+ * path.  Replaces the per-BatchNorm collectives of torch.nn.SyncBatchNorm, which the reference turns every BatchNorm
+ * into (tools/train.py:222-223; all_gather in forward, all_reduce in backward) -- 72 NCCL calls of <= 8 KB per step.
+ * A rank's exchange buffer is coocc_peer_buffer_bytes() long, zero-initialised, and mapped into every process (the
+ * caller allocates and exchanges it, e.g. torch.distributed._symmetric_memory).  peer_bufs: HOST array of `world`
+ * device pointers (entry r = rank r's buffer as seen from this device).  data: n <= slot_floats floats, summed over
+ * the ranks in rank order, in place.  slot = position of the call in the step's sequence of calls modulo nslots
+ * (>= 2), identical on all ranks; epoch: device unsigned[nslots] of the calling rank, zero-initialised.
+ * ------------------------------------------------------------------------------------------ */
+long long coocc_peer_buffer_bytes(int world, int nslots, int slot_floats);
+int coocc_peer_allreduce(float* data, int n, void* const* peer_bufs, int rank, int world, int slot, int nslots,
+                         int slot_floats, unsigned* epoch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-tensor AdamW step that also writes the bf16 operand copy of every parameter (csrc/adamw.cu, body in
  * csrc/adamw.cuh).  Replaces torch.optim.AdamW (the reference's optimizer, coocc_multi_r50_256x704.py:283-290) plus
  * the per-step fp32 -> bf16 weight conversions of the bf16 mode.  Verified against torch.optim.AdamW on the CPU
