@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <initializer_list>
+
 #include "../../include/coocc_b200.h"
 #include "act_types.cuh"
 
@@ -39,8 +41,13 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, doubl
 
 // the BatchNorm affine map, one expression shared by forward and backward so that the backward can
 // recompute the ReLU mask (y > 0) from x bit-for-bit instead of re-reading the stored output
+// (written as x * scale + shift with explicitly rounded steps: the wide kernels keep scale / shift in registers and
+// must produce the same bits)
+__device__ __forceinline__ float bn_scale(float is, float g) { return __fmul_rn(is, g); }
+__device__ __forceinline__ float bn_shift(float m, float sc, float b) { return __fmaf_rn(-m, sc, b); }
 __device__ __forceinline__ float bn_affine(float x, float m, float is, float g, float b) {
-  return (x - m) * is * g + b;
+  const float sc = bn_scale(is, g);
+  return __fmaf_rn(x, sc, bn_shift(m, sc, b));
 }
 // dz = dout * [y > 0]: mask from the stored output `o` (use_out) or recomputed from x
 __device__ __forceinline__ float4 bn_mask(float4 d, bool use_out, float4 o, float4 xv, float4 m, float4 is, float4 g,
@@ -196,6 +203,265 @@ __global__ void __launch_bounds__(256) dilate2_kernel(const T* __restrict__ src,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// "Wide" variants (the ones normally launched): every access is 16 bytes (8 bf16 / 4 fp32 channels), the per-channel
+// constants live in registers for the whole kernel, a thread walks rows with UNROLL independent rows in flight, and
+// there is no per-element 64-bit division.  The narrow kernels above ran at 43-56 % of the measured copy bandwidth
+// (profiles/r02_bench*.json hbm_kernels); they remain as the fallback for C not a multiple of the vector width.
+// Thread layout: 256 threads = (C / VEC channel groups) x (256 / groups row lanes).
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+struct VecF {
+  float v[VEC];
+};
+// raw 16-byte vectors stay packed in registers until they are used (4 registers per row in flight)
+template <typename T> struct Raw;
+template <> struct Raw<float> { typedef float4 type; };
+template <> struct Raw<__nv_bfloat16> { typedef uint4 type; };
+__device__ __forceinline__ float4 loadraw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint4 loadraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ VecF<4> unpack(const float4& t) {
+  VecF<4> r;
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  return r;
+}
+__device__ __forceinline__ VecF<8> unpack(const uint4& u) {
+  VecF<8> r;
+  r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  r.v[4] = __uint_as_float(u.z << 16); r.v[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  r.v[6] = __uint_as_float(u.w << 16); r.v[7] = __uint_as_float(u.w & 0xFFFF0000u);
+  return r;
+}
+__device__ __forceinline__ void storev(float* p, const VecF<4>& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+__device__ __forceinline__ void storev(__nv_bfloat16* p, const VecF<8>& r) {
+  uint4 u;
+  __nv_bfloat162 a = __floats2bfloat162_rn(r.v[0], r.v[1]), b = __floats2bfloat162_rn(r.v[2], r.v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(r.v[4], r.v[5]), d = __floats2bfloat162_rn(r.v[6], r.v[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+template <int VEC>
+__device__ __forceinline__ VecF<VEC> loadc(const float* p) {        // VEC consecutive fp32 constants
+  VecF<VEC> r;
+#pragma unroll
+  for (int k = 0; k < VEC; k += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + k);
+    r.v[k] = t.x; r.v[k + 1] = t.y; r.v[k + 2] = t.z; r.v[k + 3] = t.w;
+  }
+  return r;
+}
+// scale = invstd * gamma, shift = beta - mean * scale of the thread's VEC channels
+template <int VEC>
+__device__ __forceinline__ void load_affine(const float* mean_invstd, const float* gamma, const float* beta, int C, int c,
+                                            VecF<VEC>& sc, VecF<VEC>& sh) {
+  const VecF<VEC> m = loadc<VEC>(mean_invstd + c), is = loadc<VEC>(mean_invstd + C + c);
+  const VecF<VEC> g = loadc<VEC>(gamma + c), b = loadc<VEC>(beta + c);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    sc.v[k] = bn_scale(is.v[k], g.v[k]);
+    sh.v[k] = bn_shift(m.v[k], sc.v[k], b.v[k]);
+  }
+}
+
+template <typename T, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256) bn_act_fwd_wide_kernel(const T* __restrict__ x, long long ldx, long long V,
+                                                              int C, const float* __restrict__ mean_invstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const T* __restrict__ residual, long long ldr, int relu,
+                                                              T* __restrict__ out, long long ldo, int cg, int rl) {
+  typedef typename Raw<T>::type R;
+  const int tc = threadIdx.x % cg, tr = threadIdx.x / cg;
+  if (tr >= rl) return;
+  const int c = tc * VEC;
+  VecF<VEC> sc, sh;
+  load_affine<VEC>(mean_invstd, gamma, beta, C, c, sc, sh);
+  const long long stride = (long long)gridDim.x * rl;
+  for (long long r0 = (long long)blockIdx.x * rl + tr; r0 < V; r0 += stride * UNROLL) {
+    R xr[UNROLL], rr[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < V) {
+        xr[u] = loadraw(x + r * ldx + c);
+        if (residual != nullptr) rr[u] = loadraw(residual + r * ldr + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < V) {
+        const VecF<VEC> xv = unpack(xr[u]);
+        VecF<VEC> y;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) y.v[k] = __fmaf_rn(xv.v[k], sc.v[k], sh.v[k]);
+        if (residual != nullptr) {
+          const VecF<VEC> rv = unpack(rr[u]);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) y.v[k] += rv.v[k];
+        }
+        if (relu) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) y.v[k] = fmaxf(y.v[k], 0.f);
+        }
+        storev(out + r * ldo + c, y);
+      }
+    }
+  }
+}
+
+// accumulates sum dz and sum dz * x per channel; the block's reducing threads turn the latter into
+// sum dz * xhat = invstd * (sum dz * x - mean * sum dz) before the atomics
+template <typename T, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_wide_kernel(
+    const T* __restrict__ dout, long long ldd, const T* __restrict__ out, long long ldo, const T* __restrict__ x,
+    long long ldx, long long V, int C, const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+    const float* __restrict__ beta, int relu, float* __restrict__ sums, int cg, int rl) {
+  typedef typename Raw<T>::type R;
+  extern __shared__ float sh[];                    // [2][rl][C]
+  const int tc = threadIdx.x % cg, tr = threadIdx.x / cg;
+  const int c = tc * VEC;
+  const bool use_out = out != nullptr;
+  VecF<VEC> s1, s2;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { s1.v[k] = 0.f; s2.v[k] = 0.f; }
+  if (tr < rl) {
+    VecF<VEC> sc, sf;
+    if (relu && !use_out) load_affine<VEC>(mean_invstd, gamma, beta, C, c, sc, sf);
+    // shifted accumulation (x - mean) keeps sum dz * x well conditioned
+    const VecF<VEC> m = loadc<VEC>(mean_invstd + c);
+    const long long stride = (long long)gridDim.x * rl;
+    for (long long r0 = (long long)blockIdx.x * rl + tr; r0 < V; r0 += stride * UNROLL) {
+      R dr[UNROLL], xr[UNROLL], orw[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long long r = r0 + u * stride;
+        if (r < V) {
+          dr[u] = loadraw(dout + r * ldd + c);
+          xr[u] = loadraw(x + r * ldx + c);
+          if (relu && use_out) orw[u] = loadraw(out + r * ldo + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long long r = r0 + u * stride;
+        if (r < V) {
+          const VecF<VEC> dv = unpack(dr[u]), xv = unpack(xr[u]);
+          VecF<VEC> ov;
+          if (relu && use_out) ov = unpack(orw[u]);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            float d = dv.v[k];
+            if (relu) {
+              const float y = use_out ? ov.v[k] : __fmaf_rn(xv.v[k], sc.v[k], sf.v[k]);
+              d = y > 0.f ? d : 0.f;
+            }
+            s1.v[k] += d;
+            s2.v[k] += d * (xv.v[k] - m.v[k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      sh[(size_t)tr * C + c + k] = s1.v[k];
+      sh[(size_t)(rl + tr) * C + c + k] = s2.v[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    const int which = i / C, ch = i % C;
+    float t = 0.f;
+    for (int j = 0; j < rl; ++j) t += sh[(size_t)(which * rl + j) * C + ch];
+    if (which) t *= mean_invstd[C + ch];
+    atomicAdd(&sums[i], t);
+  }
+}
+
+template <typename T, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_wide_kernel(
+    const T* __restrict__ dout, long long ldd, const T* __restrict__ out, long long ldo, const T* __restrict__ x,
+    long long ldx, long long V, int C, const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ sums, int relu, T* __restrict__ dx, long long lddx,
+    T* __restrict__ dres, long long lddr, float inv_n, int cg, int rl) {
+  typedef typename Raw<T>::type R;
+  const int tc = threadIdx.x % cg, tr = threadIdx.x / cg;
+  if (tr >= rl) return;
+  const int c = tc * VEC;
+  const bool use_out = out != nullptr;
+  VecF<VEC> sc, sf;
+  if (relu && !use_out) load_affine<VEC>(mean_invstd, gamma, beta, C, c, sc, sf);
+  // dx = gamma*invstd * (dz - a/n - xhat * b/n) = ka * dz + kb * x + kc
+  VecF<VEC> ka, kb, kc;
+  {
+    const VecF<VEC> m = loadc<VEC>(mean_invstd + c), is = loadc<VEC>(mean_invstd + C + c);
+    const VecF<VEC> g = loadc<VEC>(gamma + c);
+    const VecF<VEC> a = loadc<VEC>(sums + c), b = loadc<VEC>(sums + C + c);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      ka.v[k] = g.v[k] * is.v[k];
+      kb.v[k] = -ka.v[k] * is.v[k] * (b.v[k] * inv_n);
+      kc.v[k] = -ka.v[k] * (a.v[k] * inv_n) - kb.v[k] * m.v[k];
+    }
+  }
+  const long long stride = (long long)gridDim.x * rl;
+  for (long long r0 = (long long)blockIdx.x * rl + tr; r0 < V; r0 += stride * UNROLL) {
+    R dr[UNROLL], xr[UNROLL], orw[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < V) {
+        dr[u] = loadraw(dout + r * ldd + c);
+        xr[u] = loadraw(x + r * ldx + c);
+        if (relu && use_out) orw[u] = loadraw(out + r * ldo + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long r = r0 + u * stride;
+      if (r < V) {
+        const VecF<VEC> dv = unpack(dr[u]), xv = unpack(xr[u]);
+        VecF<VEC> ov, dz, y;
+        if (relu && use_out) ov = unpack(orw[u]);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          float d = dv.v[k];
+          if (relu) {
+            const float yy = use_out ? ov.v[k] : __fmaf_rn(xv.v[k], sc.v[k], sf.v[k]);
+            d = yy > 0.f ? d : 0.f;
+          }
+          dz.v[k] = d;
+          y.v[k] = ka.v[k] * d + (kb.v[k] * xv.v[k] + kc.v[k]);
+        }
+        if (dres != nullptr) storev(dres + r * lddr + c, dz);
+        storev(dx + r * lddx + c, y);
+      }
+    }
+  }
+}
+
+// can the wide kernels serve this call?  (vector width divides C and every row stride, 16-byte aligned bases,
+// at most 256 channel groups)
+static bool wide_ok(int C, int es, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
+  const int vec = 16 / es;
+  if (C % vec || C / vec > 256) return false;
+  for (long long ld : lds)
+    if (ld % vec) return false;
+  for (const void* p : ptrs)
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+  return true;
+}
+static int wide_grid(long long V, int rl, int per_sm) {
+  long long b = (V + rl - 1) / rl;
+  if (b > 148LL * per_sm) b = 148LL * per_sm;
+  return (int)(b < 1 ? 1 : b);
+}
+
 static int grid_for(long long total) {
   long long b = (total + 255) / 256;
   if (b > 148LL * 32) b = 148LL * 32;
@@ -223,6 +489,21 @@ extern "C" int coocc_bn_act_fwd(const void* x, long long ldx, long long V, int C
                                 int relu, void* out, long long ldo, int act_bf16, void* stream) {
   if (!x || !mean_invstd || !gamma || !beta || !out || (C & 3) || (ldx & 3) || (ldo & 3)) return COOCC_ERR_ARG;
   if (residual && (ldr & 3)) return COOCC_ERR_ARG;
+  if (V < 1) return 0;
+  const int es = act_bf16 ? 2 : 4;
+  if (wide_ok(C, es, {ldx, ldo, residual ? ldr : 0}, {x, out, residual})) {
+    const int cg = C / (16 / es), rl = 256 / cg;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (act_bf16)
+      bn_act_fwd_wide_kernel<__nv_bfloat16, 8, 8><<<wide_grid(V, rl * 8, 8), 256, 0, st>>>(
+          (const __nv_bfloat16*)x, ldx, V, C, mean_invstd, gamma, beta, (const __nv_bfloat16*)residual, ldr, relu,
+          (__nv_bfloat16*)out, ldo, cg, rl);
+    else
+      bn_act_fwd_wide_kernel<float, 4, 8><<<wide_grid(V, rl * 8, 8), 256, 0, st>>>(
+          (const float*)x, ldx, V, C, mean_invstd, gamma, beta, (const float*)residual, ldr, relu, (float*)out, ldo, cg,
+          rl);
+    return CK_LAUNCH();
+  }
   const int g = grid_for(V * (C >> 2));
   if (act_bf16)
     bn_act_fwd_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)stream>>>(
@@ -248,6 +529,25 @@ extern "C" int coocc_bn_act_bwd_reduce(const void* dout, long long ldd, const vo
   if (!dout || !x || !mean_invstd || !sums || (C & 3) || (ldd & 3) || (ldx & 3)) return COOCC_ERR_ARG;
   if (relu && out && (ldo & 3)) return COOCC_ERR_ARG;
   if (relu && !out && (!gamma || !beta)) return COOCC_ERR_ARG;
+  if (V < 1) return 0;
+  {
+    const int es = act_bf16 ? 2 : 4;
+    const int cg = C / (16 / es) > 0 ? C / (16 / es) : 1, rl = 256 / cg;
+    const size_t smem = (size_t)2 * (rl > 0 ? rl : 1) * C * sizeof(float);
+    if (wide_ok(C, es, {ldd, ldx, (relu && out) ? ldo : 0}, {dout, x, (relu && out) ? out : nullptr}) && smem <= 48 * 1024) {
+      cudaStream_t st = (cudaStream_t)stream;
+      const int grid = wide_grid(V, rl * 4, 4);
+      if (act_bf16)
+        bn_act_bwd_reduce_wide_kernel<__nv_bfloat16, 8, 4><<<grid, 256, smem, st>>>(
+            (const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)x, ldx, V, C,
+            mean_invstd, gamma, beta, relu, sums, cg, rl);
+      else
+        bn_act_bwd_reduce_wide_kernel<float, 4, 4><<<grid, 256, smem, st>>>(
+            (const float*)dout, ldd, (const float*)out, ldo, (const float*)x, ldx, V, C, mean_invstd, gamma, beta, relu,
+            sums, cg, rl);
+      return CK_LAUNCH();
+    }
+  }
   const int cgroups = (C / 4 + 31) / 32;
   int rows_per_block = 256;
   long long nby = (V + rows_per_block - 1) / rows_per_block;
@@ -278,8 +578,26 @@ extern "C" int coocc_bn_act_bwd_apply(const void* dout, long long ldd, const voi
   if (relu && out && (ldo & 3)) return COOCC_ERR_ARG;
   if (relu && !out && !beta) return COOCC_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int g = grid_for(V * (C >> 2));
+  if (V < 1) return 0;
   const float inv_n = (float)(1.0 / (double)count);
+  {
+    const int es = act_bf16 ? 2 : 4;
+    if (wide_ok(C, es, {ldd, ldx, lddx, (relu && out) ? ldo : 0, dres ? lddr : 0},
+                {dout, x, dx, (relu && out) ? out : nullptr, dres})) {
+      const int cg = C / (16 / es), rl = 256 / cg;
+      const int grid = wide_grid(V, rl * 4, 8);
+      if (act_bf16)
+        bn_act_bwd_apply_wide_kernel<__nv_bfloat16, 8, 4><<<grid, 256, 0, st>>>(
+            (const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)x, ldx, V, C,
+            mean_invstd, gamma, beta, sums, relu, (__nv_bfloat16*)dx, lddx, (__nv_bfloat16*)dres, lddr, inv_n, cg, rl);
+      else
+        bn_act_bwd_apply_wide_kernel<float, 4, 4><<<grid, 256, 0, st>>>(
+            (const float*)dout, ldd, (const float*)out, ldo, (const float*)x, ldx, V, C, mean_invstd, gamma, beta, sums,
+            relu, (float*)dx, lddx, (float*)dres, lddr, inv_n, cg, rl);
+      return CK_LAUNCH();
+    }
+  }
+  const int g = grid_for(V * (C >> 2));
   if (act_bf16)
     bn_act_bwd_apply_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(
         (const __nv_bfloat16*)dout, ldd, (const __nv_bfloat16*)out, ldo, (const __nv_bfloat16*)x, ldx, V, C,
