@@ -93,6 +93,67 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src
   }
 }
 
+
+// Second-generation pack (the one normally launched): 32 voxels x 128 channels per block pass -- every thread has 16
+// independent 128-byte-row loads in flight (the first version: 4) -- and, when the fast axis and the next one are
+// contiguous in memory (both upstream layouts: [C,Z,X,Y] and [C,Z,Y,X]), the two are walked as one flat axis so that
+// no tile is partly empty (200 = 6 x 32 + 8).  fast / mid / slow = spatial axes by increasing stride; a block handles
+// flat positions f0 .. f0+31 of (mid, fast) at one `slow` coordinate.
+__global__ void __launch_bounds__(256) pack_flat_kernel(const float* __restrict__ src, long long sC, long long sF,
+                                                        long long sS, int C, int nF, int nFast, int fast, int mid,
+                                                        int slow, int Y, int Z, float* __restrict__ dst, long long ldo,
+                                                        uint8_t* __restrict__ flags) {
+  __shared__ float tile[128][33];
+  __shared__ float part[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + tx;                  // this lane's flat position in the read phase
+  const long long base = (long long)blockIdx.y * sS;
+  float sum = 0.f;
+  for (int cbase = 0; cbase < C; cbase += 128) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = cbase + ty * 16 + j;
+      v[j] = (c < C && f < nF) ? src[(long long)c * sC + base + (long long)f * sF] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      tile[ty * 16 + j][tx] = v[j];
+      sum += v[j];
+    }
+    __syncthreads();
+    // write: warp ty writes voxel rows ty*4 .. ty*4+3, lane = channel (+32, +64, +96)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = ty * 4 + j;
+      const int fl = blockIdx.x * 32 + l;
+      if (fl < nF) {
+        int c3[3];
+        c3[fast] = fl % nFast;
+        c3[mid] = fl / nFast;
+        c3[slow] = blockIdx.y;
+        float* row = dst + (((long long)c3[0] * Y + c3[1]) * Z + c3[2]) * ldo + cbase;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (cbase + tx + 32 * k < C) row[tx + 32 * k] = tile[tx + 32 * k][l];
+      }
+    }
+    __syncthreads();
+  }
+  part[ty][tx] = sum;
+  __syncthreads();
+  if (ty == 0 && f < nF) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += part[j][tx];
+    int c3[3];
+    c3[fast] = f % nFast;
+    c3[mid] = f / nFast;
+    c3[slow] = blockIdx.y;
+    flags[((long long)c3[0] * Y + c3[1]) * Z + c3[2]] = t != 0.f ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // compact: ordered stream compaction of the flags (3 passes, deterministic)
 // ------------------------------------------------------------------------------------------
@@ -668,6 +729,19 @@ extern "C" int coocc_gsf_pack(const float* src, long long sC, long long sX, long
   const int dims[3] = {X, Y, Z};
   const int a_ax = (fast == 0) ? 1 : 0;
   const int b_ax = (fast == 2) ? 1 : 2;
+  {
+    // flat walk over (mid, fast) when the two axes are contiguous in memory
+    const long long st3[3] = {sX, sY, sZ};
+    const int mid = st3[a_ax] <= st3[b_ax] ? a_ax : b_ax;
+    const int slow = mid == a_ax ? b_ax : a_ax;
+    if (st3[mid] == st3[fast] * dims[fast] && dims[slow] <= 65535 && (long long)dims[mid] * dims[fast] < (1LL << 30)) {
+      const int nF = dims[mid] * dims[fast];
+      dim3 grid((nF + 31) / 32, dims[slow]);
+      pack_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, sC, st3[fast], st3[slow], C, nF, dims[fast], fast, mid,
+                                                              slow, Y, Z, dst, ldo, flags);
+      return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+    }
+  }
   if (dims[a_ax] > 65535 || dims[b_ax] > 65535) return COOCC_ERR_CAPACITY;
   dim3 grid((dims[fast] + 31) / 32, dims[a_ax], dims[b_ax]);
   pack_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, sC, sX, sY, sZ, C, X, Y, Z, fast, dst,

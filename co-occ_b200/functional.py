@@ -760,7 +760,12 @@ class _GSFusionFn(torch.autograd.Function):
         dev = cat.device
         lists, counts = state["lists"], state["counts"]
         dcat = dcat.contiguous()
-        dgrid = [dcat[:, 0:C].contiguous(), dcat[:, C:2 * C].contiguous()]     # d_img, d_pts
+        if dcat.dtype != torch.float32:
+            dcat = dcat.float()
+        # d_img / d_pts are accumulated in place in the first two column blocks of dcat (row stride 4C): the
+        # pass-through gradient of the concat is already there, the kernels add the gather / modulate terms
+        dgrid = [dcat[:, 0:C], dcat[:, C:2 * C]]
+        ldg = dcat.stride(0)
         dW = torch.zeros_like(knn_w)
         db = torch.zeros_like(knn_b)
         for name, qi, own_col, key_col, look, dst_col in plan:
@@ -773,7 +778,7 @@ class _GSFusionFn(torch.autograd.Function):
             _lib.check(L.coocc_gsf_modulate_bwd(_p(P), _p(knn_b), _p(d["winner"]), d["winner"].stride(0),
                                                 _p(lists[qi]), _pb(counts, 4 * qi), nq, nrep, K, C,
                                                 _pb(cat, own_col * C * 4), 4 * C, _pb(dcat, dst_col * C * 4), 4 * C,
-                                                _p(dgrid[own_col]), C, _p(dP), _p(db), st), "gsf_modulate_bwd")
+                                                _p(dgrid[own_col]), ldg, _p(dP), _p(db), st), "gsf_modulate_bwd")
             dF = torch.empty_like(P)
             for k in range(K):
                 # dW[:, kC:(k+1)C] += dP[k]^T @ rows[k]
@@ -783,7 +788,7 @@ class _GSFusionFn(torch.autograd.Function):
                 _lib.check(L.coocc_sgemm(nrep + 1, C, C, _p(dP[k]), C, 1, _pb(knn_w, k * C * 4), K * C, 1,
                                          _p(dF[k]), C, 0, st), "sgemm")
             _lib.check(L.coocc_gsf_scatter_rows(_p(dF), _p(lists[look]), _pb(counts, 4 * look), _p(d["topk_idx"]),
-                                                nrep, K, C, _p(dgrid[key_col]), C, st), "gsf_scatter_rows")
+                                                nrep, K, C, _p(dgrid[key_col]), ldg, st), "gsf_scatter_rows")
         d_img = to_5d(dgrid[0], (X, Y, Z))
         d_pts = to_5d(dgrid[1], (X, Y, Z))
         return d_img, d_pts, dW, db, None, None
