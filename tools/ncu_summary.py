@@ -18,13 +18,18 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-9,
          "second": 1.0, "ns": 1e-9, "us": 1e-6, "ms": 1e-3}
 
 
-def main(path):
+def main(path, top=None, traffic_json=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     print("ncu report %s: %d profiled launches" % (path, len(rows) - 2))
-    for r in rows[2:]:
+    body = rows[2:]
+    if top:       # the `top` longest launches only (a whole step has hundreds of tiny ones)
+        di = col["gpu__time_duration.sum"]
+        body = sorted(body, key=lambda r: -float(r[di].replace(",", "") or 0) * SCALE.get(units[di], 1.0))[:top]
+    traffic = []
+    for r in body:
         name = r[col["Kernel Name"]]
         print("== %s  grid %s block %s" % (name[:100], r[col.get("Grid Size", 0)], r[col.get("Block Size", 0)]))
         vals = {}
@@ -39,10 +44,27 @@ def main(path):
         rd, wr = vals.get("dram__bytes_read.sum", 0.0), vals.get("dram__bytes_write.sum", 0.0)
         if t:
             print("   duration %.1f us   DRAM read %.2f MB  write %.2f MB  -> %.0f GB/s" % (t * 1e6, rd / 1e6, wr / 1e6, (rd + wr) / t / 1e9))
+            traffic.append(dict(kernel=name[:60], us=t * 1e6, dram_read=rd, dram_write=wr))
         for k in KEYS[3:]:
             if k in vals:
                 print("   %-66s %12.2f" % (k, vals[k]))
 
 
+    if traffic_json and traffic:
+        import json
+        # launch order of tools/ncu_conv_case.py: (fwd, dgrad, wgrad) of 512->256 then of 128->128, 3x3x3, 200x200x16, bf16
+        names = ["fwd 512->256", "dgrad 512->256", "wgrad 512->256", "fwd 128->128", "dgrad 128->128", "wgrad 128->128"]
+        per = {n: t for n, t in zip(names, traffic)}
+        ref = per.get("fwd 128->128", traffic[0])
+        note = "ncu --set full, tc_conv_kernel 3x3x3 on the 200x200x16 grid, bf16 in/out, DRAM read+write MB per launch: " + \
+            "; ".join("%s %.1f (%.0f us)" % (n, (t["dram_read"] + t["dram_write"]) / 1e6, t["us"]) for n, t in per.items()) + \
+            ".  Algorithmic bytes: 128->128 327.7 MB, 512->256 983.0 MB (x read once + y written once, bf16).  `bytes` = fwd 128->128."
+        with open(traffic_json, "w") as f:
+            json.dump(dict(bytes=ref["dram_read"] + ref["dram_write"], note=note, per_launch=per), f, indent=1)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    a = sys.argv[1:]
+    top = int(a[a.index("--top") + 1]) if "--top" in a else None
+    tj = a[a.index("--traffic-json") + 1] if "--traffic-json" in a else None
+    main(a[0], top, tj)
