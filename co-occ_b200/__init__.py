@@ -15,3 +15,5 @@ from .modules import BiFuser_N, CustomResNet3D, FPN3D, MLP, OccHead, render_fn  
 from .hotpath import HotPath, model_cfg  # noqa: F401
 from .graph import GraphedStep  # noqa: F401
 from . import lss  # noqa: F401
+from . import sparse_enc  # noqa: F401
+from . import detector  # noqa: F401

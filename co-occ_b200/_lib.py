@@ -97,6 +97,10 @@ _SIGS = {
                                   c_void_p, c_void_p, c_void_p]),
     "coocc_fine_gather_labels": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p, c_void_p]),
+    "coocc_sp_flag_outputs": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "coocc_sp_neighbors": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "coocc_sp_gather_cols": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_sp_scatter_cols": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_peer_buffer_bytes": (c_ll, [c_int, c_int, c_int]),
     "coocc_peer_allreduce": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "coocc_adamw_step": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p]),

@@ -233,8 +233,10 @@ extern "C" int coocc_groupnorm_fwd(const float* x, long long ldx, long long rows
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
   const int cpg = C / G;
-  if (span == 1 && 256 % G == 0 && (cpg == 4 || cpg == 8)) {
-    if (cpg == 4) gn_rows_fwd_kernel<4><<<rows_grid(rows, G), 256, 0, st>>>(p);
+  if (span == 1 && 256 % G == 0 && (cpg == 1 || cpg == 2 || cpg == 4 || cpg == 8)) {
+    if (cpg == 1) gn_rows_fwd_kernel<1><<<rows_grid(rows, G), 256, 0, st>>>(p);
+    else if (cpg == 2) gn_rows_fwd_kernel<2><<<rows_grid(rows, G), 256, 0, st>>>(p);
+    else if (cpg == 4) gn_rows_fwd_kernel<4><<<rows_grid(rows, G), 256, 0, st>>>(p);
     else gn_rows_fwd_kernel<8><<<rows_grid(rows, G), 256, 0, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
   }
@@ -263,8 +265,10 @@ extern "C" int coocc_groupnorm_bwd(const float* x, long long ldx, long long rows
   cudaStream_t st = (cudaStream_t)stream;
   if (rows == 0) return 0;
   const int cpg = C / G;
-  if (span == 1 && 256 % G == 0 && (cpg == 4 || cpg == 8) && C <= 128) {
-    if (cpg == 4) gn_rows_bwd_kernel<4><<<rows_grid(rows, G), 256, 0, st>>>(p);
+  if (span == 1 && 256 % G == 0 && (cpg == 1 || cpg == 2 || cpg == 4 || cpg == 8) && C <= 128) {
+    if (cpg == 1) gn_rows_bwd_kernel<1><<<rows_grid(rows, G), 256, 0, st>>>(p);
+    else if (cpg == 2) gn_rows_bwd_kernel<2><<<rows_grid(rows, G), 256, 0, st>>>(p);
+    else if (cpg == 4) gn_rows_bwd_kernel<4><<<rows_grid(rows, G), 256, 0, st>>>(p);
     else gn_rows_bwd_kernel<8><<<rows_grid(rows, G), 256, 0, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
   }

@@ -338,7 +338,8 @@ class _BNActFn(torch.autograd.Function):
     """out = relu?(batchnorm_train(x) (+ residual)) from the conv-epilogue statistics."""
 
     @staticmethod
-    def forward(ctx, x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var):
+    def forward(ctx, x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var,
+                var_count=False):
         L = _lib.lib()
         V, C = x.shape
         dev = x.device
@@ -347,6 +348,10 @@ class _BNActFn(torch.autograd.Function):
         if dist is not None:
             _stats_all_reduce(dist, stats)
             count = V * dist.get_world_size()
+            if var_count:       # rows differ per rank (sparse LiDAR features): the statistics span sum_r V_r rows
+                cnt = torch.tensor([float(V)], device=dev)
+                dist.all_reduce(cnt)
+                count = int(cnt.item())
         mi = torch.empty(2, C, device=dev, dtype=torch.float32)
         _lib.check(L.coocc_bn_finalize(_p(stats), C, count, float(eps), float(momentum), _p(running_mean),
                                        _p(running_var), _p(mi), _stream()), "bn_finalize")
@@ -397,7 +402,7 @@ class _BNActFn(torch.autograd.Function):
                                                            _stream())), "bn_act_bwd_apply")
         if has_res and dres.dtype != res_dtype:
             dres = dres.to(res_dtype)
-        return dx, None, local[1], local[0], dres, None, None, None, None, None
+        return dx, None, local[1], local[0], dres, None, None, None, None, None, None
 
 
 def bn_act_eval(x, running_mean, running_var, gamma, beta, eps, residual=None, relu=True):
@@ -416,8 +421,8 @@ def bn_act_eval(x, running_mean, running_var, gamma, beta, eps, residual=None, r
 
 
 def bn_act(x, stats, gamma, beta, residual=None, relu=True, eps=1e-5, momentum=0.1, running_mean=None,
-           running_var=None):
-    return _BNActFn.apply(x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var)
+           running_var=None, var_count=False):
+    return _BNActFn.apply(x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var, var_count)
 
 
 def linear(x2d, weight, bias=None, relu=False):

@@ -35,10 +35,14 @@ class _LocalRegistry:
 try:  # pragma: no cover - exercised only where OpenMMLab is installed
     from mmdet3d.models.builder import FUSION_LAYERS  # noqa: F401
     from mmdet.models import BACKBONES, DETECTORS, HEADS, NECKS  # noqa: F401
+    try:
+        from mmdet3d.models.builder import MIDDLE_ENCODERS  # noqa: F401
+    except Exception:  # noqa: BLE001
+        MIDDLE_ENCODERS = BACKBONES
     HAVE_MMDET3D = True
 except Exception:  # noqa: BLE001
     MODELS = _LocalRegistry("models")
-    FUSION_LAYERS = BACKBONES = NECKS = HEADS = DETECTORS = MODELS
+    FUSION_LAYERS = BACKBONES = NECKS = HEADS = DETECTORS = MIDDLE_ENCODERS = MODELS
     HAVE_MMDET3D = False
 
 
@@ -56,3 +60,7 @@ def build_neck(cfg):
 
 def build_head(cfg):
     return HEADS.build(cfg)
+
+
+def build_middle_encoder(cfg):
+    return MIDDLE_ENCODERS.build(cfg)

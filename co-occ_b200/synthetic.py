@@ -289,6 +289,55 @@ def fine_head_params(seed=0):
             "fine_mlp.3.weight": r(17, 64) * 0.12, "fine_mlp.3.bias": r(17) * 0.1}
 
 
+def sparse_enc_params(input_channel=4, base=16, out_channel=128, seed=0):
+    """State dict of SparseLiDAREnc8x (sparse_lidar_enc.py:125-160) with spconv's parameter names and weight layout
+    [Cout, kz, ky, kx, Cin]; the GroupNorm biases are non-zero so that conv_input's degenerate GroupNorm(16, 16)
+    (output = relu(bias), Q13) does not zero the whole encoder."""
+    g = _gen(seed + 67)
+
+    def conv(p, name, cin, cout, bias):
+        p[name + ".weight"] = torch.randn(cout, 3, 3, 3, cin, generator=g) * math.sqrt(2.0 / (27 * cin))
+        if bias:
+            p[name + ".bias"] = torch.randn(cout, generator=g) * 0.1
+
+    def bn(p, name, c):
+        _bn(g, p, name, c)
+
+    def gn(p, name, c):
+        p[name + ".weight"] = torch.rand(c, generator=g) * 0.5 + 0.75
+        p[name + ".bias"] = torch.rand(c, generator=g) * 0.5 + 0.1
+
+    p = {}
+    conv(p, "conv_input.0", input_channel, base, True)
+    gn(p, "conv_input.1", base)
+    cin = base
+    for i, st in enumerate(("conv1", "conv2", "conv3")):
+        cout = base * 2 ** (i + 1)
+        conv(p, st + ".0.0", cin, cout, False)
+        bn(p, st + ".0.1", cout)
+        for b in (1, 2):
+            conv(p, "%s.%d.net.0" % (st, b), cout, cout, False)
+            bn(p, "%s.%d.net.1" % (st, b), cout)
+            conv(p, "%s.%d.net.3" % (st, b), cout, cout, False)
+            bn(p, "%s.%d.net.4" % (st, b), cout)
+        cin = cout
+    conv(p, "conv_out.0", cin, out_channel, True)
+    gn(p, "conv_out.1", out_channel)
+    return p
+
+
+def make_lidar_voxels(sparse_shape_xyz, n, input_channel=4, seed=0):
+    """HardSimpleVFE output: voxel_features [N, input_channel], coors [N,4] (batch, z, y, x) of N distinct voxels,
+    in the lexicographic order the voxelizer's dense scan produces."""
+    g = _gen(seed + 83)
+    W, H, D = sparse_shape_xyz
+    lin = torch.randperm(D * H * W, generator=g)[:n].sort().values
+    z, y, x = lin // (H * W), (lin // W) % H, lin % W
+    coors = torch.stack([torch.zeros_like(z), z, y, x], 1).int()
+    feats = torch.randn(n, input_channel, generator=g)
+    return feats, coors
+
+
 def make_params(name, seed=0):
     cfg = CONFIGS[name]
     C, K = cfg["C"], cfg["K"]

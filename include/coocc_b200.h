@@ -276,6 +276,27 @@ int coocc_fine_gather_labels(const int* coords, long long M, int topk, const int
                              int GX, int GY, int GZ, int ignore, int* labels, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Sparse LiDAR encoder, index side (csrc/sparse_conv.cu) -- SURVEY §8f rank 3.  Replaces, for
+ * SparseLiDAREnc8x (P/coocc/voxel_encoder/sparse_lidar_enc.py:125-177), spconv 2.3.6's rulebook construction and
+ * gather / scatter (SubMConv3d, SparseConv3d(3, stride 2, padding 1); third-party, not vendored in the reference).
+ * A sparse convolution = sp_gather_cols (explicit sparse im2col, [N_out, 27*Cin]) + coocc_conv3d_fwd as a 1x1x1
+ * convolution over N_out rows (weight [Cout, kz, ky, kx, Cin] read in place as [Cout, 27*Cin]).
+ * coords: int32 [n][4] = (batch, z, y, x), batch 0.  Offset k = (kz*3 + ky)*3 + kx.
+ * ------------------------------------------------------------------------------------------ */
+/* flags uint8 [oD*oH*oW] (zeroed by the caller) <- 1 at every output site reached by an active input */
+int coocc_sp_flag_outputs(const int* coords, int n, int stride, int pad, int oD, int oH, int oW, unsigned char* flags,
+                          void* stream);
+/* nbr int32 [n_out][27] <- row id (from grid int32 [D*H*W] of the input level, -1 = inactive) of out*stride - pad + k */
+int coocc_sp_neighbors(const int* out_coords, int n_out, int stride, int pad, const int* grid, int D, int H, int W,
+                       int* nbr, void* stream);
+/* cols [n_out][ldc] fp32, cols[o][k*C + c] = feats[nbr[o][k]][c] or 0 */
+int coocc_sp_gather_cols(const float* feats, long long ldf, int C, const int* nbr, int n_out, float* cols, long long ldc,
+                         void* stream);
+/* dfeats [n_in][ldf] += transpose of the gather (zeroed by the caller; atomics) */
+int coocc_sp_scatter_cols(const float* dcols, long long ldc, int C, const int* nbr, int n_out, float* dfeats,
+                          long long ldf, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Small all-reduce over NVLink peer memory (csrc/peer_reduce.cu): the SyncBN statistics exchange of the data-parallel
  * path.  Replaces the per-BatchNorm collectives of torch.nn.SyncBatchNorm, which the reference turns every BatchNorm
  * into (tools/train.py:222-223; all_gather in forward, all_reduce in backward) -- 72 NCCL calls of <= 8 KB per step.
