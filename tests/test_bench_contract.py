@@ -18,7 +18,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "voxels/s" and d["higher_is_better"] is True
     assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32"
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert "voxels/sec" in d["metric"] and "200x200x16" in d["config"]["workload"]
+    # the CPU arm names the grid it actually ran (the reference's own working grid) and the GPU arm's workload beside it
+    assert "voxels/sec" in d["metric"] and "100x100x8" in d["config"]["workload"]
+    assert "200x200x16" in d["config"]["gpu_arm_workload"] and d["gpus_used"] == 0 and d["cpu_baseline"]["grid"] == [100, 100, 8]
+    assert d["requested"] == {"steps": 1, "warmup": 1}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     e = d["e2e"]
