@@ -366,6 +366,235 @@ __global__ void __launch_bounds__(256) trilinear_mix_bwd_kernel(TlMix m, int oX,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Column form of the mix (the one normally launched).  One warp owns an output column (x, y, all z): for a coarse
+// level the four (x-corner, y-corner) rows of every source z it needs are combined once and shared by all output z of
+// the column -- a 2x finer column of 16 voxels needs 4 x 5 rows per 8-voxel chunk instead of 8 rows per voxel (ncu r02:
+// the per-voxel kernels above move 0.34-0.52 GB in 0.9 ms, bound by L1/L2 row gathers, not by DRAM).  Output z is
+// processed in chunks of kZC = 8; a level qualifies if it has the output's size (direct rows) or is coarse enough
+// that a chunk touches at most kMaxZS source planes (scale <= 1/2).  Weights w_l(v) and the base are applied per voxel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kZC = 8;
+constexpr int kMaxZS = 6;
+
+struct ColZ {          // z interpolation of one output voxel w.r.t. one level
+  int z0, z1;
+  float l1;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) trilinear_mix_fwd_col_kernel(TlMix m, int oX, int oY, int oZ, int C,
+                                                                    const T* __restrict__ base, long long ldb,
+                                                                    const float* __restrict__ wts, long long ldw,
+                                                                    T* __restrict__ out, long long ldo) {
+  constexpr int G = 1;
+  const int c4 = C >> 2;
+  const int nslab = (c4 + 31) / 32;                      // 128-channel slabs: a warp owns (column, slab)
+  const int ncol = oX * oY;
+  for (int item = blockIdx.x * 8 + (threadIdx.x >> 5); item < ncol * nslab; item += gridDim.x * 8) {
+    const int col = item / nslab;
+    const int lane = (threadIdx.x & 31) + 32 * (item % nslab);     // channel group of this lane (4 channels)
+    const int x = col / oY, y = col % oY;
+    for (int zb = 0; zb < oZ; zb += kZC) {
+      float4 acc[kZC][G];
+#pragma unroll
+      for (int zi = 0; zi < kZC; ++zi) {
+        const int z = zb + zi;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          acc[zi][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (base != nullptr && z < oZ && lane + 32 * g < c4)
+            acc[zi][g] = load4(base + ((long long)col * oZ + z) * ldb + (lane + 32 * g) * 4);
+        }
+      }
+      for (int l = 0; l < m.nlev; ++l) {
+        const T* src = reinterpret_cast<const T*>(m.src[l]);
+        float wl[kZC];
+#pragma unroll
+        for (int zi = 0; zi < kZC; ++zi)
+          wl[zi] = (wts != nullptr && zb + zi < oZ) ? wts[((long long)col * oZ + zb + zi) * ldw + l] : 1.f;
+        if (m.sX[l] == oX && m.sY[l] == oY && m.sZ[l] == oZ) {           // same size: the voxel's own row
+#pragma unroll
+          for (int zi = 0; zi < kZC; ++zi) {
+            if (zb + zi >= oZ) continue;
+            const T* row = src + ((long long)col * oZ + zb + zi) * m.lds[l];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              if (lane + 32 * g < c4) {
+                const float4 sv = load4(row + (lane + 32 * g) * 4);
+                acc[zi][g].x += wl[zi] * sv.x; acc[zi][g].y += wl[zi] * sv.y;
+                acc[zi][g].z += wl[zi] * sv.z; acc[zi][g].w += wl[zi] * sv.w;
+              }
+          }
+          continue;
+        }
+        int x0, x1, y0, y1;
+        float lx, ly;
+        tl_src(x, m.fx[l], m.sX[l], x0, x1, lx);
+        tl_src(y, m.fy[l], m.sY[l], y0, y1, ly);
+        ColZ cz[kZC];
+        int zlo = 1 << 30, zhi = -1;
+#pragma unroll
+        for (int zi = 0; zi < kZC; ++zi) {
+          tl_src(min(zb + zi, oZ - 1), m.fz[l], m.sZ[l], cz[zi].z0, cz[zi].z1, cz[zi].l1);
+          zlo = min(zlo, cz[zi].z0);
+          zhi = max(zhi, cz[zi].z1);
+        }
+        const long long r00 = ((long long)x0 * m.sY[l] + y0) * m.sZ[l], r01 = ((long long)x0 * m.sY[l] + y1) * m.sZ[l];
+        const long long r10 = ((long long)x1 * m.sY[l] + y0) * m.sZ[l], r11 = ((long long)x1 * m.sY[l] + y1) * m.sZ[l];
+        const float w00 = (1.f - lx) * (1.f - ly), w01 = (1.f - lx) * ly, w10 = lx * (1.f - ly), w11 = lx * ly;
+#pragma unroll
+        for (int s = 0; s < kMaxZS; ++s) {
+          const int zs = zlo + s;
+          if (zs > zhi) break;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (lane + 32 * g >= c4) continue;
+            const int co = (lane + 32 * g) * 4;
+            const float4 a = load4(src + (r00 + zs) * m.lds[l] + co), b = load4(src + (r01 + zs) * m.lds[l] + co);
+            const float4 c = load4(src + (r10 + zs) * m.lds[l] + co), d = load4(src + (r11 + zs) * m.lds[l] + co);
+            float4 r;
+            r.x = w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x;
+            r.y = w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y;
+            r.z = w00 * a.z + w01 * b.z + w10 * c.z + w11 * d.z;
+            r.w = w00 * a.w + w01 * b.w + w10 * c.w + w11 * d.w;
+#pragma unroll
+            for (int zi = 0; zi < kZC; ++zi) {
+              const float cf = wl[zi] * ((cz[zi].z0 == zs ? 1.f - cz[zi].l1 : 0.f) + (cz[zi].z1 == zs ? cz[zi].l1 : 0.f));
+              acc[zi][g].x += cf * r.x; acc[zi][g].y += cf * r.y; acc[zi][g].z += cf * r.z; acc[zi][g].w += cf * r.w;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int zi = 0; zi < kZC; ++zi) {
+        if (zb + zi >= oZ) continue;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (lane + 32 * g < c4) store4(out + ((long long)col * oZ + zb + zi) * ldo + (lane + 32 * g) * 4, acc[zi][g]);
+      }
+    }
+  }
+}
+
+
+// Backward companion in column form (same outputs as trilinear_mix_bwd_kernel): per (column, 8-voxel chunk) the
+// 8 x 4 dot products <dout[v,:], interp_l(src_l)[v,:]> are accumulated per lane and reduced across the warp with one
+// 31-shuffle transpose reduction (lane i ends up with dot i) instead of 5 shuffles per dot.  dw needs all channels of a
+// voxel in one warp, so this form is used for C <= 128.
+template <typename T>
+__global__ void __launch_bounds__(256) trilinear_mix_bwd_col_kernel(TlMix m, int oX, int oY, int oZ, int C,
+                                                                    const T* __restrict__ dout, long long ldd,
+                                                                    const float* __restrict__ wts, long long ldw,
+                                                                    float* __restrict__ dw, long long lddw) {
+  const int lane = threadIdx.x & 31;
+  const int c4 = C >> 2;
+  const bool act = lane < c4;
+  const int ncol = oX * oY;
+  for (int col = blockIdx.x * 8 + (threadIdx.x >> 5); col < ncol; col += gridDim.x * 8) {
+    const int x = col / oY, y = col % oY;
+    for (int zb = 0; zb < oZ; zb += kZC) {
+      float4 g4[kZC];
+#pragma unroll
+      for (int zi = 0; zi < kZC; ++zi)
+        g4[zi] = (act && zb + zi < oZ) ? load4(dout + ((long long)col * oZ + zb + zi) * ldd + lane * 4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      float dots[kZC * kTlLevels];
+#pragma unroll
+      for (int i = 0; i < kZC * kTlLevels; ++i) dots[i] = 0.f;
+#pragma unroll
+      for (int l = 0; l < kTlLevels; ++l) {
+        if (l >= m.nlev) continue;
+        const T* src = reinterpret_cast<const T*>(m.src[l]);
+        const bool same = m.sX[l] == oX && m.sY[l] == oY && m.sZ[l] == oZ;
+        if (m.dsrc[l] != nullptr) {                 // same-size level: d src = w_l(v) * dout
+#pragma unroll
+          for (int zi = 0; zi < kZC; ++zi) {
+            if (!act || zb + zi >= oZ) continue;
+            const long long v = (long long)col * oZ + zb + zi;
+            const float wl = wts ? wts[v * ldw + l] : 1.f;
+            store4(reinterpret_cast<T*>(m.dsrc[l]) + v * m.lds[l] + lane * 4,
+                   make_float4(wl * g4[zi].x, wl * g4[zi].y, wl * g4[zi].z, wl * g4[zi].w));
+          }
+        }
+        if (dw == nullptr) continue;
+        if (same) {
+#pragma unroll
+          for (int zi = 0; zi < kZC; ++zi) {
+            if (!act || zb + zi >= oZ) continue;
+            const float4 sv = load4(src + ((long long)col * oZ + zb + zi) * m.lds[l] + lane * 4);
+            dots[zi * kTlLevels + l] = sv.x * g4[zi].x + sv.y * g4[zi].y + sv.z * g4[zi].z + sv.w * g4[zi].w;
+          }
+          continue;
+        }
+        int x0, x1, y0, y1;
+        float lx, ly;
+        tl_src(x, m.fx[l], m.sX[l], x0, x1, lx);
+        tl_src(y, m.fy[l], m.sY[l], y0, y1, ly);
+        ColZ cz[kZC];
+        int zlo = 1 << 30, zhi = -1;
+#pragma unroll
+        for (int zi = 0; zi < kZC; ++zi) {
+          tl_src(min(zb + zi, oZ - 1), m.fz[l], m.sZ[l], cz[zi].z0, cz[zi].z1, cz[zi].l1);
+          zlo = min(zlo, cz[zi].z0);
+          zhi = max(zhi, cz[zi].z1);
+        }
+        const long long r00 = ((long long)x0 * m.sY[l] + y0) * m.sZ[l], r01 = ((long long)x0 * m.sY[l] + y1) * m.sZ[l];
+        const long long r10 = ((long long)x1 * m.sY[l] + y0) * m.sZ[l], r11 = ((long long)x1 * m.sY[l] + y1) * m.sZ[l];
+        const float w00 = (1.f - lx) * (1.f - ly), w01 = (1.f - lx) * ly, w10 = lx * (1.f - ly), w11 = lx * ly;
+#pragma unroll
+        for (int s2 = 0; s2 < kMaxZS; ++s2) {
+          const int zs = zlo + s2;
+          if (zs > zhi || !act) break;
+          const int co = lane * 4;
+          const float4 a = load4(src + (r00 + zs) * m.lds[l] + co), b = load4(src + (r01 + zs) * m.lds[l] + co);
+          const float4 c = load4(src + (r10 + zs) * m.lds[l] + co), d = load4(src + (r11 + zs) * m.lds[l] + co);
+          float4 r;
+          r.x = w00 * a.x + w01 * b.x + w10 * c.x + w11 * d.x;
+          r.y = w00 * a.y + w01 * b.y + w10 * c.y + w11 * d.y;
+          r.z = w00 * a.z + w01 * b.z + w10 * c.z + w11 * d.z;
+          r.w = w00 * a.w + w01 * b.w + w10 * c.w + w11 * d.w;
+#pragma unroll
+          for (int zi = 0; zi < kZC; ++zi) {
+            const float cf = (cz[zi].z0 == zs ? 1.f - cz[zi].l1 : 0.f) + (cz[zi].z1 == zs ? cz[zi].l1 : 0.f);
+            dots[zi * kTlLevels + l] += cf * (r.x * g4[zi].x + r.y * g4[zi].y + r.z * g4[zi].z + r.w * g4[zi].w);
+          }
+        }
+      }
+      if (dw != nullptr) {
+        // transpose reduction: after the five steps lane i holds the warp total of dots[i]
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float send = up ? dots[i] : dots[i + off];
+            const float keep = up ? dots[i + off] : dots[i];
+            dots[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        const int zi = lane / kTlLevels, l = lane % kTlLevels;
+        if (l < m.nlev && zb + zi < oZ) dw[((long long)col * oZ + zb + zi) * lddw + l] = dots[0];
+      }
+    }
+  }
+}
+
+// can the column kernels serve this mix?  every level same-size or at most half the output's z resolution
+static bool mix_col_ok(const TlMix& m, int oX, int oY, int oZ) {
+  for (int l = 0; l < m.nlev; ++l) {
+    const bool same = m.sX[l] == oX && m.sY[l] == oY && m.sZ[l] == oZ;
+    if (!same && 2 * m.sZ[l] > oZ) return false;
+  }
+  return true;
+}
+static int mix_col_grid(int oX, int oY) {
+  long long b = ((long long)oX * oY + 7) / 8;
+  if (b > 148LL * 8) b = 148LL * 8;
+  return b < 1 ? 1 : (int)b;
+}
+
 static TlDims make_dims(int sX, int sY, int sZ, int oX, int oY, int oZ) {
   TlDims d;
   d.sX = sX; d.sY = sY; d.sZ = sZ; d.oX = oX; d.oY = oY; d.oZ = oZ;
@@ -428,10 +657,12 @@ static int trilinear_bwd_separable(const T* dout, long long ldd, int oX, int oY,
   return rc;
 }
 
-static int g_tl_separable = 1;
-/* benchmark hook: 0 = direct transposed gather, 1 = separable passes (default) */
-extern "C" int coocc_trilinear_tune(int separable) {
-  g_tl_separable = separable ? 1 : 0;
+static int g_tl_separable = 1, g_tl_column = 1;
+/* benchmark hook: bit 0: 0 = direct transposed gather, 1 = separable passes (default); bit 1 set = per-voxel mix
+ * kernels instead of the column form */
+extern "C" int coocc_trilinear_tune(int flags) {
+  g_tl_separable = (flags & 1) ? 1 : 0;
+  g_tl_column = (flags & 2) ? 0 : 1;
   return 0;
 }
 
@@ -513,6 +744,16 @@ extern "C" int coocc_trilinear_mix_fwd(int nlev, const void* const* src, const l
   TlMix m;
   int rc = fill_mix(m, nlev, src, lds, sdims, oX, oY, oZ);
   if (rc) return rc;
+  if (g_tl_column && m.nlev >= 2 && mix_col_ok(m, oX, oY, oZ)) {      // (a single coarse level gains nothing)
+    const int g = mix_col_grid(oX, oY * (((C >> 2) + 31) / 32));
+    if (act_bf16)
+      trilinear_mix_fwd_col_kernel<bf16_t><<<g, 256, 0, (cudaStream_t)stream>>>(m, oX, oY, oZ, C, (const bf16_t*)base, ldb,
+                                                                              wts, ldw, (bf16_t*)out, ldo);
+    else
+      trilinear_mix_fwd_col_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(m, oX, oY, oZ, C, (const float*)base, ldb,
+                                                                             wts, ldw, (float*)out, ldo);
+    return CK_LAUNCH();
+  }
   const int g = mix_grid(oX, oY);
   if (act_bf16)
     TL_DISPATCH_G(trilinear_mix_fwd_kernel, bf16_t, m, oX, oY, oZ, C, (const bf16_t*)base, ldb, wts, ldw, (bf16_t*)out,
@@ -536,6 +777,17 @@ extern "C" int coocc_trilinear_mix_bwd(int nlev, const void* const* src, const l
       if (dsrc_same[l] && (m.sX[l] != oX || m.sY[l] != oY || m.sZ[l] != oZ)) return COOCC_ERR_ARG;
       m.dsrc[l] = dsrc_same[l];
     }
+  static_assert(kZC * kTlLevels == 32, "the transpose reduction maps one dot product to every lane");
+  if (g_tl_column && m.nlev >= 2 && mix_col_ok(m, oX, oY, oZ) && (C >> 2) <= 32) {
+    const int g = mix_col_grid(oX, oY);
+    if (act_bf16)
+      trilinear_mix_bwd_col_kernel<bf16_t><<<g, 256, 0, (cudaStream_t)stream>>>(m, oX, oY, oZ, C, (const bf16_t*)dout, ldd,
+                                                                              wts, ldw, dw, lddw);
+    else
+      trilinear_mix_bwd_col_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(m, oX, oY, oZ, C, (const float*)dout, ldd,
+                                                                             wts, ldw, dw, lddw);
+    return CK_LAUNCH();
+  }
   const int g = mix_grid(oX, oY);
   if (act_bf16)
     TL_DISPATCH_G(trilinear_mix_bwd_kernel, bf16_t, m, oX, oY, oZ, C, (const bf16_t*)dout, ldd, wts, ldw, dw, lddw);
