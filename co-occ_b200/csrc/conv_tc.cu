@@ -91,6 +91,13 @@ struct TcParams {
   int ny, nyb;         // y rows per 128-pixel block (128 / Z), y blocks per x (ceil(Y / ny))
   int ext_bytes;       // bytes of one extended tile ((ny + 2) * Z rows of 128 B, rounded to 1 KiB)
   int NA, NB;          // ring depths: extended A tiles (MT per entry), B tiles
+  // parity-class launch of a stride-2 data gradient (dgrad_impl, `cls`): an explicit tap list -- im2col offsets and
+  // weight taps are no longer tied to each other -- and output rows scattered to the fine grid
+  int tapmode;                       // 1: tap t reads im2col offset tap_off[t] and weight tap tap_w[t]
+  unsigned char tap_off[8];          // kx | ky << 2 | kz << 4   (offsets 0 / 1)
+  unsigned char tap_w[8];            // (kx * 3 + ky) * 3 + kz of the weight tensor
+  int omap;                          // 1: output row (i, j, k) of the coarse grid -> fine voxel (2i+opx, 2j+opy, 2k+opz)
+  int opx, opy, opz, fX, fY, fZ;
 };
 
 template <int ES> struct Elt {
@@ -289,10 +296,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           const int tap = wgrad ? wg_tap * p.NT : it / kb_per_tap;    // wgrad: first tap of the group
           const int kb = wgrad ? it : it % kb_per_tap;
           // filter offsets of this tap in the im2col operand (W<->z, H<->y, D<->x)
-          const int kx = (p.taps == 1) ? 0 : tap / 9, ky = (p.taps == 1) ? 0 : (tap / 3) % 3,
-                    kz = (p.taps == 1) ? 0 : tap % 3;
+          int kx = (p.taps == 1) ? 0 : tap / 9, ky = (p.taps == 1) ? 0 : (tap / 3) % 3,
+              kz = (p.taps == 1) ? 0 : tap % 3;
           // dgrad walks the mirrored tap of the weight tensor
-          const int wtap = (p.mode == MODE_DGRAD) ? (p.taps - 1 - tap) : tap;
+          int wtap = (p.mode == MODE_DGRAD) ? (p.taps - 1 - tap) : tap;
+          if (p.tapmode) {
+            const int o = p.tap_off[tap];
+            kx = o & 3; ky = (o >> 2) & 3; kz = (o >> 4) & 3;
+            wtap = p.tap_w[tap];
+          }
           {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * stage_bytes;
@@ -535,6 +547,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       if (wgrad && wtap >= p.taps) continue;
       int row = (mt * p.MT + hh) * kBM + q * 32 + lane;
       bool row_ok = row < p.M;
+      if (p.omap && row_ok) {
+        const int z = row % p.oZ, t = row / p.oZ;
+        const int y = t % p.oY, x = t / p.oY;
+        const int fx = 2 * x + p.opx, fy = 2 * y + p.opy, fz = 2 * z + p.opz;
+        row_ok = fx < p.fX && fy < p.fY && fz < p.fZ;
+        row = (fx * p.fY + fy) * p.fZ + fz;
+      }
       if (p.ky && !wgrad) {
         // block (x, yb): 128 consecutive pixels of x row `x` starting at yb * 128
         const int mb = mt * p.MT + hh;
@@ -1132,11 +1151,83 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, void
 // dX[v, ci] = sum_{tap,co} dY[v - tap + pad, co] W[co, tap, ci]; stride-1 convolutions only
 // (for stride 2 the caller scatters dY onto the input lattice first, see conv3d_dgrad docs).
 static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, void* dxv, long long ldo,
-                      int accum, void* stream) {
+                      int accum, void* stream, int cls = -1) {
   int rc = check_desc(d);
   if (rc) return rc;
-  if (d->stride != 1) return COOCC_ERR_ARG;
+  if ((d->stride != 1) != (cls >= 0)) return COOCC_ERR_ARG;
   if ((rc = init_driver_api())) return rc;
+  if (cls >= 0) {
+    // Stride-2 data gradient, parity class cls = px*4 + py*2 + pz of the fine grid (d->X/Y/Z):
+    //   dx[2i + p] = sum_t dy[(2i + p + 1 - t) / 2] W_t  over the taps t of matching parity, per axis
+    //     p = 0: t = 1 (dy[i]);   p = 1: t = 2 (dy[i]) and t = 0 (dy[i + 1])      (3x3x3, padding 1)
+    //     1x1x1: class 0 only, dx[2i] = dy[i] W_0
+    // i.e. a small convolution of dy on its own (coarse) grid with 1 / 2 / 4 / 8 of the 27 taps whose output rows
+    // are the class's voxels of dx: the eight classes together do the forward's FLOPs, where zero insertion
+    // (coocc_dilate2 + a stride-1 dgrad, round 1) did eight times as many.
+    const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
+    const int ch = 128 / es;
+    const int px = (cls >> 2) & 1, py = (cls >> 1) & 1, pz = cls & 1;
+    if (d->ksize == 1 && cls != 0) return COOCC_ERR_ARG;
+    const int oX = out_dim(d->X, d->ksize, 2), oY = out_dim(d->Y, d->ksize, 2), oZ = out_dim(d->Z, d->ksize, 2);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = MODE_DGRAD;
+    p.M = oX * oY * oZ;
+    p.N = d->Cin;
+    p.BN = ((d->Cin + ch - 1) / ch) * ch;
+    if (p.BN > kMaxBN) {
+      p.BN = kMaxBN;
+      for (int t = 256; t >= ch; t -= ch)
+        if (d->Cin % t == 0) { p.BN = t; break; }
+    }
+    p.tapmode = 1;
+    int nt = 0;
+    if (d->ksize == 1) {
+      p.tap_off[0] = 0; p.tap_w[0] = 0; nt = 1;
+    } else {
+      const int par[3] = {px, py, pz};
+      int offs[3][2], wts[3][2], cnt[3];
+      for (int a = 0; a < 3; ++a) {
+        if (par[a] == 0) { cnt[a] = 1; offs[a][0] = 0; wts[a][0] = 1; }
+        else { cnt[a] = 2; offs[a][0] = 0; wts[a][0] = 2; offs[a][1] = 1; wts[a][1] = 0; }
+      }
+      for (int a = 0; a < cnt[0]; ++a)
+        for (int b = 0; b < cnt[1]; ++b)
+          for (int c = 0; c < cnt[2]; ++c) {
+            p.tap_off[nt] = (unsigned char)(offs[0][a] | (offs[1][b] << 2) | (offs[2][c] << 4));
+            p.tap_w[nt] = (unsigned char)((wts[0][a] * 3 + wts[1][b]) * 3 + wts[2][c]);
+            ++nt;
+          }
+    }
+    p.taps = nt;
+    p.Kc = d->Cout;
+    p.Cin = d->Cin;
+    p.oX = oX; p.oY = oY; p.oZ = oZ;
+    p.cstride = 1;
+    p.lo = 0;
+    p.omap = 1; p.opx = px; p.opy = py; p.opz = pz; p.fX = d->X; p.fY = d->Y; p.fZ = d->Z;
+    p.out = reinterpret_cast<float*>(dxv); p.ldc = ldo; p.accum = accum;
+    p.out_bf16 = d->out_bf16 ? 1 : 0;
+    if (p.out_bf16 && accum) return COOCC_ERR_ARG;
+    p.es = es;
+    const int wtaps = d->ksize == 3 ? 27 : 1;
+    if (d->ksize == 1) {
+      p.a_im2col = 0;
+      rc = make_tm_2d(&p.tmA, dy, es, p.M, d->Cout, d->ldy, ch, kBM, false);
+    } else {
+      p.a_im2col = 1;
+      rc = make_tm_im2col(&p.tmA, dy, es, oX, oY, oZ, d->Cout, d->ldy, 0, 0, 1, ch, kBM, false);
+    }
+    if (rc) return rc;
+    rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)wtaps * d->Cin, (long long)wtaps * d->Cin, ch, ch, true);
+    if (rc) return rc;
+    if ((rc = prepare_split(p, nt * ((d->Cout + ch - 1) / ch), (cudaStream_t)stream, false))) return rc;
+    p.ksplit = 1;            // (split-K accumulates into a contiguous zeroed [M, N] block; the class rows are scattered)
+    p.mc = 0;
+    const int ntm_ = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
+    const int ntiles = ntm_ * ((p.N + p.BN - 1) / p.BN);
+    return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+  }
   const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
   const int taps = d->ksize == 3 ? 27 : 1;
   const int ch = 128 / es;
@@ -1405,9 +1496,38 @@ extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const v
 extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, void* dx,
                                   long long ldo, void* stream) {
   if (!d) return COOCC_ERR_ARG;
-  if (d->dtype != COOCC_DTYPE_TF32X3) return dgrad_impl(d, dy, w, dx, ldo, 0, stream);
   cudaStream_t st = (cudaStream_t)stream;
   const int taps = d->ksize == 3 ? 27 : 1;
+  if (d->stride == 2) {
+    // d->X/Y/Z = the (fine) input grid, dy lives on the strided output grid: one launch per parity class
+    const int ncls = d->ksize == 3 ? 8 : 1;
+    const long long Vf = (long long)d->X * d->Y * d->Z;
+    const long long Vo = (long long)out_dim(d->X, d->ksize, 2) * out_dim(d->Y, d->ksize, 2) * out_dim(d->Z, d->ksize, 2);
+    int rc = 0;
+    if (d->ksize == 1) {       // only the even voxels receive a gradient
+      const size_t eb = d->out_bf16 ? 2 : 4;
+      if (cudaMemset2DAsync(dx, (size_t)ldo * eb, 0, (size_t)d->Cin * eb, (size_t)Vf, st) != cudaSuccess) return COOCC_ERR_CUDA;
+    }
+    if (d->dtype != COOCC_DTYPE_TF32X3) {
+      for (int c = 0; c < ncls && !rc; ++c) rc = dgrad_impl(d, dy, w, dx, ldo, 0, stream, c);
+      return rc;
+    }
+    SplitBuf gs, ws;
+    rc = split_rows(dy, d->ldy, Vo, d->Cout, &gs, st);
+    if (!rc) rc = split_rows(w, (long long)taps * d->Cin, d->Cout, taps * d->Cin, &ws, st);
+    coocc_conv_desc t = *d;
+    t.dtype = COOCC_DTYPE_TF32;
+    t.ldy = gs.ld;
+    for (int c = 0; c < ncls && !rc; ++c) {
+      rc = dgrad_impl(&t, gs.hi, ws.hi, dx, ldo, 0, stream, c);
+      if (!rc) rc = dgrad_impl(&t, gs.hi, ws.lo, dx, ldo, 1, stream, c);
+      if (!rc) rc = dgrad_impl(&t, gs.lo, ws.hi, dx, ldo, 1, stream, c);
+    }
+    split_free(&gs, st);
+    split_free(&ws, st);
+    return rc;
+  }
+  if (d->dtype != COOCC_DTYPE_TF32X3) return dgrad_impl(d, dy, w, dx, ldo, 0, stream);
   SplitBuf gs, ws;
   int rc = split_rows(dy, d->ldy, (long long)d->X * d->Y * d->Z, d->Cout, &gs, st);
   if (!rc) rc = split_rows(w, (long long)taps * d->Cin, d->Cout, taps * d->Cin, &ws, st);

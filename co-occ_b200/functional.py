@@ -269,16 +269,6 @@ class _Conv3dFn(torch.autograd.Function):
                 # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
                 dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
         if ctx.needs_input_grad[0]:
-            if s != 1:
-                # scatter dy onto the input lattice (even positions), then a stride-1 dgrad
-                X, Y, Z = dims
-                dy_in = torch.empty(X * Y * Z, dyo.stride(0), device=dy.device, dtype=dyo.dtype)
-                _lib.check(L.coocc_dilate2(_p(dyo), dyo.stride(0), odims[0], odims[1], odims[2], dyo.stride(0),
-                                           _p(dy_in), dy_in.stride(0), X, Y, Z, 1 if dtype == DT_BF16 else 0,
-                                           _stream()), "dilate2")
-                dy_in = dy_in[:, :cout]
-            else:
-                dy_in = dyo
             # the data gradient is written in the storage type of x (bf16 activations stay bf16)
             if ctx.x_bf16 and dtype == DT_BF16:
                 ldo = (cin + 7) // 8 * 8
@@ -286,10 +276,12 @@ class _Conv3dFn(torch.autograd.Function):
             else:
                 ldo = (cin + 3) // 4 * 4
                 dxb = torch.empty(dims[0] * dims[1] * dims[2], ldo, device=dy.device, dtype=torch.float32)
-            d = _conv_desc(dims, cin, cout, k, 1, ldo, dy_in.stride(0), dtype)
+            # stride 2: the kernel runs one launch per parity class of the input lattice (csrc/conv_tc.cu dgrad_impl,
+            # `cls`) -- the forward's FLOPs; round 1 zero-inserted dy (coocc_dilate2) and paid eight times as many
+            d = _conv_desc(dims, cin, cout, k, s, ldo, dyo.stride(0), dtype)
             d.out_bf16 = _is_bf16(dxb)
             flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
-            _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dy_in), _p(wo), _p(dxb),
+            _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dyo), _p(wo), _p(dxb),
                                                                           dxb.stride(0), _stream()),
                               " %s %d->%d k%d s%d" % (dims, cin, cout, k, s)), "conv3d_dgrad")
             dx = dxb[:, :cin]

@@ -61,9 +61,11 @@ typedef struct coocc_conv_desc {
 int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, void* y, long long ldo,
                      const float* bias, int relu, float* stats, void* stream);
 
-/* dx[v, ci] (fp32 or bf16 per d->out_bf16, row stride ldo) for a stride-1 convolution; dy has the conv's output extent
- * (= input extent).  Strided convolutions: scatter dy onto the input lattice with
- * coocc_dilate2 first and call this with stride = 1. */
+/* dx[v, ci] (fp32 or bf16 per d->out_bf16, row stride ldo) over the convolution's INPUT grid d->X/Y/Z; dy has the
+ * conv's output extent.  stride 1: one launch.  stride 2: one launch per parity class of the input lattice (8 for
+ * 3x3x3, 1 + a zero fill for 1x1x1), each a small convolution of dy on its own grid with the taps of matching parity
+ * whose output rows are scattered to the class's voxels -- the forward's FLOPs (zero insertion with coocc_dilate2 + a
+ * stride-1 call, the round-1 route, multiplies eight times as many zeros). */
 int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, void* dx, long long ldo,
                        void* stream);
 
