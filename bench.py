@@ -395,9 +395,11 @@ def run_ours(args, cfg):
         o.zero_grad(set_to_none=True)
         reducer.begin()
         CF.begin_step()
+        CF.zero_pool_begin(dev)
         losses, _, _ = call(model.forward_train, d)
         loss = sum(losses[k] for k in LOSS_KEYS)
         loss.backward()
+        CF.zero_pool_end()
         reducer.finish()
         o.step()
         return loss

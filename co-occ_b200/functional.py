@@ -223,7 +223,7 @@ class _Conv3dFn(torch.autograd.Function):
         # operands in their storage type (bf16 mode: converted once here and kept for backward)
         xo = _operand(_as_rows(x2d), dtype)
         wo = weight_operand(w5d, dtype)
-        stats = torch.zeros(2, cout, device=x2d.device, dtype=torch.float32) if want_stats else None
+        stats = zeros_small((2, cout), x2d.device) if want_stats else None
         y, odims = conv_fwd_raw(xo, wo, dims, cin, cout, k, s, bias, relu, stats=stats, dtype=dtype,
                                 out_bf16=out_bf16)
         ctx.save_for_backward(xo, wo, y if relu else None)
@@ -319,6 +319,41 @@ def begin_step():
         PEER.begin_step()
 
 
+# One pre-zeroed pool per step for the many small accumulators the kernels add into (BatchNorm statistics [2,C] of every
+# conv epilogue, the [2,C] backward sums): ~80 torch.zeros() fill launches per step become one.  The step runner
+# (graph.GraphedStep, bench.py) brackets a step with zero_pool_begin() -- a device memset, so it must sit INSIDE a
+# captured graph -- and zero_pool_end(); outside such a bracket zeros_small() is plain torch.zeros().
+_ZERO_POOL = {"buf": None, "cursor": 0, "armed": False}
+ZERO_POOL_FLOATS = 1 << 19          # 2 MB
+
+
+def zero_pool_begin(device):
+    zp = _ZERO_POOL
+    if zp["buf"] is None or zp["buf"].device != torch.device(device):
+        zp["buf"] = torch.zeros(ZERO_POOL_FLOATS, device=device, dtype=torch.float32)
+    else:
+        zp["buf"].zero_()
+    zp["cursor"], zp["armed"] = 0, True
+
+
+def zero_pool_end():
+    _ZERO_POOL["armed"] = False
+
+
+def zeros_small(shape, device):
+    """zero-initialised fp32 tensor for a kernel to accumulate into (16-byte aligned)"""
+    zp = _ZERO_POOL
+    n = 1
+    for v in shape:
+        n *= int(v)
+    n4 = (n + 3) // 4 * 4
+    if zp["armed"] and zp["buf"].device == torch.device(device) and zp["cursor"] + n4 <= ZERO_POOL_FLOATS:
+        t = zp["buf"][zp["cursor"]:zp["cursor"] + n].view(*shape)
+        zp["cursor"] += n4
+        return t
+    return torch.zeros(*shape, device=device, dtype=torch.float32)
+
+
 def _stats_all_reduce(dist, t):
     if PEER is not None and PEER.fits(t):
         PEER.all_reduce(t)
@@ -373,7 +408,7 @@ class _BNActFn(torch.autograd.Function):
         V, C = x.shape
         dout = _as_rows(dout, x.dtype)
         bf = _is_bf16(x)
-        sums = torch.zeros(2, C, device=x.device, dtype=torch.float32)
+        sums = zeros_small((2, C), x.device)
         ldo = out.stride(0) if out is not None else 0
         e = x.element_size()
         _lib.check(_timed("hbm:bn_act_bwd_reduce", float(e * V * C * (3 if out is not None else 2)),

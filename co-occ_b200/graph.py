@@ -71,9 +71,13 @@ class GraphedStep:
         if self.reducer is not None:
             self.reducer.begin()
         CF.begin_step()
-        losses, _, _ = self.model.forward_train(img, pts, geom, gt_depth, gt_img, gt_occ, img_feats, transform)
-        loss = self._loss(losses)
-        loss.backward()
+        CF.zero_pool_begin(img.device)
+        try:
+            losses, _, _ = self.model.forward_train(img, pts, geom, gt_depth, gt_img, gt_occ, img_feats, transform)
+            loss = self._loss(losses)
+            loss.backward()
+        finally:
+            CF.zero_pool_end()
         if self.reducer is not None:
             self.reducer.finish()
         if self.opt is not None:
@@ -201,10 +205,12 @@ class GraphedStep:
             _dbg("capture begin key=%s" % (key,))
             # thread_local: NCCL's watchdog / heartbeat threads query events while this thread captures
             with torch.cuda.graph(g, stream=self._stream, capture_error_mode="thread_local"):
+                CF.zero_pool_begin(img.device)          # (a memset node: every replay starts from a clean pool)
                 losses, _, _ = self.model.forward_train(img, pts, s["geom"], s["gt_depth"], s["gt_img"], s["gt_occ"],
                                                         s["img_feats"], self._static_transform())
                 loss = self._loss(losses)
                 loss.backward()
+                CF.zero_pool_end()
                 if self.reducer is not None:
                     self.reducer.finish()
                 if self.opt is not None:
@@ -213,6 +219,7 @@ class GraphedStep:
         finally:
             CF.GSF_OVERRIDE = None
             CF.DEFERRED_ERRORS = None
+            CF.zero_pool_end()
         _dbg("capture end")
         entry = dict(graph=g, loss=loss, launches=_lib.CALLS["n"] - n0, deferred=deferred)
         self.launches_per_replay = entry["launches"]
