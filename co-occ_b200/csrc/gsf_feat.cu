@@ -175,6 +175,91 @@ __global__ void __launch_bounds__(128) modulate_bwd_kernel(const float* __restri
     if (sb[c] != 0.f) atomicAdd(&dbias[c], sb[c]);
 }
 
+
+// Run-aggregating variant (the one normally launched, C <= 128, K <= 4): a warp walks kRun consecutive queries and keeps
+// the dP contribution of the current representative of every k in registers, flushing with atomics only when the
+// representative changes.  Queries are ordered by voxel id, so neighbours along z share their representative (each
+// serves a radius-6 ball): the first version issued K atomics per (query, channel) into <= 2049 rows per k -- 98 M
+// atomics on the 200x200x16 grid, 1.16 ms (ncu r02) -- this one a tenth of that.  dbias is summed in registers.
+constexpr int kModRun = 16;
+__global__ void __launch_bounds__(128) modulate_bwd_run_kernel(const float* __restrict__ P,
+                                                               const float* __restrict__ bias,
+                                                               const int* __restrict__ winner, int nq_stride,
+                                                               const int* __restrict__ qlist,
+                                                               const int* __restrict__ qcount, int nrep, int K, int C,
+                                                               const float* __restrict__ own, long long ld_own,
+                                                               const float* __restrict__ g, long long ld_g,
+                                                               float* __restrict__ d_own, long long ld_down,
+                                                               float* __restrict__ dP, float* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31;
+  const int n = *qcount;
+  const int nj = (C + 31) / 32;                 // channels per lane (<= 4)
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  float bia[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bia[j] = (j < nj && lane + 32 * j < C) ? bias[lane + 32 * j] : 0.f;
+  const int nwarps = gridDim.x * 4;
+  for (int q0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * kModRun; q0 < n; q0 += nwarps * kModRun) {
+    int cur[4] = {-1, -1, -1, -1};
+    float acc[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+    const int q1 = min(n, q0 + kModRun);
+    for (int q = q0; q < q1; ++q) {
+      const long long v = qlist[q];
+      int w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        w[k] = -1;
+        if (k < K) {
+          w[k] = winner[k * nq_stride + q];
+          if (w[k] < 0) w[k] = nrep;
+          if (w[k] != cur[k]) {                        // representative changed: flush the finished run
+            if (cur[k] >= 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < nj && lane + 32 * j < C && acc[k][j] != 0.f)
+                  atomicAdd(&dP[((long long)k * (nrep + 1) + cur[k]) * C + lane + 32 * j], acc[k][j]);
+            }
+            cur[k] = w[k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * j;
+        if (j >= nj || c >= C) continue;
+        float sv = bia[j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < K) sv += P[((long long)k * (nrep + 1) + w[k]) * C + c];
+        const float gv = g[v * ld_g + c];
+        d_own[v * ld_down + c] += gv * fmaxf(sv, 0.f);
+        const float ds = sv > 0.f ? gv * own[v * ld_own + c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < K) acc[k][j] += ds;
+        bsum[j] += ds;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < K && cur[k] >= 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nj && lane + 32 * j < C && acc[k][j] != 0.f)
+            atomicAdd(&dP[((long long)k * (nrep + 1) + cur[k]) * C + lane + 32 * j], acc[k][j]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < nj && lane + 32 * j < C && bsum[j] != 0.f) atomicAdd(&dbias[lane + 32 * j], bsum[j]);
+}
+
 // d_grid[ lookup[idx(r,k)] ][:] += dF[k][r][:]   (duplicates across r, k -> atomics)
 __global__ void __launch_bounds__(128) scatter_rows_kernel(const float* __restrict__ dF,
                                                            const int* __restrict__ lookup,
@@ -269,6 +354,13 @@ extern "C" int coocc_gsf_modulate_bwd(const float* P, const float* bias, const i
   if (!P || !bias || !winner || !qlist || !qcount || !own || !g || !d_own || !dP || !dbias || nq_max < 1 ||
       K < 1 || K > 8)
     return COOCC_ERR_ARG;
+  if (C <= 128 && K <= 4) {
+    int blocks = (nq_max + 4 * kModRun - 1) / (4 * kModRun);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    modulate_bwd_run_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(P, bias, winner, nq_stride, qlist, qcount, nrep, K, C,
+                                                                     own, ld_own, g, ld_g, d_own, ld_down, dP, dbias);
+    return CK_LAUNCH();
+  }
   int blocks = (nq_max + 3) / 4;
   if (blocks > 148 * 8) blocks = 148 * 8;
   modulate_bwd_kernel<<<blocks, 128, C * sizeof(float), (cudaStream_t)stream>>>(
