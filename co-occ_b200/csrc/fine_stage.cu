@@ -4,6 +4,7 @@
 // reference fixture (tests/test_gpu_fine.py).  GroupNorm additionally has CUDA-only kernels below (same formulas):
 // the generic one-item-per-thread bodies serialise the per-channel dgamma / dbeta atomics of 10^5 point rows.
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 #include "../../include/coocc_b200.h"
 #include "fine_stage.cuh"
@@ -185,8 +186,9 @@ extern "C" int coocc_fine_sample3d_fwd(const float* feats, long long ld, int X, 
 
 extern "C" int coocc_fine_sample3d_bwd(const float* gout, long long ldg, int X, int Y, int Z, int C, const int* coords,
                                        int M, int SX, int SY, int SZ, float* dfeats, long long ldd, void* stream) {
-  if (!gout || !coords || !dfeats || C < 4 || (C & 3) || (ldg & 3) || M < 0 || SX < 2 || SY < 2 || SZ < 2)
+  if (!gout || !coords || !dfeats || C < 4 || (C & 3) || (ldg & 3) || (ldd & 3) || M < 0 || SX < 2 || SY < 2 || SZ < 2)
     return COOCC_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(dfeats) & 15) return COOCC_ERR_ALIGN;      // 16-byte vector reductions
   Sample3dP p{};
   p.X = X; p.Y = Y; p.Z = Z; p.C = C; p.coords = coords; p.M = M; p.SX = SX; p.SY = SY; p.SZ = SZ;
   p.gout = gout; p.ldg = ldg; p.dfeats = dfeats; p.ldd = ldd;
@@ -215,7 +217,8 @@ extern "C" int coocc_fine_sample2d_fwd(const float* img, long long ld, int ncam,
 
 extern "C" int coocc_fine_sample2d_bwd(const float* gout, long long ldg, int ncam, int H, int W, int C, const float* uv,
                                        const unsigned char* mask, int M, float* dimg, long long ldd, void* stream) {
-  if (!gout || !uv || !mask || !dimg || C < 4 || (C & 3) || (ldg & 3) || M < 0) return COOCC_ERR_ARG;
+  if (!gout || !uv || !mask || !dimg || C < 4 || (C & 3) || (ldg & 3) || (ldd & 3) || M < 0) return COOCC_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(dimg) & 15) return COOCC_ERR_ALIGN;        // 16-byte vector reductions
   Sample2dP p{};
   p.ncam = ncam; p.H = H; p.W = W; p.C = C; p.uv = uv; p.mask = mask; p.M = M;
   p.gout = gout; p.ldg = ldg; p.dimg = dimg; p.ldd = ldd;
