@@ -5,6 +5,7 @@ import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import coocc_b200
+from coocc_b200 import functional as CF
 from coocc_b200 import synthetic as S
 from coocc_b200.ddp import GradArena
 from coocc_b200.optim import FusedAdamW, norm_decay_mults
@@ -44,9 +45,12 @@ def step():
         opt.zero_grad()
     else:
         model.zero_grad(set_to_none=True)
+    CF.begin_step()
+    CF.zero_pool_begin(dev)
     losses, _, _ = model.forward_train(d["img_voxel_feats"], d["pts_voxel_feats"], d["geom"], d["gt_depth"], d["gt_img"], occ,
                                        img_feats, tr)
     sum(losses.values()).backward()
+    CF.zero_pool_end()
     if opt is not None:
         opt.step()
 
