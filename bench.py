@@ -480,6 +480,7 @@ def run_ours(args, cfg):
     # ---- rooflines, measured live with CUDA events: one eager step with every conv / BN / pack launch bracketed ---
     def profile_step():
         CF.PROFILE = []
+        CF.PROFILE_AHEAD_MS = 40        # brackets must time kernels, not the host's launch overhead (see CF._timed)
         eager_step(resident)
         torch.cuda.synchronize()
         prof, CF.PROFILE = CF.PROFILE, None
@@ -589,6 +590,7 @@ def run_ours(args, cfg):
                 n_t = 5
                 ms_m = timed(lambda: call(gs, resident), n_t) / n_t
                 CF.PROFILE = []
+                CF.PROFILE_AHEAD_MS = 40
                 eager_step(resident, opt_m)
                 torch.cuda.synchronize()
                 prof, CF.PROFILE = CF.PROFILE, None

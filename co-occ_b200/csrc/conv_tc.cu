@@ -19,8 +19,9 @@
 //           A = dY MN-major (TMA tiled), B = X MN-major (TMA im2col), split-K over voxel blocks,
 //           fp32 red.global.add epilogue.
 //
-// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
-// epilogue.  Persistent grid (<= #SMs), 4-stage smem ring, 2 TMEM accumulator buffers so the
+// CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11
+// epilogue (two per TMEM lane quadrant; a single warp per scheduler was issue-bound: the 1x1x1 layers spent 3.7 us
+// per tile in the epilogue against 0.2 us of MMAs, profiles/r02_conv_k1_ncu.txt).  Persistent grid (<= #SMs), 4-stage smem ring, 2 TMEM accumulator buffers so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -42,12 +43,18 @@ constexpr int kMaxBN = 256;           // MMA N upper bound (TMEM columns per acc
 constexpr int kABytes = kBM * 128;    // 16 KiB per stage
 constexpr int kBBytesMax = kMaxBN * 128;
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kRingBytes = 220 * 1024;                  // operand ring(s), cut into `nstages` stages
+constexpr int kRingBytes = 216 * 1024;                  // operand ring(s), cut into `nstages` stages (every ring layout
+                                                        // in use fits: ky 3 x 40 + 6 x 16 KiB, ky wgrad 3 x 72 KiB)
 constexpr int kMaxBRing = 8;          // ky-fused path: weight-tile ring depth bound
 constexpr int kMaxARing = 4;          // ky-fused path: extended activation-tile ring depth bound
-constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int kStatAccBytes = 8192;   // per-CTA running BatchNorm sums: [epilogue warp][column chunk][lane] float2
+constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 512 /*barriers*/ + kStatAccBytes;
+static_assert(kSmemBytes <= 232448, "shared memory");
 static_assert(kStages * kStageBytes <= kRingBytes, "ring");
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;          // two epilogue warps per TMEM lane quadrant (they split the 32-column chunks)
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kStatRow = 36;          // words per row of the statistics staging tile (conflict-free 16 B stores / column reads)
+constexpr int kStatBytes = kEpiWarps * 32 * kStatRow * 4;
 
 enum { MODE_FPROP = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
 
@@ -93,6 +100,9 @@ struct TcParams {
   int NA, NB;          // ring depths: extended A tiles (MT per entry), B tiles
   // parity-class launch of a stride-2 data gradient (dgrad_impl, `cls`): an explicit tap list -- im2col offsets and
   // weight taps are no longer tied to each other -- and output rows scattered to the fine grid
+  int b_kmajor;                      // dgrad: B is a transposed weight copy [Cin][taps][Cout] (K-major, like fprop)
+  int epi;                           // epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two, splitting the column chunks)
+  int stat_off;                      // byte offset of the statistics staging tiles behind the operand ring (0: none)
   int tapmode;                       // 1: tap t reads im2col offset tap_off[t] and weight tap tap_w[t]
   unsigned char tap_off[8];          // kx | ky << 2 | kz << 4   (offsets 0 / 1)
   unsigned char tap_w[8];            // (kx * 3 + ky) * 3 + kz of the weight tensor
@@ -124,6 +134,88 @@ __device__ __forceinline__ void pixel_to_whd(const TcParams& p, int pix, int& w,
   d = p.lo + x * p.cstride;
 }
 
+// Explicit shared-state-space accesses (32-bit addresses): the kernel's smem base goes through an integer alignment
+// round trip, so plain pointer dereferences compile to *generic* LD/ST -- measured as the top long-scoreboard stalls of
+// the 1x1x1 epilogue (profiles/r02_conv_k1_ncu.txt).
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float f;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(a));
+  return f;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 f;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f.x), "=f"(f.y) : "r"(a));
+  return f;
+}
+__device__ __forceinline__ void sts_f32x2(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// Epilogue helper: per-column sum / sum of squares of a 32 x 32 accumulator chunk (row = lane) over the valid rows,
+// added to the warp's running cell (shared address `cell`) of column c0 + lane.
+//   tile != 0: shared-memory transpose -- every lane stores its row (8 x 16 B, row stride 36 words: conflict-free),
+//     then sums one column; ~110 instructions
+//   else: register butterfly transpose-reduce; ~310 instructions (when the operand ring leaves no room for the tiles)
+__device__ __forceinline__ void epi_stats(const uint32_t (&v)[32], bool row_ok, uint32_t tile, uint32_t cell, int lane) {
+  float st, qt;
+  if (tile != 0u) {
+    const int nvalid = __popc(__ballot_sync(0xffffffffu, row_ok));    // valid rows are a prefix of the warp
+    const uint32_t dst = tile + (uint32_t)(lane * kStatRow * 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sts_u32x4(dst + 16u * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    __syncwarp();
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+    const uint32_t src = tile + (uint32_t)(lane * 4);
+    if (nvalid == 32) {
+#pragma unroll
+      for (int r = 0; r < 32; r += 2) {
+        const float f = lds_f32(src + (uint32_t)(r * kStatRow * 4)), g = lds_f32(src + (uint32_t)((r + 1) * kStatRow * 4));
+        s0 += f; q0 = fmaf(f, f, q0);
+        s1 += g; q1 = fmaf(g, g, q1);
+      }
+    } else {
+      for (int r = 0; r < nvalid; ++r) {
+        const float f = lds_f32(src + (uint32_t)(r * kStatRow * 4));
+        s0 += f; q0 = fmaf(f, f, q0);
+      }
+    }
+    __syncwarp();
+    st = s0 + s1; qt = q0 + q1;
+  } else {
+    float s[32], ss[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float f = row_ok ? __uint_as_float(v[i]) : 0.f;
+      s[i] = f;
+      ss[i] = f * f;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send_s = up ? s[i] : s[i + off];
+        const float send_q = up ? ss[i] : ss[i + off];
+        const float recv_s = __shfl_xor_sync(0xffffffffu, send_s, off);
+        const float recv_q = __shfl_xor_sync(0xffffffffu, send_q, off);
+        s[i] = (up ? s[i + off] : s[i]) + recv_s;
+        ss[i] = (up ? ss[i + off] : ss[i]) + recv_q;
+      }
+    }
+    st = s[0]; qt = ss[0];
+  }
+  const float2 a = lds_f32x2(cell);
+  sts_f32x2(cell, a.x + st, a.y + qt);
+}
+
 template <int ES>
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
   using E = Elt<ES>;
@@ -142,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   const int lane = threadIdx.x & 31;
   const bool wgrad = (p.mode == MODE_WGRAD);
   const bool a_mn = wgrad;
-  const bool b_mn = (p.mode != MODE_FPROP);
+  const bool b_mn = (p.mode != MODE_FPROP) && !p.b_kmajor;
 
   // ---- tile bookkeeping (identical in every role) ---------------------------------------
   const int ntn = (p.N + p.BN - 1) / p.BN;
@@ -171,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], (uint32_t)p.epi);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -518,6 +610,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   } else if (warp >= 4) {
     // =========================== epilogue (4 warps = 128 TMEM lanes) =====================
     const int q = warp & 3;                 // TMEM lane quadrant of this warp
+    const int csel = (warp - 4) >> 2;       // which of the quadrant's two warps: chunks csel, csel + 2, ...
+    // staging tile of this warp (shared address; 0: none): statistics transpose + output rows for coalesced stores
+    const uint32_t stat_tile = p.stat_off ? smem_u32(smem + p.stat_off) + (uint32_t)((warp - 4) * (32 * kStatRow * 4)) : 0u;
+    // Running per-column sums of this warp over all the tiles of the CTA (cell = [column chunk of this warp][lane]),
+    // flushed with global atomics once at the end (or when the N tile changes).  One atomic pair per tile and column
+    // chunk put 20 000 same-line requests on each L2 slice holding `stats` -- the 1x1x1 layers ran at the speed of
+    // those atomics (122 us for 246 MB), not of their loads.
+    const int cshift = p.epi == 8 ? 6 : 5;                                  // columns between two chunks of this warp
+    const uint32_t stat_acc = smem_u32(smem + kRingBytes + 512) + (uint32_t)((((warp - 4) * (32 / p.epi)) * 32 + lane) * 8);
+    const int nslots = (p.BN - csel * 32 + (1 << cshift) - 1) >> cshift;    // chunks this warp handles per tile
+    int acc_nt = -1;
+    auto stat_flush = [&]() {
+      for (int sl = 0; sl < nslots; ++sl) {
+        const int cc = csel * 32 + (sl << cshift) + lane;
+        const int col = acc_nt * p.BN + cc;
+        const float2 a = lds_f32x2(stat_acc + (uint32_t)(sl * 256));
+        if (col < p.N && cc < p.BN) {
+          atomicAdd(&p.stats[col], a.x);
+          atomicAdd(&p.stats[p.N + col], a.y);
+        }
+      }
+    };
+    if (p.stats != nullptr)
+      for (int sl = 0; sl < nslots; ++sl) sts_f32x2(stat_acc + (uint32_t)(sl * 256), 0.f, 0.f);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cidx; tile < ntiles; tile += cnum) {
@@ -536,6 +652,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         mt = t % ntm; t /= ntm;
         tap = t * p.NT;              // first tap of the group (ky path: t = kx * 3 + kz, see wtap)
         nk = (int)((long long)p.nvb * (sp + 1) / p.ksplit) - (int)((long long)p.nvb * sp / p.ksplit);
+      }
+      if (p.stats != nullptr && nt != acc_nt) {
+        if (acc_nt >= 0) {
+          stat_flush();
+          for (int sl = 0; sl < nslots; ++sl) sts_f32x2(stat_acc + (uint32_t)(sl * 256), 0.f, 0.f);
+        }
+        acc_nt = nt;
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -562,7 +685,76 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         row_ok = (mb < nmb) && (in_x < p.gYZ);
       }
       const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(u * p.hstride) + ((uint32_t)(q * 32) << 16);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      if (!wgrad && p.ksplit == 1 && p.out_bf16 && !p.accum && nk > 0 && (p.ldc & 7) == 0 && (p.BN & 31) == 0 &&
+          (nt + 1) * p.BN <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+        // common case (bf16 activations, whole chunks): a lean loop -- the generic one below re-tests its options per
+        // chunk and per value (~350 instructions per chunk besides the statistics)
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldc + nt * p.BN;
+        // Row-per-lane 16-byte stores fill half a 32-byte sector per request and the write-heavy 1x1x1 layers ran at
+        // the L2's sector rate (128->256 on 640 k voxels: 237 us for 492 MB).  With a staging tile the warp transposes
+        // the packed rows through shared memory (XOR-swizzled 16-byte pieces, conflict-free both ways) and every
+        // store instruction writes 8 rows x 64 contiguous bytes.
+        const bool staged = stat_tile != 0u && !p.omap;
+        const int nvalid = __popc(__ballot_sync(0xffffffffu, row_ok));          // valid rows are a prefix
+        __nv_bfloat16* const obase = orow - (long long)lane * p.ldc;            // row 0 of this warp
+        for (int c0 = csel * 32; c0 < p.BN; c0 += 1 << cshift) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_base + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (p.stats != nullptr) epi_stats(v, row_ok, stat_tile, stat_acc + (uint32_t)((c0 >> cshift) * 256), lane);
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * p.BN + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + b.x);
+              v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + b.y);
+              v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + b.z);
+              v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + b.w);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaxf(__uint_as_float(v[i]), 0.f));
+          }
+          if (staged) {
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h =
+                    __floats2bfloat162_rn(__uint_as_float(v[8 * pc + 2 * j]), __uint_as_float(v[8 * pc + 2 * j + 1]));
+                w4[j] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              sts_u32x4(stat_tile + (uint32_t)(64 * lane + 16 * (pc ^ sw)), w4[0], w4[1], w4[2], w4[3]);
+            }
+            __syncwarp();
+            const int pp = lane & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = 8 * j + (lane >> 2);
+              const uint4 val = lds_u32x4(stat_tile + (uint32_t)(64 * r + 16 * (pp ^ ((r >> 1) & 3))));
+              if (r < nvalid) *reinterpret_cast<uint4*>(obase + (long long)r * p.ldc + c0 + 8 * pp) = val;
+            }
+            __syncwarp();
+          } else if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[i + 2 * j]), __uint_as_float(v[i + 2 * j + 1]));
+                w4[j] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(orow + c0 + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
+        }
+        continue;
+      }
+      for (int c0 = csel * 32; c0 < p.BN; c0 += 1 << cshift) {
         uint32_t v[32];
         if (nk > 0) {
           tmem_ld_32x32(t_base + (uint32_t)c0, v);
@@ -610,35 +802,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 if (col0 + i < p.N) v[i] = __float_as_uint(__uint_as_float(v[i]) + o[i]);
             }
           }
-          if (p.stats != nullptr) {
-            // per-column sum / sum of squares over the rows of this warp (raw accumulators):
-            // butterfly transpose-reduce, lane l ends with the totals of column c0 + l
-            float s[32], ss[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float f = row_ok ? __uint_as_float(v[i]) : 0.f;
-              s[i] = f;
-              ss[i] = f * f;
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-              const bool up = (lane & off) != 0;
-#pragma unroll
-              for (int i = 0; i < off; ++i) {
-                const float send_s = up ? s[i] : s[i + off];
-                const float send_q = up ? ss[i] : ss[i + off];
-                const float recv_s = __shfl_xor_sync(0xffffffffu, send_s, off);
-                const float recv_q = __shfl_xor_sync(0xffffffffu, send_q, off);
-                s[i] = (up ? s[i + off] : s[i]) + recv_s;
-                ss[i] = (up ? ss[i + off] : ss[i]) + recv_q;
-              }
-            }
-            const int col = col0 + lane;
-            if (col < p.N) {
-              atomicAdd(&p.stats[col], s[0]);
-              atomicAdd(&p.stats[p.N + col], ss[0]);
-            }
-          }
+          if (p.stats != nullptr) epi_stats(v, row_ok, stat_tile, stat_acc + (uint32_t)((c0 >> cshift) * 256), lane);
           if (row_ok && p.out_bf16) {
             // bf16 activations: the next convolution's operand type, written straight from the epilogue
             __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldc + col0;
@@ -720,6 +884,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.stats != nullptr && acc_nt >= 0) stat_flush();
   }
 
   tc_fence_before();
@@ -848,8 +1013,27 @@ static int out_dim(int in, int ksize, int stride) {
   return (in + 2 * pad - ksize) / stride + 1;
 }
 
+// epilogue warps of a launch (COOCC_CONV_EPI=4|8 forces one setting)
+static int pick_epi(const TcParams& p) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("COOCC_CONV_EPI");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 4 || forced == 8) return forced;
+  return kEpiWarps;
+}
+
 template <int ES>
-static int launch(const TcParams& p, int ntiles, cudaStream_t st) {
+static int launch(const TcParams& p_in, int ntiles, cudaStream_t st) {
+  TcParams p = p_in;
+  p.epi = pick_epi(p);
+  static int stat_smem = -1;
+  if (stat_smem < 0) {
+    const char* e = getenv("COOCC_CONV_STATSMEM");
+    stat_smem = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!stat_smem) p.stat_off = 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel<ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -873,7 +1057,7 @@ static int launch(const TcParams& p, int ntiles, cudaStream_t st) {
   } else {
     cfg.gridDim = dim3(ntiles < g_num_sms ? ntiles : g_num_sms, 1, 1);
   }
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(128 + 32 * p.epi, 1, 1);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = st;
   return cudaLaunchKernelEx(&cfg, tc_conv_kernel<ES>, p) == cudaSuccess ? 0 : COOCC_ERR_CUDA;
@@ -932,6 +1116,12 @@ static int prepare_split(TcParams& p, int nk_total, cudaStream_t st, bool zero_o
     const int stage = kABytes * p.MT + (p.BN * 128 + 1023) / 1024 * 1024;
     p.nstages = kRingBytes / stage;
     if (p.nstages > kStages) p.nstages = kStages;
+    // statistics staging tiles go behind the ring when it leaves room (the 1x1x1 and narrow layers: exactly the
+    // ones whose epilogue is exposed)
+    // (they also stage the bf16 output rows for coalesced stores; a 1x1x1 layer gives up a ring stage for them)
+    if (p.taps == 1 && p.nstages == 4 && kRingBytes - 4 * stage < kStatBytes && kRingBytes - 3 * stage >= kStatBytes)
+      p.nstages = 3;
+    p.stat_off = (kRingBytes - p.nstages * stage >= kStatBytes) ? p.nstages * stage : 0;
   }
   const int ntm = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
   const int ntiles = ntm * ((p.N + p.BN - 1) / p.BN);
@@ -1148,6 +1338,24 @@ static int fwd_impl(const coocc_conv_desc* d, const void* x, const void* w, void
   return rc ? rc : rc2;
 }
 
+// W[Cout][T][Cin] -> Wt[Cin][T][Cout] (bf16), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_w_kernel(const uint16_t* __restrict__ w, uint16_t* __restrict__ wt,
+                                                          int Cout, int T, int Cin) {
+  __shared__ uint16_t tile[32][34];
+  const int t = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + tx;
+    tile[r][tx] = (co < Cout && ci < Cin) ? w[((long long)co * T + t) * Cin + ci] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + tx;
+    if (ci < Cin && co < Cout) wt[((long long)ci * T + t) * Cout + co] = tile[tx][r];
+  }
+}
+
 // dX[v, ci] = sum_{tap,co} dY[v - tap + pad, co] W[co, tap, ci]; stride-1 convolutions only
 // (for stride 2 the caller scatters dY onto the input lattice first, see conv3d_dgrad docs).
 static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, void* dxv, long long ldo,
@@ -1262,9 +1470,33 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, v
     rc = make_tm_im2col(&p.tmA, dy, es, d->X, d->Y, d->Z, d->Cout, d->ldy, -1, -1, 1, ch, (p.ny + 2) * d->Z, false,
                         up_h);
     if (rc) return rc;
+    const int ntiles = ((p.gX * p.nyb + p.MT - 1) / p.MT) * ((p.N + p.BN - 1) / p.BN);
+    // bf16: run the big-grid data gradients on a transposed copy of the weights (K-major B operand, the forward's
+    // configuration).  Reading W in place as an MN-major operand kept the tensor pipe at 67 % active against 79 % for
+    // the forward of the same layer (profiles/r02_conv_full.summary.txt); the copy is a few MB per layer.
+    static int wt_enabled = -1;
+    if (wt_enabled < 0) {
+      const char* e = getenv("COOCC_DGRAD_WT");
+      wt_enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    const long long welts = (long long)d->Cout * taps * d->Cin;
+    // (measured: 128->128 on the 200x200x16 grid 1.71 -> 1.53 ms for four launches; no gain for 256-wide N tiles)
+    if (es == 2 && wt_enabled && p.BN <= 128 && welts <= (8ll << 20) && (d->Cout % 8) == 0) {
+      uint16_t* wt = nullptr;
+      if (cudaMallocAsync(reinterpret_cast<void**>(&wt), (size_t)welts * 2, (cudaStream_t)stream) != cudaSuccess)
+        return COOCC_ERR_CUDA;
+      dim3 grid((d->Cin + 31) / 32, (d->Cout + 31) / 32, taps);
+      transpose_w_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint16_t*>(w), wt, d->Cout, taps,
+                                                                d->Cin);
+      p.b_kmajor = 1;
+      p.Cin = d->Cout;                   // B K-offset per tap in the transposed copy
+      rc = make_tm_2d(&p.tmB, wt, es, d->Cin, (long long)taps * d->Cout, (long long)taps * d->Cout, ch, p.BN, false);
+      if (!rc) rc = launch<2>(p, ntiles, (cudaStream_t)stream);
+      cudaFreeAsync(wt, (cudaStream_t)stream);
+      return rc;
+    }
     rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, ch, ch, true);
     if (rc) return rc;
-    const int ntiles = ((p.gX * p.nyb + p.MT - 1) / p.MT) * ((p.N + p.BN - 1) / p.BN);
     return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
   }
   if (plain) {

@@ -45,6 +45,7 @@ def act_bf16():
 
 
 PROFILE = None     # bench.py sets this to a list to time every conv launch with CUDA events
+PROFILE_AHEAD_MS = 0   # > 0: whenever a bracket finds the stream idle, a spin kernel of this length is queued first
 
 # Device-side error flags cannot be read while a CUDA graph is being captured: graph.GraphedStep
 # sets this to a list, the (flag, exception) pairs land there and GraphedStep.check() reads them
@@ -67,6 +68,10 @@ def _timed(tag, flops, fn, info=""):
     algorithmic work: FLOPs for the tensor-core kernels, BYTES for tags starting with "hbm:"."""
     if PROFILE is None:
         return fn()
+    if PROFILE_AHEAD_MS and torch.cuda.current_stream().query():
+        # The stream has drained: the host is the bottleneck and the event pair below would time the host's launch
+        # overhead (~50 us per call), not the kernel.  Park the GPU for a while so the host gets ahead again.
+        torch.cuda._sleep(int(PROFILE_AHEAD_MS * 1.9e6))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = fn()

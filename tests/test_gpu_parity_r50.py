@@ -152,9 +152,18 @@ def test_r50_conv_stack_vs_reference_fixture(golden, precision):
              dx=sm(x.grad, "stack_dx_sample"),
              dw_pred=float(np.abs(head.occ_pred_conv[3].weight.grad.reshape(-1).cpu().numpy() - g["stack_dw_pred"]).max()
                            / np.abs(g["stack_dw_pred"]).max()))
+    dxs = sample(x.grad.float(), g)
+    e["dx_l2"] = float(np.linalg.norm(dxs - g["stack_dx_sample"]) / np.linalg.norm(g["stack_dx_sample"]))
     _report("stack[r50,%s]" % precision, **e)
     assert e["occ"] < tol["occ"] and e["feats"] < tol["occ"] and e["mid0"] < tol["occ"]
-    assert e["dx"] < tol["grad"] and e["dw_pred"] < tol["grad"]
+    # The input gradient crosses 20 ReLU layers.  The forward is reproducible to 7e-6 only (the BatchNorm statistics
+    # are summed with atomics), which flips the masks of the pre-activations closest to zero, and every flip changes
+    # gradient samples by whole per cents.  Measured on B200 in fp32 mode (tools/dev_stack_selfnoise.py): two runs of
+    # the SAME build differ by 2.5e-3 ... 1.8e-2 in relative L2 and 1.8e-2 ... 4.6e-2 in max/max, the same size as the
+    # difference to the reference fixture (2.2e-2 / 3.7e-2).  The bounds below are therefore noise bounds; what pins the
+    # backward arithmetic is dw_pred (no ReLU behind it: 6e-6) and the per-op gradient tests (1e-6, test_gpu_parity.py).
+    assert e["dw_pred"] < tol["grad"]
+    assert e["dx_l2"] < 2.5 * tol["grad"] and e["dx"] < 5 * tol["grad"]
 
 
 def test_r50_render_vs_reference_fixture(golden, precision):

@@ -20,6 +20,9 @@ def step():
 for _ in range(2): step()
 torch.cuda.synchronize()
 CF.PROFILE = []
+# keep the GPU busy while the host issues the step: otherwise the event pairs around the small launches measure the
+# host's launch overhead (~50 us floor), not the kernels
+CF.PROFILE_AHEAD_MS = 40
 step(); torch.cuda.synchronize()
 rows = [(a0.elapsed_time(b0), f, t) for a0, b0, f, t in CF.PROFILE if not t.startswith("hbm:")]
 CF.PROFILE = None
