@@ -71,6 +71,9 @@ _SIGS = {
     "coocc_render_box": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "coocc_render_box_gather": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "coocc_render_box_scatter_add": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_relu_bias_bwd": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
+    "coocc_render_box_gather_bf16": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "coocc_render_box_scatter_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_render_composite_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "coocc_render_composite_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "coocc_render_upsample_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -86,6 +89,7 @@ _SIGS = {
     "coocc_lss_pool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_lss_pool_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
     "coocc_fine_sample3d_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_fine_sample3d_fwd_bf16": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_fine_sample3d_bwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_fine_project": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "coocc_fine_sample2d_fwd": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_ll, c_void_p]),

@@ -184,6 +184,16 @@ extern "C" int coocc_fine_sample3d_fwd(const float* feats, long long ld, int X, 
   return run<Sample3dP, sample3d_fwd_item>(p, (long long)M * (C >> 2), (cudaStream_t)stream);
 }
 
+extern "C" int coocc_fine_sample3d_fwd_bf16(const void* feats, long long ld, int X, int Y, int Z, int C, const int* coords,
+                                            int M, int SX, int SY, int SZ, float* out, long long ldo, void* stream) {
+  if (!feats || !coords || !out || C < 4 || (C & 3) || (ld & 3) || (ldo & 3) || M < 0 || SX < 2 || SY < 2 || SZ < 2)
+    return COOCC_ERR_ARG;
+  Sample3dP p{};
+  p.feats_bf16 = reinterpret_cast<const unsigned short*>(feats); p.ld = ld; p.X = X; p.Y = Y; p.Z = Z; p.C = C;
+  p.coords = coords; p.M = M; p.SX = SX; p.SY = SY; p.SZ = SZ; p.out = out; p.ldo = ldo;
+  return run<Sample3dP, sample3d_fwd_item>(p, (long long)M * (C >> 2), (cudaStream_t)stream);
+}
+
 extern "C" int coocc_fine_sample3d_bwd(const float* gout, long long ldg, int X, int Y, int Z, int C, const int* coords,
                                        int M, int SX, int SY, int SZ, float* dfeats, long long ldd, void* stream) {
   if (!gout || !coords || !dfeats || C < 4 || (C & 3) || (ldg & 3) || (ldd & 3) || M < 0 || SX < 2 || SY < 2 || SZ < 2)

@@ -12,6 +12,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define COOCC_HD __host__ __device__ __forceinline__
@@ -43,6 +44,7 @@ COOCC_HD void atomic_add4f(float* p, float a, float b, float c, float d) {
 // ------------------------------------------------------------------------------------------
 struct Sample3dP {
   const float* feats; long long ld;
+  const unsigned short* feats_bf16;     // non-null: the grid is stored in bf16 (feats unused), row stride ld elements
   int X, Y, Z, C;
   const int* coords;     // [3][M] fine voxel indices (x, y, z)
   int M;
@@ -53,6 +55,14 @@ struct Sample3dP {
 };
 
 struct Corner3 { int v[8]; float w[8]; };
+
+// bf16 storage bits -> fp32 (host + device)
+COOCC_HD float bf16_bits(unsigned short b) {
+  const unsigned int u = (unsigned int)b << 16;
+  float f;
+  memcpy(&f, &u, sizeof(f));
+  return f;
+}
 
 // grid = (c / (S - 1) - 0.5) * 2 (occ_head.py:214-216), unnormalised with align_corners=False:
 // ((g + 1) * size - 1) / 2; corners in ATen's order tnw, tne, tsw, tse, bnw, bne, bsw, bse
@@ -87,6 +97,12 @@ COOCC_HD void sample3d_fwd_item(const Sample3dP& p, long long id) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   for (int j = 0; j < 8; ++j) {
     if (k.v[j] < 0) continue;
+    if (p.feats_bf16 != nullptr) {
+      const unsigned short* s = p.feats_bf16 + (long long)k.v[j] * p.ld + c;
+      a0 += bf16_bits(s[0]) * k.w[j]; a1 += bf16_bits(s[1]) * k.w[j];
+      a2 += bf16_bits(s[2]) * k.w[j]; a3 += bf16_bits(s[3]) * k.w[j];
+      continue;
+    }
     const float* s = p.feats + (long long)k.v[j] * p.ld + c;
     a0 += s[0] * k.w[j]; a1 += s[1] * k.w[j]; a2 += s[2] * k.w[j]; a3 += s[3] * k.w[j];
   }

@@ -40,6 +40,29 @@ __global__ void box_scatter_add_kernel(const float* __restrict__ rows, int C, in
   for (int c = threadIdx.x & 31; c < C; c += 32) d[c] += s[c];
 }
 
+// bf16 activations: the box rows are gathered as they are stored (8 channels per 16-byte access) ...
+__global__ void box_gather_bf16_kernel(const uint4* __restrict__ grid, long long ld8, int Y, int Z, int bx, int by,
+                                       int bz, int C8, uint4* __restrict__ rows) {
+  const long long t = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= (long long)bx * by * bz) return;
+  const int z = t % bz, y = (t / bz) % by, x = t / (bz * by);
+  const uint4* s = grid + (((long long)x * Y + y) * Z + z) * ld8;
+  uint4* d = rows + t * C8;
+  for (int c = threadIdx.x & 31; c < C8; c += 32) d[c] = s[c];
+}
+// ... and the gradient of the whole grid is written in one pass: the box rows' gradients inside the box, zeros elsewhere
+// (no separate zero fill, no fp32 round trip)
+__global__ void box_scatter_bf16_kernel(const uint4* __restrict__ rows, int C8, int X, int Y, int Z, int bx, int by,
+                                        int bz, uint4* __restrict__ grid, long long ld8) {
+  const long long v = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= (long long)X * Y * Z) return;
+  const int z = v % Z, y = (v / Z) % Y, x = v / ((long long)Z * Y);
+  const bool in = x < bx && y < by && z < bz;
+  const uint4* s = rows + (((long long)x * by + y) * bz + z) * C8;
+  uint4* d = grid + v * ld8;
+  for (int c = threadIdx.x & 31; c < C8; c += 32) d[c] = in ? s[c] : make_uint4(0u, 0u, 0u, 0u);
+}
+
 // torch.linspace(0, D, D)[i] (ATen's symmetric evaluation)
 __device__ __forceinline__ float zval(int i, int D) {
   const float step = (float)D / (float)(D - 1);
@@ -398,6 +421,28 @@ extern "C" int coocc_render_box_scatter_add(const float* rows, int C, int X, int
   coocc_render_box(X, Y, Z, &bx, &by, &bz);
   const long long T = (long long)bx * by * bz;
   box_scatter_add_kernel<<<(unsigned)((T + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rows, C, Y, Z, bx, by, bz, grid, ld);
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_render_box_gather_bf16(const void* grid, long long ld, int X, int Y, int Z, int C, void* rows,
+                                            void* stream) {
+  if (!grid || !rows || (C & 7) || (ld & 7)) return COOCC_ERR_ARG;
+  int bx, by, bz;
+  coocc_render_box(X, Y, Z, &bx, &by, &bz);
+  const long long T = (long long)bx * by * bz;
+  box_gather_bf16_kernel<<<(unsigned)((T + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(grid), ld / 8, Y, Z, bx, by, bz, C / 8, reinterpret_cast<uint4*>(rows));
+  return CK_LAUNCH();
+}
+
+extern "C" int coocc_render_box_scatter_bf16(const void* rows, int C, int X, int Y, int Z, void* grid, long long ld,
+                                             void* stream) {
+  if (!grid || !rows || (C & 7) || (ld & 7)) return COOCC_ERR_ARG;
+  int bx, by, bz;
+  coocc_render_box(X, Y, Z, &bx, &by, &bz);
+  const long long V = (long long)X * Y * Z;
+  box_scatter_bf16_kernel<<<(unsigned)((V + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(rows), C / 8, X, Y, Z, bx, by, bz, reinterpret_cast<uint4*>(grid), ld / 8);
   return CK_LAUNCH();
 }
 

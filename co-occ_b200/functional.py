@@ -245,11 +245,32 @@ class _Conv3dFn(torch.autograd.Function):
         xo, wo, y = ctx.saved_tensors
         dims, odims, k, s, relu, has_bias, dtype, cin, cout = ctx.meta
         L = _lib.lib()
-        if relu:
-            dy = dy * (y > 0)
         dy = _as_rows(dy)
-        db = dy.float().sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
-        dyo = _operand(dy, dtype)
+        want_db = has_bias and ctx.needs_input_grad[2]
+        db = None
+        if (relu or want_db) and dy.dtype in (torch.float32, torch.bfloat16) and dy.stride(1) == 1 and cout <= 1024:
+            # ReLU mask, bias gradient and the conversion to the operand type in one pass (csrc/elementwise.cu)
+            want_bf16 = dtype == DT_BF16
+            if relu or (want_bf16 and dy.dtype != torch.bfloat16) or (not want_bf16 and dy.dtype != torch.float32):
+                ld = (cout + 7) // 8 * 8
+                mk = torch.empty if ld == cout else torch.zeros
+                dyo_full = mk(dy.shape[0], ld, device=dy.device, dtype=torch.bfloat16 if want_bf16 else torch.float32)
+                dyo = dyo_full[:, :cout]
+            else:
+                dyo_full, dyo = None, dy                   # already in operand form: only the bias sums are needed
+            if want_db:
+                db = zeros_small((cout,), dy.device)
+            ym = _as_rows(y) if relu else None
+            _lib.check(L.coocc_relu_bias_bwd(_p(dy), dy.stride(0), 1 if dy.dtype == torch.bfloat16 else 0,
+                                             _p(ym), ym.stride(0) if relu else 0,
+                                             1 if (relu and ym.dtype == torch.bfloat16) else 0, dy.shape[0], cout,
+                                             _p(dyo_full), dyo_full.stride(0) if dyo_full is not None else 0,
+                                             1 if want_bf16 else 0, _p(db), _stream()), "relu_bias_bwd")
+        else:
+            if relu:
+                dy = dy * (y > 0)
+            db = dy.float().sum(0) if want_db else None
+            dyo = _operand(dy, dtype)
         dx = dw = None
         if ctx.needs_input_grad[1]:
             # the kernel accumulates (split-K red.add).  With a gradient arena (ddp.GradArena) it adds straight into
@@ -457,10 +478,11 @@ def bn_act(x, stats, gamma, beta, residual=None, relu=True, eps=1e-5, momentum=0
     return _BNActFn.apply(x, stats, gamma, beta, residual, relu, eps, momentum, running_mean, running_var, var_count)
 
 
-def linear(x2d, weight, bias=None, relu=False):
-    """nn.Linear on the tensor cores: a 1x1x1 convolution over `rows` voxels."""
+def linear(x2d, weight, bias=None, relu=False, out_bf16=False):
+    """nn.Linear on the tensor cores: a 1x1x1 convolution over `rows` voxels.  out_bf16: in bf16 mode the result is
+    written in bf16 (for hidden layers whose only consumer is the next Linear, which rounds to bf16 anyway)."""
     w5d = weight.reshape(weight.shape[0], weight.shape[1], 1, 1, 1)
-    return _Conv3dFn.apply(x2d, w5d, bias, (x2d.shape[0], 1, 1), 1, 1, relu)
+    return _Conv3dFn.apply(x2d, w5d, bias, (x2d.shape[0], 1, 1), 1, 1, relu, False, out_bf16)
 
 
 class _ResizeAddFn(torch.autograd.Function):
@@ -860,6 +882,15 @@ class _BoxRowsFn(torch.autograd.Function):
             return x2d.view_as(x2d)
         ctx.full = False
         T = box[0] * box[1] * box[2]
+        ctx.bf16 = x2d.dtype == torch.bfloat16 and x2d.shape[1] % 8 == 0 and x2d.stride(0) % 8 == 0
+        if ctx.bf16:
+            # bf16 activations: rows gathered as stored (the heads' first Linear takes bf16 operands anyway)
+            rows = torch.empty(T, x2d.shape[1], device=x2d.device, dtype=torch.bfloat16)
+            _lib.check(L.coocc_render_box_gather_bf16(_p(x2d), x2d.stride(0), dims[0], dims[1], dims[2], x2d.shape[1],
+                                                      _p(rows), _stream()), "render_box_gather_bf16")
+            return rows
+        if x2d.dtype != torch.float32:
+            x2d = x2d.float()
         rows = torch.empty(T, x2d.shape[1], device=x2d.device, dtype=torch.float32)
         _lib.check(L.coocc_render_box_gather(_p(x2d), x2d.stride(0), dims[0], dims[1], dims[2], x2d.shape[1],
                                              _p(rows), _stream()), "render_box_gather")
@@ -871,6 +902,13 @@ class _BoxRowsFn(torch.autograd.Function):
             return g, None
         L = _lib.lib()
         g = g.contiguous()
+        if ctx.bf16:
+            # one pass writes the whole grid's gradient (zeros outside the box): no zero fill, no fp32 round trip
+            g = g if g.dtype == torch.bfloat16 else g.to(torch.bfloat16)
+            dx = torch.empty(ctx.shape, device=g.device, dtype=torch.bfloat16)
+            _lib.check(L.coocc_render_box_scatter_bf16(_p(g), g.shape[1], ctx.dims[0], ctx.dims[1], ctx.dims[2],
+                                                       _p(dx), dx.stride(0), _stream()), "render_box_scatter_bf16")
+            return dx, None
         dx = torch.zeros(ctx.shape, device=g.device, dtype=torch.float32)
         _lib.check(L.coocc_render_box_scatter_add(_p(g), g.shape[1], ctx.dims[0], ctx.dims[1], ctx.dims[2],
                                                   _p(dx), dx.stride(0), _stream()), "render_box_scatter_add")
@@ -1107,14 +1145,17 @@ class _Sample3dFn(torch.autograd.Function):
         L = _lib.lib()
         _require_cuda(feats, coords)
         ctx.in_dtype = feats.dtype
-        feats = _as_rows(feats.float() if feats.dtype != torch.float32 else feats)
+        if feats.dtype not in (torch.float32, torch.bfloat16):
+            feats = feats.float()
+        feats = _as_rows(feats)                  # bf16 grids are sampled as stored (no fp32 copy of the grid)
         C = feats.shape[1]
         coords = coords.to(torch.int32).contiguous()
         M = coords.shape[1]
         out = torch.empty(M, C, device=feats.device, dtype=torch.float32)
-        _lib.check(L.coocc_fine_sample3d_fwd(_p(feats), feats.stride(0), dims[0], dims[1], dims[2], C, _p(coords), M,
-                                             int(final_size[0]), int(final_size[1]), int(final_size[2]), _p(out), C,
-                                             _stream()), "fine_sample3d_fwd")
+        fn = L.coocc_fine_sample3d_fwd_bf16 if feats.dtype == torch.bfloat16 else L.coocc_fine_sample3d_fwd
+        _lib.check(fn(_p(feats), feats.stride(0), dims[0], dims[1], dims[2], C, _p(coords), M,
+                      int(final_size[0]), int(final_size[1]), int(final_size[2]), _p(out), C, _stream()),
+                   "fine_sample3d_fwd")
         ctx.save_for_backward(coords)
         ctx.meta = (tuple(dims), C, M, tuple(int(v) for v in final_size), feats.shape[0])
         return out

@@ -492,7 +492,7 @@ class MLP(nn.Module):
 
     def forward_rows(self, x2d, relu_out=False):
         for lin in self.hidden_layers:
-            x2d = CF.linear(x2d, lin.weight, lin.bias, relu=True)
+            x2d = CF.linear(x2d, lin.weight, lin.bias, relu=True, out_bf16=True)
         return CF.linear(x2d, self.output_layer.weight, self.output_layer.bias, relu=relu_out)
 
     def forward(self, x):
@@ -512,7 +512,7 @@ def render_fn(voxel_feats, gemo, sigma_head, rgb_head, gt_depth, gt_img):
     B, N, D, H, W, _ = gemo.shape
     assert B == 1
     x2d, dims = CF.to_cl2d(voxel_feats)
-    rows = CF.box_rows(x2d.float(), dims)       # (bf16 activations: the render box is gathered in fp32)
+    rows = CF.box_rows(x2d, dims)               # (bf16 activations: gathered as stored, no fp32 copy of the grid)
     sigma = sigma_head.forward_rows(rows, relu_out=True)        # [T,1] = relu(sigma_head(f))
     if rgb_head is not None:
         rgb_raw = rgb_head.forward_rows(rows)                   # [T,3]

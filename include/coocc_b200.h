@@ -144,6 +144,12 @@ int coocc_render_box_gather(const float* grid, long long ld, int X, int Y, int Z
                             void* stream);
 int coocc_render_box_scatter_add(const float* rows, int C, int X, int Y, int Z, float* grid, long long ld,
                                  void* stream);
+/* bf16 grids (C and ld multiples of 8): rows gathered in bf16; scatter writes the gradient of the WHOLE grid (the box
+ * rows inside the box, zeros elsewhere) in one pass. */
+int coocc_render_box_gather_bf16(const void* grid, long long ld, int X, int Y, int Z, int C, void* rows,
+                                 void* stream);
+int coocc_render_box_scatter_bf16(const void* rows, int C, int X, int Y, int Z, void* grid, long long ld,
+                                  void* stream);
 /* geom [ncam][D][H][W][3] fp32 ego metres -> rgb_map [ncam][H][W][3], depth_map [ncam][H][W];
  * err[0] = 1 if an in-box sample falls outside the feature grid (the reference raises). */
 int coocc_render_composite_fwd(const float* geom, int ncam, int D, int H, int W, const float* tab, int X,
@@ -243,6 +249,9 @@ int coocc_lss_pool_bwd(const unsigned int* point_keys, long long npts, int V, in
 int coocc_fine_sample3d_fwd(const float* feats, long long ld, int X, int Y, int Z, int C, const int* coords, int M,
                             int SX, int SY, int SZ, float* out, long long ldo, void* stream);
 /* dfeats [X*Y*Z][ldd] += scatter of gout [M][ldg] (atomics; zeroed by the caller) */
+/* same, the feature grid stored in bf16 (samples are still fp32) */
+int coocc_fine_sample3d_fwd_bf16(const void* feats, long long ld, int X, int Y, int Z, int C, const int* coords, int M,
+                                 int SX, int SY, int SZ, float* out, long long ldo, void* stream);
 int coocc_fine_sample3d_bwd(const float* gout, long long ldg, int X, int Y, int Z, int C, const int* coords, int M,
                             int SX, int SY, int SZ, float* dfeats, long long ldd, void* stream);
 /* vs3 / lo3: HOST float[3] voxel size and lower corner; inv_bda float[9]; cam27 [ncam][27] = inverse(rots)(9) |
@@ -360,6 +369,11 @@ int coocc_bn_act_bwd_apply(const void* dout, long long ldd, const void* out, lon
                            long long ldx, long long V, int C, const float* mean_invstd, const float* gamma,
                            const float* beta, int relu, const float* sums, long long count, void* dx, long long lddx,
                            int act_bf16, void* dres, long long lddr, void* stream);
+/* Backward glue of a Linear / convolution with bias and ReLU epilogue (nerf_mlp.py:92-105 and the fine-stage MLPs):
+ * out[r][c] = dy[r][c] * [y[r][c] > 0] (y NULL: no mask) in fp32 or bf16, db[c] += sum_r out[r][c] (db NULL: skipped;
+ * must be zero-initialised).  dy / y / out are [M][C] rows with their own strides and storage types. */
+int coocc_relu_bias_bwd(const void* dy, long long ld_dy, int dy_bf16, const void* y, long long ld_y, int y_bf16,
+                        int M, int C, void* out, long long ldo, int out_bf16, float* db, void* stream);
 /* dst[(2x,2y,2z)] = src[(x,y,z)], zero elsewhere (dst extent X,Y,Z; src extent oX,oY,oZ) */
 int coocc_dilate2(const void* src, long long lds, int oX, int oY, int oZ, int C, void* dst, long long ldd,
                   int X, int Y, int Z, int is_bf16, void* stream);
