@@ -47,6 +47,7 @@ constexpr int kRingBytes = 216 * 1024;                  // operand ring(s), cut 
                                                         // in use fits: ky 3 x 40 + 6 x 16 KiB, ky wgrad 3 x 72 KiB)
 constexpr int kMaxBRing = 8;          // ky-fused path: weight-tile ring depth bound
 constexpr int kMaxARing = 4;          // ky-fused path: extended activation-tile ring depth bound
+constexpr int kMaxAcc = 4;            // TMEM accumulator buffers (512 columns / acc_stride)
 constexpr int kStatAccBytes = 8192;   // per-CTA running BatchNorm sums: [epilogue warp][column chunk][lane] float2
 constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 512 /*barriers*/ + kStatAccBytes;
 static_assert(kSmemBytes <= 232448, "shared memory");
@@ -67,7 +68,9 @@ struct TcParams {
   int MT;              // 128-row MMA tiles per CTA tile (1, 2 or 4; MT*BN <= 512 TMEM columns)
   int NT;              // wgrad: filter taps per CTA tile sharing one dY tile (1 or 3)
   int nstages;         // smem ring depth (4, or 3 when a stage is 64 KiB)
-  int nacc;            // TMEM accumulator buffers (2, or 1 when MT*BN > 256: epilogue not overlapped)
+  int nacc;            // TMEM accumulator buffers (2, or 1 when MT*BN > 256: epilogue not overlapped; 4 for the narrow
+                       // 1x1x1 tiles, whose per-tile load -> MMA -> epilogue chain is latency-bound)
+  int acc_stride;      // TMEM columns between accumulator buffers
   int hstride;         // TMEM column stride between the MT halves
   int es;              // operand element size in bytes (host bookkeeping)
   int mc;              // 1: CTA pairs (cluster of 2) on adjacent M tiles share the B tile by TMA multicast
@@ -226,9 +229,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   uint64_t* empty_bar = full_bar + kMaxBRing;
   uint64_t* fulla_bar = empty_bar + kMaxBRing;  // ky path: extended A tiles
   uint64_t* emptya_bar = fulla_bar + kMaxARing;
-  uint64_t* tfull_bar = emptya_bar + kMaxARing; // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tfull_bar = emptya_bar + kMaxARing; // [kMaxAcc] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + kMaxAcc;   // [kMaxAcc] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAcc);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       mbar_init(&fulla_bar[s], 1);
       mbar_init(&emptya_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxAcc; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], (uint32_t)p.epi);   // one arrive per epilogue warp
     }
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         for (int tile = cidx; tile < ntiles; tile += cnum) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
           for (int g = 0; g < ngroups; ++g) {
             mbar_wait(&fulla_bar[sa_i], pa);
             const uint32_t sa = ringA + sa_i * a_entry;
@@ -573,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kMaxBN;   // nacc == 1 -> acc stays 0
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);   // nacc == 1 -> acc stays 0
         for (int k = 0; k < nk; ++k) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         row = x * p.gYZ + in_x;
         row_ok = (mb < nmb) && (in_x < p.gYZ);
       }
-      const uint32_t t_base = tmem_base + (uint32_t)acc * kMaxBN + (uint32_t)(u * p.hstride) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_base = tmem_base + (uint32_t)(acc * p.acc_stride) + (uint32_t)(u * p.hstride) + ((uint32_t)(q * 32) << 16);
       if (!wgrad && p.ksplit == 1 && p.out_bf16 && !p.accum && nk > 0 && (p.ldc & 7) == 0 && (p.BN & 31) == 0 &&
           (nt + 1) * p.BN <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
         // common case (bf16 activations, whole chunks): a lean loop -- the generic one below re-tests its options per
@@ -1028,6 +1031,7 @@ template <int ES>
 static int launch(const TcParams& p_in, int ntiles, cudaStream_t st) {
   TcParams p = p_in;
   p.epi = pick_epi(p);
+  if (p.acc_stride == 0) p.acc_stride = kMaxBN;
   static int stat_smem = -1;
   if (stat_smem < 0) {
     const char* e = getenv("COOCC_CONV_STATSMEM");
@@ -1113,14 +1117,31 @@ static int prepare_split(TcParams& p, int nk_total, cudaStream_t st, bool zero_o
   p.hstride = p.BN <= 128 ? 128 : 256;
   p.nacc = (p.MT * p.hstride <= 256) ? 2 : 1;
   {
+    static int acc4 = -1;
+    if (acc4 < 0) {
+      const char* e = getenv("COOCC_CONV_ACC4");
+      acc4 = (e && e[0] == '1') ? 1 : 0;      // measured slower than 256-row tiles with two buffers (91 vs 75 us): opt-in
+    }
+    if (acc4 && p.taps == 1 && p.BN <= 128) { p.MT = 1; p.nacc = 4; p.acc_stride = 128; }
+  }
+  {
     const int stage = kABytes * p.MT + (p.BN * 128 + 1023) / 1024 * 1024;
+    // (COOCC_CONV_DEEP_RING=1: up to 8 stages for the 1x1x1 layers.  Measured: no change -- 75 / 99 / 172 us for
+    // 128->64 / 128 / 256 on 640 k voxels either way; those layers are bound by the per-tile load -> MMA -> epilogue
+    // latency chain, not by bytes in flight -- so it stays off)
+    static int deep = -1;
+    if (deep < 0) {
+      const char* e = getenv("COOCC_CONV_DEEP_RING");
+      deep = (e && e[0] == '1') ? 1 : 0;
+    }
+    const int cap = (p.taps == 1 && deep) ? kMaxBRing : kStages;
     p.nstages = kRingBytes / stage;
-    if (p.nstages > kStages) p.nstages = kStages;
+    if (p.nstages > cap) p.nstages = cap;
     // statistics staging tiles go behind the ring when it leaves room (the 1x1x1 and narrow layers: exactly the
-    // ones whose epilogue is exposed)
-    // (they also stage the bf16 output rows for coalesced stores; a 1x1x1 layer gives up a ring stage for them)
-    if (p.taps == 1 && p.nstages == 4 && kRingBytes - 4 * stage < kStatBytes && kRingBytes - 3 * stage >= kStatBytes)
-      p.nstages = 3;
+    // ones whose epilogue is exposed); they also stage the bf16 output rows for coalesced stores, for which a 1x1x1
+    // layer gives up ring stages (down to 3)
+    if (p.taps == 1)
+      while (p.nstages > 3 && kRingBytes - p.nstages * stage < kStatBytes) --p.nstages;
     p.stat_off = (kRingBytes - p.nstages * stage >= kStatBytes) ? p.nstages * stage : 0;
   }
   const int ntm = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
@@ -1621,7 +1642,9 @@ static int wgrad_impl(const coocc_conv_desc* d, const void* x, const void* dy, f
   {
     const int stage = kABytes * p.MT + p.NT * ((p.BN * 128 + 1023) / 1024 * 1024);
     p.nstages = kRingBytes / stage;
-    if (p.nstages > kStages) p.nstages = kStages;
+    const char* e = getenv("COOCC_CONV_DEEP_RING");
+    const int cap = (taps == 1 && e && e[0] == '1') ? kMaxBRing : kStages;        // (opt-in, see prepare_split)
+    if (p.nstages > cap) p.nstages = cap;
   }
   const int base_tiles = ((p.M + kBM * p.MT - 1) / (kBM * p.MT)) * ((p.N + p.BN - 1) / p.BN) * ((taps + p.NT - 1) / p.NT);
   // split-K factor: tiles are dealt round-robin to the persistent CTAs, so pick the factor whose

@@ -54,13 +54,14 @@ __global__ void box_gather_bf16_kernel(const uint4* __restrict__ grid, long long
 // (no separate zero fill, no fp32 round trip)
 __global__ void box_scatter_bf16_kernel(const uint4* __restrict__ rows, int C8, int X, int Y, int Z, int bx, int by,
                                         int bz, uint4* __restrict__ grid, long long ld8) {
-  const long long v = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (v >= (long long)X * Y * Z) return;
-  const int z = v % Z, y = (v / Z) % Y, x = v / ((long long)Z * Y);
-  const bool in = x < bx && y < by && z < bz;
-  const uint4* s = rows + (((long long)x * by + y) * bz + z) * C8;
-  uint4* d = grid + v * ld8;
-  for (int c = threadIdx.x & 31; c < C8; c += 32) d[c] = in ? s[c] : make_uint4(0u, 0u, 0u, 0u);
+  const long long total = (long long)X * Y * Z * C8;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256LL) {
+    const long long v = i / C8;
+    const int c = (int)(i - v * C8);
+    const int z = v % Z, y = (v / Z) % Y, x = v / ((long long)Z * Y);
+    const bool in = x < bx && y < by && z < bz;
+    grid[v * ld8 + c] = in ? rows[(((long long)x * by + y) * bz + z) * C8 + c] : make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // torch.linspace(0, D, D)[i] (ATen's symmetric evaluation)
@@ -441,7 +442,9 @@ extern "C" int coocc_render_box_scatter_bf16(const void* rows, int C, int X, int
   int bx, by, bz;
   coocc_render_box(X, Y, Z, &bx, &by, &bz);
   const long long V = (long long)X * Y * Z;
-  box_scatter_bf16_kernel<<<(unsigned)((V + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  long long blocks = (V * (C / 8) + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  box_scatter_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4*>(rows), C / 8, X, Y, Z, bx, by, bz, reinterpret_cast<uint4*>(grid), ld / 8);
   return CK_LAUNCH();
 }
