@@ -40,6 +40,7 @@ _SIGS = {
     "coocc_version": (c_int, []),
     "coocc_conv3d_fwd": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p]),
     "coocc_conv3d_dgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "coocc_conv3d_dgrad_add": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p]),
     "coocc_conv3d_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "coocc_conv_tune": (c_int, [c_int, c_int]),
     "coocc_gsf_pack": (c_int, [c_void_p, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p]),

@@ -103,6 +103,8 @@ struct TcParams {
   int NA, NB;          // ring depths: extended A tiles (MT per entry), B tiles
   // parity-class launch of a stride-2 data gradient (dgrad_impl, `cls`): an explicit tap list -- im2col offsets and
   // weight taps are no longer tied to each other -- and output rows scattered to the fine grid
+  const void* addend;                // lean bf16 epilogue: out = acc + addend (bf16 rows, the gradient arriving through
+  long long ld_add;                  //   a skip connection; saves the separate add pass over the tensor)
   int b_kmajor;                      // dgrad: B is a transposed weight copy [Cin][taps][Cout] (K-major, like fprop)
   int epi;                           // epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two, splitting the column chunks)
   int stat_off;                      // byte offset of the statistics staging tiles behind the operand ring (0: none)
@@ -160,6 +162,17 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
 }
 __device__ __forceinline__ void sts_u32x4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+// a + b on 8 packed bf16 values, evaluated in fp32 and rounded once (what torch's bf16 add does)
+__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
+  const float lo = __uint_as_float(a << 16) + __uint_as_float(b << 16);
+  const float hi = __uint_as_float(a & 0xFFFF0000u) + __uint_as_float(b & 0xFFFF0000u);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 bf16x8_add(uint4 a, uint4 b) {
+  return make_uint4(bf16x2_add(a.x, b.x), bf16x2_add(a.y, b.y), bf16x2_add(a.z, b.z), bf16x2_add(a.w, b.w));
 }
 
 // Epilogue helper: per-column sum / sum of squares of a 32 x 32 accumulator chunk (row = lane) over the valid rows,
@@ -700,6 +713,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         const bool staged = stat_tile != 0u && !p.omap;
         const int nvalid = __popc(__ballot_sync(0xffffffffu, row_ok));          // valid rows are a prefix
         __nv_bfloat16* const obase = orow - (long long)lane * p.ldc;            // row 0 of this warp
+        // gradient of a skip connection added on the way out (same row index as the output, own row stride)
+        const __nv_bfloat16* const arow =
+            p.addend ? reinterpret_cast<const __nv_bfloat16*>(p.addend) + (long long)row * p.ld_add + nt * p.BN : nullptr;
+        const __nv_bfloat16* const abase = arow ? arow - (long long)lane * p.ld_add : nullptr;
         for (int c0 = csel * 32; c0 < p.BN; c0 += 1 << cshift) {
           uint32_t v[32];
           tmem_ld_32x32(t_base + (uint32_t)c0, v);
@@ -738,8 +755,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int r = 8 * j + (lane >> 2);
-              const uint4 val = lds_u32x4(stat_tile + (uint32_t)(64 * r + 16 * (pp ^ ((r >> 1) & 3))));
-              if (r < nvalid) *reinterpret_cast<uint4*>(obase + (long long)r * p.ldc + c0 + 8 * pp) = val;
+              uint4 val = lds_u32x4(stat_tile + (uint32_t)(64 * r + 16 * (pp ^ ((r >> 1) & 3))));
+              if (r < nvalid) {
+                if (abase != nullptr)
+                  val = bf16x8_add(val, __ldg(reinterpret_cast<const uint4*>(abase + (long long)r * p.ld_add + c0 + 8 * pp)));
+                *reinterpret_cast<uint4*>(obase + (long long)r * p.ldc + c0 + 8 * pp) = val;
+              }
             }
             __syncwarp();
           } else if (row_ok) {
@@ -751,7 +772,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[i + 2 * j]), __uint_as_float(v[i + 2 * j + 1]));
                 w4[j] = *reinterpret_cast<const uint32_t*>(&h);
               }
-              *reinterpret_cast<uint4*>(orow + c0 + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              uint4 val = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              if (arow != nullptr) val = bf16x8_add(val, __ldg(reinterpret_cast<const uint4*>(arow + c0 + i)));
+              *reinterpret_cast<uint4*>(orow + c0 + i) = val;
             }
           }
         }
@@ -1379,8 +1402,29 @@ __global__ void __launch_bounds__(256) transpose_w_kernel(const uint16_t* __rest
 
 // dX[v, ci] = sum_{tap,co} dY[v - tap + pad, co] W[co, tap, ci]; stride-1 convolutions only
 // (for stride 2 the caller scatters dY onto the input lattice first, see conv3d_dgrad docs).
+// dx[r][c] += addend[r][c] on bf16 rows (fallback of the fused skip-gradient add for launches that cannot take the
+// lean epilogue: split-K layers, ragged N tiles, strided data gradients)
+__global__ void __launch_bounds__(256) add_rows_bf16_kernel(__nv_bfloat16* __restrict__ dx, long long ldo,
+                                                            const __nv_bfloat16* __restrict__ addend, long long ld_add,
+                                                            long long M, int C) {
+  const long long total = M * C;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256LL) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    dx[r * ldo + c] = __float2bfloat16_rn(__bfloat162float(dx[r * ldo + c]) + __bfloat162float(addend[r * ld_add + c]));
+  }
+}
+static int add_rows_bf16(void* dx, long long ldo, const void* addend, long long ld_add, long long M, int C,
+                         cudaStream_t st) {
+  long long blocks = (M * C + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  add_rows_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(dx), ldo,
+                                                    reinterpret_cast<const __nv_bfloat16*>(addend), ld_add, M, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+
 static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, void* dxv, long long ldo,
-                      int accum, void* stream, int cls = -1) {
+                      int accum, void* stream, int cls = -1, const void* addend = nullptr, long long ld_add = 0) {
   int rc = check_desc(d);
   if (rc) return rc;
   if ((d->stride != 1) != (cls >= 0)) return COOCC_ERR_ARG;
@@ -1492,6 +1536,13 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, v
                         up_h);
     if (rc) return rc;
     const int ntiles = ((p.gX * p.nyb + p.MT - 1) / p.MT) * ((p.N + p.BN - 1) / p.BN);
+    const bool fuse_add = addend && p.out_bf16 && !accum && (ldo % 8) == 0 && (ld_add % 8) == 0 && (p.BN % 32) == 0 &&
+                          (p.N % p.BN) == 0;
+    if (fuse_add) { p.addend = addend; p.ld_add = ld_add; }
+    const auto finish = [&](int rc_) {
+      if (!rc_ && addend && !fuse_add) rc_ = add_rows_bf16(dxv, ldo, addend, ld_add, p.M, d->Cin, (cudaStream_t)stream);
+      return rc_;
+    };
     // bf16: run the big-grid data gradients on a transposed copy of the weights (K-major B operand, the forward's
     // configuration).  Reading W in place as an MN-major operand kept the tensor pipe at 67 % active against 79 % for
     // the forward of the same layer (profiles/r02_conv_full.summary.txt); the copy is a few MB per layer.
@@ -1514,11 +1565,11 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, v
       rc = make_tm_2d(&p.tmB, wt, es, d->Cin, (long long)taps * d->Cout, (long long)taps * d->Cout, ch, p.BN, false);
       if (!rc) rc = launch<2>(p, ntiles, (cudaStream_t)stream);
       cudaFreeAsync(wt, (cudaStream_t)stream);
-      return rc;
+      return finish(rc);
     }
     rc = make_tm_2d(&p.tmB, w, es, d->Cout, (long long)taps * d->Cin, (long long)taps * d->Cin, ch, ch, true);
     if (rc) return rc;
-    return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
+    return finish(es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream));
   }
   if (plain) {
     rc = make_tm_2d(&p.tmA, dy, es, p.M, d->Cout, d->ldy, ch, kBM, false);
@@ -1532,12 +1583,16 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, v
   if (rc) return rc;
   p.es = es;
   if ((rc = prepare_split(p, taps * ((d->Cout + ch - 1) / ch), (cudaStream_t)stream, false))) return rc;
+  const bool fuse_add = addend && p.ksplit == 1 && p.out_bf16 && !accum && (ldo % 8) == 0 && (ld_add % 8) == 0 &&
+                        (p.BN % 32) == 0 && (p.N % p.BN) == 0;
+  if (fuse_add) { p.addend = addend; p.ld_add = ld_add; }
   SplitScratch sc;
   if ((rc = split_scratch_begin(p, sc, (cudaStream_t)stream))) return rc;
   const int ntm_ = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
   const int ntiles = (p.mc ? (ntm_ + 1) / 2 : ntm_) * ((p.N + p.BN - 1) / p.BN) * p.ksplit;
   rc = es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
   const int rc2 = split_scratch_end(p, sc, (cudaStream_t)stream);
+  if (!rc && !rc2 && addend && !fuse_add) rc = add_rows_bf16(dxv, ldo, addend, ld_add, p.M, d->Cin, (cudaStream_t)stream);
   return rc ? rc : rc2;
 }
 
@@ -1746,6 +1801,13 @@ extern "C" int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const v
   split_free(&xs, st);
   split_free(&ws, st);
   return rc;
+}
+
+extern "C" int coocc_conv3d_dgrad_add(const coocc_conv_desc* d, const void* dy, const void* w, void* dx, long long ldo,
+                                      const void* addend, long long ld_add, void* stream) {
+  if (!d || !addend) return COOCC_ERR_ARG;
+  if (d->dtype != COOCC_DTYPE_BF16 || !d->out_bf16 || d->stride != 1) return COOCC_ERR_ARG;
+  return dgrad_impl(d, dy, w, dx, ldo, 0, stream, -1, addend, ld_add);
 }
 
 extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, void* dx,

@@ -220,8 +220,10 @@ class _Conv3dFn(torch.autograd.Function):
     """y[Vout,Cout] = conv3d(x[V,Cin], w[Cout,Cin,k,k,k]) (+bias)(relu), padding k//2."""
 
     @staticmethod
-    def forward(ctx, x2d, w5d, bias, dims, k, s, relu, want_stats=False, out_bf16=False):
+    def forward(ctx, x2d, w5d, bias, dims, k, s, relu, want_stats=False, out_bf16=False, skip=False):
         _require_cuda(x2d, w5d)
+        ctx.set_materialize_grads(False)
+        ctx.flags = (bool(want_stats), bool(skip))
         cout, cin = w5d.shape[0], w5d.shape[1]
         dtype = _DT[_PRECISION["mode"]]
         out_bf16 = bool(out_bf16) and dtype == DT_BF16
@@ -235,16 +237,26 @@ class _Conv3dFn(torch.autograd.Function):
         ctx.meta = (dims, odims, k, s, relu, bias is not None, dtype, cin, cout)
         ctx.wparam = w5d if getattr(w5d, "_coocc_grad", None) is not None else None
         ctx.x_bf16 = x2d.dtype == torch.bfloat16
+        outs = [y]
         if want_stats:
             ctx.mark_non_differentiable(stats)
-            return y, stats
-        return y
+            outs.append(stats)
+        if skip:
+            # x handed on as an OUTPUT of this node: a second consumer of x (residual branch, another head) that takes
+            # this alias sends its gradient into backward() below, where the data-gradient kernel adds it in its
+            # epilogue -- instead of autograd summing two [V, C] tensors in a separate pass
+            outs.append(x2d.view_as(x2d))
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
-    def backward(ctx, dy, _dstats=None):
+    def backward(ctx, dy, *more):
         xo, wo, y = ctx.saved_tensors
         dims, odims, k, s, relu, has_bias, dtype, cin, cout = ctx.meta
+        want_stats, skip = ctx.flags
+        dskip = more[1 if want_stats else 0] if skip else None
         L = _lib.lib()
+        if dy is None:                                      # only the alias was used downstream
+            return dskip, None, None, None, None, None, None, None, None, None
         dy = _as_rows(dy)
         want_db = has_bias and ctx.needs_input_grad[2]
         db = None
@@ -307,17 +319,29 @@ class _Conv3dFn(torch.autograd.Function):
             d = _conv_desc(dims, cin, cout, k, s, ldo, dyo.stride(0), dtype)
             d.out_bf16 = _is_bf16(dxb)
             flops = 2.0 * odims[0] * odims[1] * odims[2] * (k ** 3) * cin * cout
-            _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dyo), _p(wo), _p(dxb),
-                                                                          dxb.stride(0), _stream()),
-                              " %s %d->%d k%d s%d" % (dims, cin, cout, k, s)), "conv3d_dgrad")
+            fuse = (dskip is not None and d.out_bf16 and s == 1 and dtype == DT_BF16 and dskip.dtype == torch.bfloat16
+                    and dskip.dim() == 2 and dskip.stride(1) == 1 and dskip.stride(0) % 8 == 0)
+            if fuse:
+                _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad_add(
+                    ctypes.byref(d), _p(dyo), _p(wo), _p(dxb), dxb.stride(0), _p(dskip), dskip.stride(0), _stream()),
+                                  " %s %d->%d k%d s%d" % (dims, cin, cout, k, s)), "conv3d_dgrad_add")
+                dskip = None
+            else:
+                _lib.check(_timed("dgrad", flops, lambda: L.coocc_conv3d_dgrad(ctypes.byref(d), _p(dyo), _p(wo), _p(dxb),
+                                                                              dxb.stride(0), _stream()),
+                                  " %s %d->%d k%d s%d" % (dims, cin, cout, k, s)), "conv3d_dgrad")
             dx = dxb[:, :cin]
             if ctx.x_bf16 and dx.dtype != torch.bfloat16:
                 dx = dx.to(torch.bfloat16)
-        return dx, dw, db, None, None, None, None, None, None
+        if dskip is not None:
+            dx = dskip if dx is None else dx + dskip.to(dx.dtype)
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
-def conv3d(x2d, w5d, dims, k, s=1, bias=None, relu=False, want_stats=False, out_bf16=False):
-    return _Conv3dFn.apply(x2d, w5d, bias, dims, k, s, relu, want_stats, out_bf16)
+def conv3d(x2d, w5d, dims, k, s=1, bias=None, relu=False, want_stats=False, out_bf16=False, skip=False):
+    """skip=True appends an alias of x2d to the outputs: route x's OTHER consumer through it and its gradient is added
+    in this convolution's data-gradient epilogue (see _Conv3dFn.forward)."""
+    return _Conv3dFn.apply(x2d, w5d, bias, dims, k, s, relu, want_stats, out_bf16, skip)
 
 
 def _sync_group():

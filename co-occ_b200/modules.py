@@ -62,13 +62,25 @@ def batch_norm2d(x2d, bn):
                         bn.weight, bn.bias, use_batch, mom, bn.eps)
 
 
-def conv_bn_act(x2d, dims, conv, bn=None, relu=True, residual=None):
-    """conv -> BatchNorm (batch statistics from the conv epilogue) -> (+ residual) -> ReLU."""
+def conv_bn_act(x2d, dims, conv, bn=None, relu=True, residual=None, skip=False):
+    """conv -> BatchNorm (batch statistics from the conv epilogue) -> (+ residual) -> ReLU.
+    skip=True: returns (y, odims, x_alias); hand x_alias to the OTHER consumer of x (the residual branch) and its gradient
+    is added inside this convolution's data-gradient kernel (CF.conv3d) instead of in a separate pass."""
     k = conv.kernel_size[0]
     s = conv.stride[0]
     odims = tuple(CF.out_dim(n, k, s) for n in dims)
     fused = (bn is not None and bn.training and conv.bias is None and conv.out_channels % 4 == 0
              and bn.momentum is not None)
+    if skip:
+        if not (fused and torch.is_grad_enabled()):
+            return conv_bn_act(x2d, dims, conv, bn, relu, residual) + (x2d,)
+        y, stats, xs = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, want_stats=True, out_bf16=CF.act_bf16(), skip=True)
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        track = bn.track_running_stats
+        y = CF.bn_act(y, stats, bn.weight, bn.bias, residual, relu, bn.eps, bn.momentum,
+                      bn.running_mean if track else None, bn.running_var if track else None)
+        return y, odims, xs
     if fused:
         y, stats = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, want_stats=True, out_bf16=CF.act_bf16())
         if bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -140,11 +152,12 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward2d(self, x, dims):
-        out, odims = conv_bn_act(x, dims, self.conv1, self.bn1)
         if self.downsample is not None:
+            out, odims = conv_bn_act(x, dims, self.conv1, self.bn1)
             idn, _ = conv_bn_act(x, dims, self.downsample[0], self.downsample[1], relu=False)
         else:
-            idn = x
+            # identity shortcut: the residual gradient is added in conv1's data-gradient epilogue
+            out, odims, idn = conv_bn_act(x, dims, self.conv1, self.bn1, skip=True)
         out, _ = conv_bn_act(out, odims, self.conv2, self.bn2, relu=True, residual=idn)   # resnet3d.py:53-60
         return out, odims
 
@@ -329,7 +342,8 @@ class OccHead(nn.Module):
             feats = CF.resize_mix(occs, dims, d0, wts=w)
         else:
             feats = CF.resize_mix(occs, dims, d0) * (1.0 / self.num_level)
-        y, _ = conv_bn_act(feats, d0, self.occ_pred_conv[0], self.occ_pred_conv[1])
+        # (out_voxel_feats is also sampled by the fine stage: that gradient joins occ_pred_conv's data gradient)
+        y, _, feats = conv_bn_act(feats, d0, self.occ_pred_conv[0], self.occ_pred_conv[1], skip=True)
         occ, _ = conv_bn_act(y, d0, self.occ_pred_conv[3], None, relu=False)
         return {"out_voxel_feats": [CF.to_5d(feats, d0)], "occ": [CF.to_5d(occ, d0)]}
 

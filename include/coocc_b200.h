@@ -68,6 +68,11 @@ int coocc_conv3d_fwd(const coocc_conv_desc* d, const void* x, const void* w, voi
  * stride-1 call, the round-1 route, multiplies eight times as many zeros). */
 int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, void* dx, long long ldo,
                        void* stream);
+/* dx = dgrad(dy, w) + addend: the data gradient plus the gradient arriving through a skip connection of x (a residual
+ * branch, a second consumer), added in the convolution's epilogue instead of in a separate pass.  bf16 descriptors with
+ * bf16 output and stride 1 only; addend = [V][Cin] bf16 rows with row stride ld_add. */
+int coocc_conv3d_dgrad_add(const coocc_conv_desc* d, const void* dy, const void* w, void* dx, long long ldo,
+                           const void* addend, long long ld_add, void* stream);
 
 /* dw[co][tap][ci] += ... (fp32; caller zero-fills dw; split-K partial sums are added atomically). */
 int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
