@@ -111,6 +111,13 @@ struct TcParams {
   int tapmode;                       // 1: tap t reads im2col offset tap_off[t] and weight tap tap_w[t]
   unsigned char tap_off[8];          // kx | ky << 2 | kz << 4   (offsets 0 / 1)
   unsigned char tap_w[8];            // (kx * 3 + ky) * 3 + kz of the weight tensor
+  // all eight parity classes in ONE launch (tile = (class, mt, nt), class-major, classes ordered by tap count so the
+  // long tiles are dealt first): eight separate launches left the small grids on 4-20 SMs each
+  int ncls;                          // 0: single class (tap_off / tap_w / opx.. above), 8: class table below
+  unsigned char cls_ntaps[8];
+  unsigned char cls_par[8];          // px << 2 | py << 1 | pz
+  unsigned char cls_off[8][8];
+  unsigned char cls_w[8][8];
   int omap;                          // 1: output row (i, j, k) of the coarse grid -> fine voxel (2i+opx, 2j+opy, 2k+opz)
   int opx, opy, opz, fX, fY, fZ;
 };
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   const int cnum = p.mc ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int ntm_sched = p.mc ? (ntm + 1) / 2 : ntm;
   const int ntg = (p.taps + p.NT - 1) / p.NT;       // wgrad: tap groups
-  const int ntiles = wgrad ? ntm * ntn * ntg * p.ksplit : ntm_sched * ntn * p.ksplit;
+  const int ntiles = wgrad ? ntm * ntn * ntg * p.ksplit : ntm_sched * ntn * p.ksplit * (p.ncls ? p.ncls : 1);
   const int kb_per_tap = (p.Kc + E::BKE - 1) / E::BKE;
 
   if (threadIdx.x == 0) {
@@ -382,13 +389,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       uint32_t phase = 0;
       for (int tile = cidx; tile < ntiles; tile += cnum) {
         int mt, nt, it0, it1;          // it = flattened (tap, k-block) iteration
-        int wg_tap = 0;
+        int wg_tap = 0, cls = 0;
         if (!wgrad) {
           int t = tile;
           const int sp = t % p.ksplit; t /= p.ksplit;
           nt = t % ntn;
           mt = p.mc ? 2 * (t / ntn) + crank : t / ntn;
-          const int nk_total = p.taps * kb_per_tap;
+          if (p.ncls) { cls = mt / ntm; mt -= cls * ntm; }
+          const int nk_total = (p.ncls ? (int)p.cls_ntaps[cls] : p.taps) * kb_per_tap;
           it0 = (int)((long long)nk_total * sp / p.ksplit);
           it1 = (int)((long long)nk_total * (sp + 1) / p.ksplit);
         } else {
@@ -409,9 +417,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           // dgrad walks the mirrored tap of the weight tensor
           int wtap = (p.mode == MODE_DGRAD) ? (p.taps - 1 - tap) : tap;
           if (p.tapmode) {
-            const int o = p.tap_off[tap];
+            const int o = p.ncls ? p.cls_off[cls][tap] : p.tap_off[tap];
             kx = o & 3; ky = (o >> 2) & 3; kz = (o >> 4) & 3;
-            wtap = p.tap_w[tap];
+            wtap = p.ncls ? p.cls_w[cls][tap] : p.tap_w[tap];
           }
           {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -580,7 +588,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         int nk, ntap = 1;
         {
           const int sp = tile % p.ksplit;
-          const int tot = wgrad ? p.nvb : p.taps * kb_per_tap;
+          const int ntaps_t = p.ncls ? (int)p.cls_ntaps[tile / p.ksplit / ntn / ntm] : p.taps;
+          const int tot = wgrad ? p.nvb : ntaps_t * kb_per_tap;
           nk = (int)((long long)tot * (sp + 1) / p.ksplit) - (int)((long long)tot * sp / p.ksplit);
           if (wgrad) {
             const int tg = tile / p.ksplit / ntn / ntm;
@@ -654,12 +663,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = cidx; tile < ntiles; tile += cnum) {
       int mt, nt, tap = 0, nk = 1;
+      int opx = p.opx, opy = p.opy, opz = p.opz;
       if (!wgrad) {
         int t = tile;
         const int sp = t % p.ksplit; t /= p.ksplit;
         nt = t % ntn;
         mt = p.mc ? 2 * (t / ntn) + crank : t / ntn;
-        const int tot = p.taps * kb_per_tap;
+        int ntaps_t = p.taps;
+        if (p.ncls) {
+          const int cls = mt / ntm;
+          mt -= cls * ntm;
+          ntaps_t = p.cls_ntaps[cls];
+          const int par = p.cls_par[cls];
+          opx = (par >> 2) & 1; opy = (par >> 1) & 1; opz = par & 1;
+        }
+        const int tot = ntaps_t * kb_per_tap;
         nk = (int)((long long)tot * (sp + 1) / p.ksplit) - (int)((long long)tot * sp / p.ksplit);
       } else {
         int t = tile;
@@ -689,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       if (p.omap && row_ok) {
         const int z = row % p.oZ, t = row / p.oZ;
         const int y = t % p.oY, x = t / p.oY;
-        const int fx = 2 * x + p.opx, fy = 2 * y + p.opy, fz = 2 * z + p.opz;
+        const int fx = 2 * x + opx, fy = 2 * y + opy, fz = 2 * z + opz;
         row_ok = fx < p.fX && fy < p.fY && fz < p.fZ;
         row = (fx * p.fY + fy) * p.fZ + fz;
       }
@@ -1441,6 +1459,7 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, v
     const int ch = 128 / es;
     const int px = (cls >> 2) & 1, py = (cls >> 1) & 1, pz = cls & 1;
     if (d->ksize == 1 && cls != 0) return COOCC_ERR_ARG;
+    if (cls > 8) return COOCC_ERR_ARG;
     const int oX = out_dim(d->X, d->ksize, 2), oY = out_dim(d->Y, d->ksize, 2), oZ = out_dim(d->Z, d->ksize, 2);
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -1455,11 +1474,10 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, v
     }
     p.tapmode = 1;
     int nt = 0;
-    if (d->ksize == 1) {
-      p.tap_off[0] = 0; p.tap_w[0] = 0; nt = 1;
-    } else {
-      const int par[3] = {px, py, pz};
-      int offs[3][2], wts[3][2], cnt[3];
+    // tap list of one parity class: im2col offsets and weight taps
+    const auto class_taps = [](int cx, int cy, int cz, unsigned char* off, unsigned char* wt) {
+      const int par[3] = {cx, cy, cz};
+      int offs[3][2], wts[3][2], cnt[3], n = 0;
       for (int a = 0; a < 3; ++a) {
         if (par[a] == 0) { cnt[a] = 1; offs[a][0] = 0; wts[a][0] = 1; }
         else { cnt[a] = 2; offs[a][0] = 0; wts[a][0] = 2; offs[a][1] = 1; wts[a][1] = 0; }
@@ -1467,10 +1485,26 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, v
       for (int a = 0; a < cnt[0]; ++a)
         for (int b = 0; b < cnt[1]; ++b)
           for (int c = 0; c < cnt[2]; ++c) {
-            p.tap_off[nt] = (unsigned char)(offs[0][a] | (offs[1][b] << 2) | (offs[2][c] << 4));
-            p.tap_w[nt] = (unsigned char)((wts[0][a] * 3 + wts[1][b]) * 3 + wts[2][c]);
-            ++nt;
+            off[n] = (unsigned char)(offs[0][a] | (offs[1][b] << 2) | (offs[2][c] << 4));
+            wt[n] = (unsigned char)((wts[0][a] * 3 + wts[1][b]) * 3 + wts[2][c]);
+            ++n;
           }
+      return n;
+    };
+    if (d->ksize == 1) {
+      p.tap_off[0] = 0; p.tap_w[0] = 0; nt = 1;
+    } else if (cls == 8) {
+      // every class in one launch, most taps first: 7 | 3 5 6 | 1 2 4 | 0
+      static const int order[8] = {7, 3, 5, 6, 1, 2, 4, 0};
+      p.ncls = 8;
+      for (int i = 0; i < 8; ++i) {
+        const int c = order[i];
+        p.cls_par[i] = (unsigned char)c;
+        p.cls_ntaps[i] = (unsigned char)class_taps((c >> 2) & 1, (c >> 1) & 1, c & 1, p.cls_off[i], p.cls_w[i]);
+      }
+      nt = 8;                       // (upper bound: sizes the split / MT heuristics; tiles use cls_ntaps)
+    } else {
+      nt = class_taps(px, py, pz, p.tap_off, p.tap_w);
     }
     p.taps = nt;
     p.Kc = d->Cout;
@@ -1498,7 +1532,7 @@ static int dgrad_impl(const coocc_conv_desc* d, const void* dy, const void* w, v
     p.ksplit = 1;            // (split-K accumulates into a contiguous zeroed [M, N] block; the class rows are scattered)
     p.mc = 0;
     const int ntm_ = (p.M + kBM * p.MT - 1) / (kBM * p.MT);
-    const int ntiles = ntm_ * ((p.N + p.BN - 1) / p.BN);
+    const int ntiles = ntm_ * ((p.N + p.BN - 1) / p.BN) * (p.ncls ? p.ncls : 1);
     return es == 4 ? launch<4>(p, ntiles, (cudaStream_t)stream) : launch<2>(p, ntiles, (cudaStream_t)stream);
   }
   const int es = d->dtype == COOCC_DTYPE_TF32 ? 4 : 2;
@@ -1825,7 +1859,13 @@ extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, cons
       const size_t eb = d->out_bf16 ? 2 : 4;
       if (cudaMemset2DAsync(dx, (size_t)ldo * eb, 0, (size_t)d->Cin * eb, (size_t)Vf, st) != cudaSuccess) return COOCC_ERR_CUDA;
     }
+    static int one_launch = -1;
+    if (one_launch < 0) {
+      const char* e = getenv("COOCC_DGRAD_S2_ONE");
+      one_launch = (e && e[0] == '0') ? 0 : 1;
+    }
     if (d->dtype != COOCC_DTYPE_TF32X3) {
+      if (ncls == 8 && one_launch) return dgrad_impl(d, dy, w, dx, ldo, 0, stream, 8);
       for (int c = 0; c < ncls && !rc; ++c) rc = dgrad_impl(d, dy, w, dx, ldo, 0, stream, c);
       return rc;
     }
@@ -1835,7 +1875,7 @@ extern "C" int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, cons
     coocc_conv_desc t = *d;
     t.dtype = COOCC_DTYPE_TF32;
     t.ldy = gs.ld;
-    for (int c = 0; c < ncls && !rc; ++c) {
+    for (int c = (ncls == 8 && one_launch) ? 8 : 0; c < (ncls == 8 && one_launch ? 9 : ncls) && !rc; ++c) {
       rc = dgrad_impl(&t, gs.hi, ws.hi, dx, ldo, 0, stream, c);
       if (!rc) rc = dgrad_impl(&t, gs.hi, ws.lo, dx, ldo, 1, stream, c);
       if (!rc) rc = dgrad_impl(&t, gs.lo, ws.hi, dx, ldo, 1, stream, c);
