@@ -384,10 +384,47 @@ def zero_pool_begin(device):
     else:
         zp["buf"].zero_()
     zp["cursor"], zp["armed"] = 0, True
+    zp["step"] = zp.get("step", 0) + 1
+    _PENDING_COUNTERS.clear()
 
 
 def zero_pool_end():
     _ZERO_POOL["armed"] = False
+    if _PENDING_COUNTERS:
+        torch._foreach_add_(list(_PENDING_COUNTERS), 1)      # one launch for all num_batches_tracked counters
+        _PENDING_COUNTERS.clear()
+
+
+_PENDING_COUNTERS = []
+
+
+def count_batch(counter):
+    """num_batches_tracked += 1 (nn.BatchNorm semantics).  Inside a bracketed step the 36 one-element increments are
+    deferred to zero_pool_end() and issued as one multi-tensor launch."""
+    if _ZERO_POOL["armed"] and counter.is_cuda:
+        _PENDING_COUNTERS.append(counter)
+    else:
+        counter.add_(1)
+
+
+def _bn_grad_sink(gamma, beta, C):
+    """[2, C] view of the gradient arena covering (d beta, d gamma) when ddp.GradArena laid the two gradients out back
+    to back, the step is bracketed (arena cleared before the step, one backward per step) and this BatchNorm has not
+    been used yet in this step; else None.  The backward-reduce kernel then accumulates its sums straight into the
+    gradients: no zero-filled scratch, no two AccumulateGrad launches per BatchNorm."""
+    zp = _ZERO_POOL
+    if not zp["armed"]:
+        return None
+    gs, bs = getattr(gamma, "_coocc_grad", None), getattr(beta, "_coocc_grad", None)
+    if gs is None or bs is None or gamma.grad is not gs or beta.grad is not bs:
+        return None
+    if not (gs.is_contiguous() and bs.is_contiguous() and gs.numel() == C and bs.numel() == C
+            and gs.data_ptr() == bs.data_ptr() + 4 * C and bs.data_ptr() % 16 == 0):
+        return None
+    if getattr(gamma, "_coocc_sink_step", None) == zp["step"]:
+        return None                       # second use in one step: the sums would mix
+    gamma._coocc_sink_step = zp["step"]
+    return bs.as_strided((2, C), (C, 1))
 
 
 def zeros_small(shape, device):
@@ -448,6 +485,7 @@ class _BNActFn(torch.autograd.Function):
         # y > 0 from x, gamma, beta (the forward's own expression) and `out` is not read again
         ctx.save_for_backward(x, out if (relu and residual is not None) else None, mi, gamma, beta)
         ctx.meta = (relu, residual is not None, count, res_dtype)
+        ctx.bn_params = (gamma, beta) if getattr(gamma, "_coocc_grad", None) is not None else (None, None)
         return out
 
     @staticmethod
@@ -458,7 +496,10 @@ class _BNActFn(torch.autograd.Function):
         V, C = x.shape
         dout = _as_rows(dout, x.dtype)
         bf = _is_bf16(x)
-        sums = zeros_small((2, C), x.device)
+        gparam, bparam = ctx.bn_params
+        sink = _bn_grad_sink(gparam, bparam, C) if (gparam is not None and ctx.needs_input_grad[2]
+                                                    and ctx.needs_input_grad[3]) else None
+        sums = sink if sink is not None else zeros_small((2, C), x.device)
         ldo = out.stride(0) if out is not None else 0
         e = x.element_size()
         _lib.check(_timed("hbm:bn_act_bwd_reduce", float(e * V * C * (3 if out is not None else 2)),
@@ -468,7 +509,10 @@ class _BNActFn(torch.autograd.Function):
         local = sums
         if count != V:                      # SyncBN: batch terms use the sums over all ranks
             dist = _sync_group()
-            local = sums.clone()            # dgamma / dbeta stay per-rank (DDP averages them)
+            if sink is not None:
+                sums = sums.clone()         # the arena keeps the per-rank sums (DDP averages them)
+            else:
+                local = sums.clone()        # dgamma / dbeta stay per-rank (DDP averages them)
             _stats_all_reduce(dist, sums)
         dx = torch.empty(V, C, device=x.device, dtype=x.dtype)
         dres = torch.empty(V, C, device=x.device, dtype=x.dtype) if has_res else None
@@ -479,6 +523,12 @@ class _BNActFn(torch.autograd.Function):
                                                            _stream())), "bn_act_bwd_apply")
         if has_res and dres.dtype != res_dtype:
             dres = dres.to(res_dtype)
+        if sink is not None:
+            for prm in (bparam, gparam):
+                cb = getattr(prm, "_coocc_on_grad", None)       # ddp.GradReducer: this gradient is final
+                if cb is not None:
+                    cb(prm)
+            return dx, None, None, None, dres, None, None, None, None, None, None
         return dx, None, local[1], local[0], dres, None, None, None, None, None, None
 
 

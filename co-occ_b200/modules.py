@@ -54,7 +54,7 @@ def _cl3d_all(module):
 def batch_norm2d(x2d, bn):
     """BatchNorm3d over a [V,C] view (N*D*H*W = V rows), same running-stat updates."""
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+        CF.count_batch(bn.num_batches_tracked)
     mom = 0.0 if bn.momentum is None else bn.momentum
     use_batch = bn.training or bn.running_mean is None
     return F.batch_norm(x2d, bn.running_mean if not bn.training or bn.track_running_stats else None,
@@ -76,7 +76,7 @@ def conv_bn_act(x2d, dims, conv, bn=None, relu=True, residual=None, skip=False):
             return conv_bn_act(x2d, dims, conv, bn, relu, residual) + (x2d,)
         y, stats, xs = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, want_stats=True, out_bf16=CF.act_bf16(), skip=True)
         if bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+            CF.count_batch(bn.num_batches_tracked)
         track = bn.track_running_stats
         y = CF.bn_act(y, stats, bn.weight, bn.bias, residual, relu, bn.eps, bn.momentum,
                       bn.running_mean if track else None, bn.running_var if track else None)
@@ -84,7 +84,7 @@ def conv_bn_act(x2d, dims, conv, bn=None, relu=True, residual=None, skip=False):
     if fused:
         y, stats = CF.conv3d(x2d, _cl3d_(conv), dims, k, s, want_stats=True, out_bf16=CF.act_bf16())
         if bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+            CF.count_batch(bn.num_batches_tracked)
         track = bn.track_running_stats
         y = CF.bn_act(y, stats, bn.weight, bn.bias, residual, relu, bn.eps, bn.momentum,
                       bn.running_mean if track else None, bn.running_var if track else None)
