@@ -1132,10 +1132,30 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
 
 // split the reduction of an under-filled fprop/dgrad launch over several CTAs
 static int pick_ksplit(int ntiles, int nk_total) {
-  if (ntiles * 2 > g_num_sms || nk_total < 8) return 1;
-  int ks = g_num_sms / ntiles;
-  if (ks > nk_total / 4) ks = nk_total / 4;
-  return ks < 1 ? 1 : ks;
+  static int model = -1;
+  if (model < 0) {
+    const char* e = getenv("COOCC_CONV_KSPLIT_MODEL");
+    model = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!model) {
+    if (ntiles * 2 > g_num_sms || nk_total < 8) return 1;
+    int ks = g_num_sms / ntiles;
+    if (ks > nk_total / 4) ks = nk_total / 4;
+    return ks < 1 ? 1 : ks;
+  }
+  // Wave-quantisation model, in k-block units (one k-block of a 128 x 256 tile ~ 0.4 us): the persistent CTAs take
+  // ceil(tiles * ks / SMs) rounds of nk / ks k-blocks plus a fixed cost per tile (pipeline fill, epilogue -- atomic
+  // for ks > 1), and a split launch pays for its scratch memset, the bf16 conversion and the statistics pass.
+  // 79 or 158 tiles on 148 SMs (the 50x50x4 levels) run at 53 % unsplit; 3-7 splits bring that to ~85 %.
+  if (nk_total < 16 || ntiles >= 4 * g_num_sms) return 1;
+  double best = 1e30;
+  int best_ks = 1;
+  for (int ks = 1; ks <= 16 && ks * 8 <= nk_total; ++ks) {
+    const long long waves = ((long long)ntiles * ks + g_num_sms - 1) / g_num_sms;
+    const double t = (double)waves * ((double)nk_total / ks + (ks > 1 ? 16.0 : 10.0)) + (ks > 1 ? 64.0 : 0.0);
+    if (t < best * 0.97) { best = t; best_ks = ks; }      // (a larger split has to win by 3 %)
+  }
+  return best_ks;
 }
 
 static int prepare_split(TcParams& p, int nk_total, cudaStream_t st, bool zero_out = true) {
