@@ -52,13 +52,15 @@ def main(path, top=None, traffic_json=None):
 
     if traffic_json and traffic:
         import json
-        # launch order of tools/ncu_conv_case.py: (fwd, dgrad, wgrad) of 512->256 then of 128->128, 3x3x3, 200x200x16, bf16
-        names = ["fwd 512->256", "dgrad 512->256", "wgrad 512->256", "fwd 128->128", "dgrad 128->128", "wgrad 128->128"]
+        # tools/profile_round.sh captures launches 7..12 of tools/ncu_conv_case.py (`-s 6 -c 6`): the six 512->256 launches
+        # are skipped, what is profiled is (fwd, dgrad, wgrad) of the 128->128 3x3x3 layer on the 200x200x16 grid, twice
+        names = ["fwd 128->128", "dgrad 128->128", "wgrad 128->128", "fwd 128->128 (2nd)", "dgrad 128->128 (2nd)",
+                 "wgrad 128->128 (2nd)"]
         per = {n: t for n, t in zip(names, traffic)}
         ref = per.get("fwd 128->128", traffic[0])
-        note = "ncu --set full, tc_conv_kernel 3x3x3 on the 200x200x16 grid, bf16 in/out, DRAM read+write MB per launch: " + \
+        note = "ncu --set full, tc_conv_kernel 3x3x3 128->128 on the 200x200x16 grid, bf16 in/out, DRAM read+write MB per launch: " + \
             "; ".join("%s %.1f (%.0f us)" % (n, (t["dram_read"] + t["dram_write"]) / 1e6, t["us"]) for n, t in per.items()) + \
-            ".  Algorithmic bytes: 128->128 327.7 MB, 512->256 983.0 MB (x read once + y written once, bf16).  `bytes` = fwd 128->128."
+            ".  Algorithmic bytes: 327.7 MB (x read once + y written once, bf16).  `bytes` = fwd 128->128."
         with open(traffic_json, "w") as f:
             json.dump(dict(bytes=ref["dram_read"] + ref["dram_write"], note=note, per_launch=per), f, indent=1)
 
