@@ -9,6 +9,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libcoocc_b200.so")
+if os.environ.get("COOCC_SO"):          # A/B runs against another build of the library (tools/)
+    SO_PATH = os.environ["COOCC_SO"]
 
 _lib = None
 

@@ -670,7 +670,10 @@ extern "C" int coocc_trilinear_bwd(const void* dout, long long ldd, int oX, int 
                                    const float* wts, long long ldw, void* dsrc, long long lds, int sX, int sY,
                                    int sZ, int act_bf16, void* stream) {
   if (!dout || !dsrc || (C & 3) || (lds & 3) || (ldd & 3)) return COOCC_ERR_ARG;
-  if (g_tl_separable && (long long)oX * oY * oZ >= 4096) {
+  // separable passes win from x4 upwards (each source voxel would gather 10^3+ output rows directly); for x2 the direct
+  // gather is faster (B200, 200x200x16 <- 100x100x8: C=128 0.43 vs 0.49 ms, C=256 0.82 vs 1.15 ms; x4: 0.38 vs 0.29;
+  // x8: 1.10 vs 0.56; tools/tl_axis_bench.py)
+  if (g_tl_separable && (long long)oX * oY * oZ >= 4096 && (long long)oX * oY * oZ >= 27LL * sX * sY * sZ) {
     return act_bf16 ? trilinear_bwd_separable<bf16_t>((const bf16_t*)dout, ldd, oX, oY, oZ, C, wts, ldw, (bf16_t*)dsrc,
                                                       lds, sX, sY, sZ, (cudaStream_t)stream)
                     : trilinear_bwd_separable<float>((const float*)dout, ldd, oX, oY, oZ, C, wts, ldw, (float*)dsrc,
