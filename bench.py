@@ -60,6 +60,7 @@ def parse():
                     help="coocc: co-occ_b200/optim.py FusedAdamW (one multi-tensor kernel that also writes the bf16 weight "
                          "operands); torch: torch.optim.AdamW(fused=True)")
     ap.add_argument("--no-peer", action="store_true", help="SyncBN statistics through NCCL instead of the peer-memory kernel")
+    ap.add_argument("--no-pipeline", action="store_true", help="no index pipelining across steps (GraphedStep next_inputs)")
     ap.add_argument("--no-fine", action="store_true", help="coarse head only (cascade_ratio=1), the round-1 step")
     ap.add_argument("--launch", default=os.environ.get("COOCC_LAUNCH", "graph"), choices=["graph", "eager"],
                     help="graph: the step is replayed as one CUDA graph (co-occ_b200/graph.py); eager: one launch per kernel")
@@ -238,8 +239,10 @@ def workload_config(args, cfg, fine):
                 parallelism="dp%d (replicas only)" % args.gpus, precision=args.precision,
                 optimizer="torch.optim.AdamW(fused)" if args.optimizer == "torch" else
                 "coocc FusedAdamW (norm_decay_mult 0, grad_clip 5, bf16 shadow, gradient arena)",
-                launch="cuda_graph (whole step, co-occ_b200/graph.py)" if args.launch == "graph" else "eager",
-                setup_steps="2 untimed calls before the warm-up (lazy init, graph capture)")
+                launch=("cuda_graph (whole step, co-occ_b200/graph.py%s)" % (
+                    "" if args.no_pipeline else "; the next batch's neighbour-search tables are computed on a side branch "
+                    "of the graph, under the GSFusion backward and the optimizer")) if args.launch == "graph" else "eager",
+                setup_steps="3 untimed calls before the warm-up (lazy init, one graph capture per buffer parity)")
 
 
 # ------------------------------------------------------------------------------------------
@@ -385,10 +388,15 @@ def run_ours(args, cfg):
     def call(fn, d):
         return fn(d["img"], d["pts"], d["geom"], d["gt_depth"], d["gt_img"], d["gt_occ"], d.get("img_feats"), d["transform"])
 
-    def step(d):
+    def step(d, nxt=None):
         # forward + backward + gradient all-reduce + AdamW; replayed as one CUDA graph after the first
-        # calls (--launch graph), launched kernel by kernel otherwise
-        return call(gstep, d)
+        # calls (--launch graph), launched kernel by kernel otherwise.  nxt = the following step's inputs (already on
+        # the device, as a prefetching loader has them): its neighbour-search tables are computed inside this step's
+        # graph, under the GSFusion backward and the optimizer (graph.GraphedStep, index pipelining)
+        if nxt is None or args.no_pipeline:
+            return call(gstep, d)
+        return gstep(d["img"], d["pts"], d["geom"], d["gt_depth"], d["gt_img"], d["gt_occ"], d.get("img_feats"),
+                     d["transform"], next_inputs=(nxt["img"], nxt["pts"]))
 
     def eager_step(d, optimizer=None):
         o = optimizer or opt
@@ -425,16 +433,16 @@ def run_ours(args, cfg):
         return ms
 
     resident = to_device()
-    for _ in range(2):                       # setup: lazy init (eager), graph capture
-        step(resident)
+    for _ in range(3):                       # setup: lazy init (eager), graph captures (two buffer parities)
+        step(resident, resident)
     for _ in range(args.warmup):
-        step(resident)
+        step(resident, resident)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     _lib.CALLS["n"] = 0
     r0 = gstep.stats["replays"]
-    ms = timed(lambda: step(resident), args.steps)
+    ms = timed(lambda: step(resident, resident), args.steps)
     # kernel-launching C-ABI calls executed in the timed region: the eager ones + those replayed inside graphs
     launches = _lib.CALLS["n"] + (gstep.stats["replays"] - r0) * gstep.launches_per_replay
     # end-to-end: host (pinned) inputs in, loss out, every step.  The copy of step i+1's inputs is
@@ -442,24 +450,32 @@ def run_ours(args, cfg):
     # H2D copy and D2H loss read happen inside the timed region.
     last = {}
     copy_stream = torch.cuda.Stream()
-    pending = {}
+    queue = []                 # [(inputs on the device, copy-done event)]: this step's and the next step's
 
     def prefetch():
         with torch.cuda.stream(copy_stream):
-            pending["d"] = to_device()
-            pending["ev"] = torch.cuda.Event()
-            pending["ev"].record(copy_stream)
+            d = to_device()
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        queue.append((d, ev))
 
     def e2e_step():
-        torch.cuda.current_stream().wait_event(pending["ev"])
-        d = pending["d"]
-        for t in d.values():
-            if torch.is_tensor(t):
-                t.record_stream(torch.cuda.current_stream())
-        prefetch()                                    # next step's inputs, overlapped with this step
-        last["loss"] = float(step(d).item())
+        # a loader two batches ahead: step i runs on batch i and prepares the index tables of batch i+1 (both on the
+        # device by now); the copy of batch i+2 is issued here and overlaps this step
+        cur = torch.cuda.current_stream()
+        for d_, ev_ in queue[:2]:
+            cur.wait_event(ev_)
+            for t in d_.values():
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
+        d, nxt = queue[0][0], queue[1][0]
+        queue.pop(0)
+        prefetch()
+        last["loss"] = float(step(d, nxt).item())
 
     prefetch()
+    prefetch()
+    e2e_step()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     clk = clocks.stop() if rank == 0 else None
@@ -600,9 +616,15 @@ def run_ours(args, cfg):
                 opt_m = make_opt()
                 gs = coocc_b200.GraphedStep(model, opt_m, reducer, LOSS_KEYS, enabled=(args.launch == "graph"))
                 for _ in range(2 + 3):
-                    call(gs, resident)
+                    gs(resident["img"], resident["pts"], resident["geom"], resident["gt_depth"], resident["gt_img"],
+                       resident["gt_occ"], resident.get("img_feats"), resident["transform"],
+                       next_inputs=None if args.no_pipeline else (resident["img"], resident["pts"]))
                 n_t = 5
-                ms_m = timed(lambda: call(gs, resident), n_t) / n_t
+                ms_m = timed(lambda: gs(resident["img"], resident["pts"], resident["geom"], resident["gt_depth"],
+                                        resident["gt_img"], resident["gt_occ"], resident.get("img_feats"),
+                                        resident["transform"],
+                                        next_inputs=None if args.no_pipeline else (resident["img"], resident["pts"])),
+                             n_t) / n_t
                 cm = conv_roofline([(ms_, w) for ms_, w, t in bracketed_step(opt_m) if not t.startswith("hbm:")])
                 pk = peak / 2 if mode == "tf32" else peak / 6
                 runs[mode] = dict(ms_per_step=ms_m, value=nvox / (ms_m / 1e3), unit=UNIT,

@@ -800,27 +800,58 @@ def gsf_index(img5d, pts5d, K, fix_k1_fps=False, want_parts=False):
                 raise ReferenceQuirk("reference BiFuser_N(knum=1) fails for N_query > 2048 (fps_NN_fast returns "
                                      "None, bifuser_n.py:62-85); pass fix_k1_fps=True for the intended result")
             fps_jobs.append((name, qi, ki, nb))
-    if fps_jobs:
-        reps = [torch.empty(FPS_NUM, device=dev, dtype=torch.int32) for _ in fps_jobs]
-        j0 = fps_jobs[0]
-        j1 = fps_jobs[1] if len(fps_jobs) > 1 else None
-        _lib.check(L.coocc_gsf_fps(_p(lists[j0[1]]), _pb(counts, 4 * j0[1]), _p(reps[0]),
-                                   _p(lists[j1[1]]) if j1 else None, _pb(counts, 4 * j1[1]) if j1 else None,
-                                   _p(reps[1]) if j1 else None, max(j[3] for j in fps_jobs), FPS_NUM, Y, Z, st),
-                   "gsf_fps")
-        for (name, qi, ki, nq), rep in zip(fps_jobs, reps):
-            topk_idx = torch.empty(FPS_NUM, K, device=dev, dtype=torch.int32)
-            topk_d2 = torch.empty(FPS_NUM, K, device=dev, dtype=torch.int32)
-            _lib.check(L.coocc_gsf_rep_topk(_p(rep), FPS_NUM, _p(lists[qi]), _p(ranks[ki]), X, Y, Z, K,
-                                            _p(topk_idx), _p(topk_d2), st), "gsf_rep_topk")
-            winner = torch.full((K, V), -1, device=dev, dtype=torch.int32)
-            group = torch.empty(FPS_NUM, BALL_SAMPLES, device=dev, dtype=torch.int32) if want_parts else None
-            _lib.check(L.coocc_gsf_ball_assign(_p(rep), FPS_NUM, _p(lists[qi]), _p(ranks[qi]), _p(topk_idx), X, Y, Z,
-                                               K, BALL_RADIUS, BALL_SAMPLES, V, _p(winner), _p(group), st),
-                       "gsf_ball_assign")
-            state[name] = dict(rep_idx=rep, nrep=FPS_NUM, topk_idx=topk_idx, topk_d2=topk_d2, winner=winner,
-                               group=group)
+    if fps_jobs and ov is not None and ov.get("tables") is not None:
+        # index tables of this input computed ahead of time (graph.GraphedStep: on a side branch of the PREVIOUS step's
+        # graph, under its GSFusion backward and optimizer)
+        for name, qi, ki, nb in fps_jobs:
+            state[name] = ov["tables"][name]
+    elif fps_jobs:
+        state.update(gsf_index_tables(pro, fps_jobs, K, want_parts))
     return cat, state
+
+
+def gsf_index_tables(pro, fps_jobs, K, want_parts=False, out=None):
+    """FPS + rep->key top-K + ball assignment for the directions in `fps_jobs` [(name, query grid, key grid, launch
+    bound)] on the compacted lists of `pro` (gsf_prologue).  No host synchronisation; `out` = a previous result whose
+    tensors are reused (fixed addresses for CUDA graphs).  Weight-independent: depends on the inputs' occupancy only."""
+    L = _lib.lib()
+    st = _stream()
+    lists, ranks, counts = pro["lists"], pro["ranks"], pro["counts"]
+    X, Y, Z = pro["dims"]
+    V = X * Y * Z
+    dev = lists.device
+    res = {}
+    mk = lambda name, key, *shape: (out[name][key] if out is not None else
+                                    torch.empty(*shape, device=dev, dtype=torch.int32))
+    reps = [mk(j[0], "rep_idx", FPS_NUM) for j in fps_jobs]
+    j0 = fps_jobs[0]
+    j1 = fps_jobs[1] if len(fps_jobs) > 1 else None
+    _lib.check(L.coocc_gsf_fps(_p(lists[j0[1]]), _pb(counts, 4 * j0[1]), _p(reps[0]),
+                               _p(lists[j1[1]]) if j1 else None, _pb(counts, 4 * j1[1]) if j1 else None,
+                               _p(reps[1]) if j1 else None, max(j[3] for j in fps_jobs), FPS_NUM, Y, Z, st),
+               "gsf_fps")
+    for (name, qi, ki, nq), rep in zip(fps_jobs, reps):
+        topk_idx = mk(name, "topk_idx", FPS_NUM, K)
+        topk_d2 = mk(name, "topk_d2", FPS_NUM, K)
+        _lib.check(L.coocc_gsf_rep_topk(_p(rep), FPS_NUM, _p(lists[qi]), _p(ranks[ki]), X, Y, Z, K,
+                                        _p(topk_idx), _p(topk_d2), st), "gsf_rep_topk")
+        if out is not None:
+            winner = out[name]["winner"]
+            winner.fill_(-1)
+        else:
+            winner = torch.full((K, V), -1, device=dev, dtype=torch.int32)
+        group = torch.empty(FPS_NUM, BALL_SAMPLES, device=dev, dtype=torch.int32) if want_parts else None
+        _lib.check(L.coocc_gsf_ball_assign(_p(rep), FPS_NUM, _p(lists[qi]), _p(ranks[qi]), _p(topk_idx), X, Y, Z,
+                                           K, BALL_RADIUS, BALL_SAMPLES, V, _p(winner), _p(group), st),
+                   "gsf_ball_assign")
+        res[name] = dict(rep_idx=rep, nrep=FPS_NUM, topk_idx=topk_idx, topk_d2=topk_d2, winner=winner, group=group)
+    return res
+
+
+# graph.GraphedStep: called once at the start of the fuser's backward -- the point of a step behind which only
+# HBM-bound work is left (GSFusion backward, gradient reduction tail, optimizer): the next step's index tables are
+# computed on a side stream from there on
+TAIL_HOOK = None
 
 
 def gsf_nn_indices(state, name):
@@ -884,6 +915,8 @@ class _GSFusionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dcat):
+        if TAIL_HOOK is not None:
+            TAIL_HOOK()
         L = _lib.lib()
         st = _stream()
         cat, knn_w, knn_b = ctx.saved_tensors

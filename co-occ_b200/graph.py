@@ -33,7 +33,9 @@ def _dbg(msg):
 
 class GraphedStep:
     """step(img, pts, geom, gt_depth, gt_img, gt_occ) -> loss (a 0-dim tensor that the next
-    replay overwrites).
+    replay overwrites).  Gradients live in the buffers of the graph that produced them: with an optimizer inside the
+    graph that is invisible; without one (optimizer=None) `p.grad` refers to the most recently CAPTURED graph, so read
+    gradients only while a single graph exists.
 
     model      HotPath (train mode)
     optimizer  torch optimizer constructed with capturable=True (or None: forward+backward only)
@@ -42,7 +44,7 @@ class GraphedStep:
     """
 
     def __init__(self, model, optimizer=None, reducer=None, loss_keys=None, bucket=8192, max_graphs=4,
-                 enabled=True):
+                 enabled=True, pipeline_index=None):
         self.model, self.opt, self.reducer = model, optimizer, reducer
         self.loss_keys = loss_keys
         self.bucket, self.max_graphs = int(bucket), int(max_graphs)
@@ -56,6 +58,19 @@ class GraphedStep:
         self._stream = None         # capture stream; the warm-up step runs on it too, so that autograd's
         self._warm = False
         self._last = None           # AccumulateGrad nodes live on the stream the capture uses
+        # Index pipelining (step(..., next_inputs=...)): the neighbour search of BiFuser_N (FPS + top-K + ball assignment,
+        # 3.2 ms, 2047 dependent FPS rounds on 32 SMs) depends on the inputs' occupancy only, so the tables of step i+1
+        # are computed on a side branch of step i's graph, forked at the start of the fuser's backward -- the point
+        # behind which only HBM-bound kernels are left (GSFusion backward, gradient-reduction tail, optimizer).  Two
+        # sets of pack / table buffers alternate; a step whose tables were not prepared computes them up front.
+        if pipeline_index is None:
+            pipeline_index = os.environ.get("COOCC_PIPELINE_INDEX", "1") != "0"
+        self.pipeline_index = bool(pipeline_index)
+        self._pro = [None, None]
+        self._tables = [None, None]
+        self._par = 0
+        self._ahead = None          # dict(img, pts, n_img, n_pts, par): what the last step prepared
+        self._side = None
         self._tr_fixed, self._tr_len = None, 0
 
     # ------------------------------------------------------------------------------------
@@ -120,11 +135,18 @@ class GraphedStep:
         tr[-1] = self._tr_fixed
         return tuple(tr)
 
-    def __call__(self, img, pts, geom, gt_depth, gt_img, gt_occ=None, img_feats=None, transform=None):
+    def __call__(self, img, pts, geom, gt_depth, gt_img, gt_occ=None, img_feats=None, transform=None,
+                 next_inputs=None):
+        """next_inputs = (img_voxel_feats, pts_voxel_feats) of the FOLLOWING step (device tensors, e.g. from a
+        prefetching loader): enables index pipelining; pass the very same tensor objects as img / pts next time."""
         args = (img, pts, geom, gt_depth, gt_img, gt_occ, img_feats, transform)
         if not self.enabled:
             self.stats["eager"] += 1
             return self._eager(*args)
+        if self.pipeline_index and next_inputs is not None and self._warm and \
+                not (self.opt is not None and len(self.opt.state) == 0):
+            return self._call_pipelined(args, next_inputs)
+        self._ahead = None
         K = self.model.occ_fuser.knum
         # optimizer state must exist before a capture (lazy state init allocates and syncs)
         if self._stream is None:
@@ -177,6 +199,78 @@ class GraphedStep:
         self._last = entry
         return entry["loss"]
 
+    # ------------------------------------------------------------------------------------
+    def _covered(self, n_img, n_pts, K):
+        return (n_img > CF.FPS_NUM and n_pts > CF.FPS_NUM and not (K > 1 and n_pts > n_img)
+                and (K > 1 or self.model.occ_fuser.fix_k1_fps))
+
+    def _alloc_tables(self, K, V, dev):
+        mk = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.int32)
+        return {name: dict(rep_idx=mk(CF.FPS_NUM), nrep=CF.FPS_NUM, topk_idx=mk(CF.FPS_NUM, K), topk_d2=mk(CF.FPS_NUM, K),
+                           winner=mk(K, V), group=None) for name in ("A", "B")}
+
+    @staticmethod
+    def _jobs(nb_img, nb_pts):
+        # functional.gsf_index: direction A = LiDAR queries / image keys, B = image queries / LiDAR keys
+        return [("A", 1, 0, nb_pts), ("B", 0, 1, nb_img)]
+
+    def _call_pipelined(self, args, next_inputs):
+        img, pts, geom, gt_depth, gt_img, gt_occ, img_feats, transform = args
+        K = self.model.occ_fuser.knum
+        p = self._par
+        ah, self._ahead = self._ahead, None
+        prepared = ah is not None and ah["img"] is img and ah["pts"] is pts and ah["par"] == p
+        if prepared:
+            n_img, n_pts = ah["n_img"], ah["n_pts"]
+        else:
+            self._pro[p] = CF.gsf_prologue(img, pts, out=self._pro[p])
+            n_img, n_pts = (int(v) for v in self._pro[p]["counts"].tolist())
+        if not self._covered(n_img, n_pts, K):
+            self.stats["eager"] += 1
+            return self._eager(*args)
+        X, Y, Z = self._pro[p]["dims"]
+        V = X * Y * Z
+        nb_img, nb_pts = self._round(n_img, V), self._round(n_pts, V)
+        if self._tables[p] is None:
+            self._tables[p] = self._alloc_tables(K, V, img.device)
+        if self._tables[1 - p] is None:
+            self._tables[1 - p] = self._alloc_tables(K, V, img.device)
+        if not prepared:
+            CF.gsf_index_tables(self._pro[p], self._jobs(nb_img, nb_pts), K, out=self._tables[p])
+        # the following step's inputs: pack + compact now (as every step does), tables inside this step's graph
+        nimg, npts = next_inputs
+        self._pro[1 - p] = CF.gsf_prologue(nimg, npts, out=self._pro[1 - p])
+        m_img, m_pts = (int(v) for v in self._pro[1 - p]["counts"].tolist())      # the step's one host sync
+        nxt = None
+        if self._covered(m_img, m_pts, K):
+            mb_img, mb_pts = self._round(m_img, V), self._round(m_pts, V)
+            nxt = dict(prologue=self._pro[1 - p], jobs=self._jobs(mb_img, mb_pts), out=self._tables[1 - p], K=K)
+        key = (nb_img, nb_pts, (mb_img, mb_pts) if nxt is not None else None, p)
+        self._bind_static(geom, gt_depth, gt_img, gt_occ, img_feats, transform)
+        ov = dict(prologue=self._pro[p], n_img=n_img, n_pts=n_pts, nb_img=nb_img, nb_pts=nb_pts, tables=self._tables[p])
+        entry = self.graphs.get(key)
+        if entry is None:
+            if len(self.graphs) >= self.max_graphs:
+                self.stats["eager"] += 1
+                return self._eager(*args)
+            try:
+                entry = self._capture(key, ov, img, pts, nxt)
+            except Exception as e:  # noqa: BLE001 -- same policy as the plain path
+                self.enabled = False
+                self.capture_error = "%s: %s" % (type(e).__name__, (str(e).splitlines() or [""])[0][:200])
+                _dbg("capture failed, falling back to eager: " + self.capture_error)
+                torch.cuda.synchronize()
+                self.stats["eager"] += 1
+                return self._eager(*args)
+        entry["graph"].replay()
+        self.stats["replays"] += 1
+        self.stats["pipelined"] = self.stats.get("pipelined", 0) + (1 if prepared else 0)
+        self._last = entry
+        if nxt is not None:
+            self._ahead = dict(img=nimg, pts=npts, n_img=m_img, n_pts=m_pts, par=1 - p)
+        self._par = 1 - p
+        return entry["loss"]
+
     def check(self):
         """Raise what the eager path would have raised from device-side error flags of the last
         replayed step (synchronises; the reference's IndexError cases)."""
@@ -187,7 +281,7 @@ class GraphedStep:
             if int(flag.item()) != 0:
                 raise exc
 
-    def _capture(self, key, ov, img, pts):
+    def _capture(self, key, ov, img, pts, nxt=None):
         from . import _lib
         s = self.static
         if self.opt is not None:
@@ -201,6 +295,21 @@ class GraphedStep:
         n0 = _lib.CALLS["n"]
         CF.GSF_OVERRIDE = ov
         CF.DEFERRED_ERRORS = deferred = []
+        fired = [False]
+        if nxt is not None:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+
+            def tail_hook():
+                # (called from the autograd thread at the start of the fuser's backward)
+                if fired[0]:
+                    return
+                fired[0] = True
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    CF.gsf_index_tables(nxt["prologue"], nxt["jobs"], nxt["K"], out=nxt["out"])
+            CF.TAIL_HOOK = tail_hook
         try:
             _dbg("capture begin key=%s" % (key,))
             # thread_local: NCCL's watchdog / heartbeat threads query events while this thread captures
@@ -216,7 +325,13 @@ class GraphedStep:
                 if self.opt is not None:
                     self.opt.step()
                 loss = loss.detach()
+                if nxt is not None:
+                    if fired[0]:
+                        torch.cuda.current_stream().wait_stream(self._side)     # join the side branch
+                    else:           # the fuser's backward did not run (inputs without gradient): no overlap, same result
+                        CF.gsf_index_tables(nxt["prologue"], nxt["jobs"], nxt["K"], out=nxt["out"])
         finally:
+            CF.TAIL_HOOK = None
             CF.GSF_OVERRIDE = None
             CF.DEFERRED_ERRORS = None
             CF.zero_pool_end()

@@ -135,3 +135,50 @@ def test_graph_falls_back_to_eager_outside_covered_branches():
         assert l2 < l0 or l1 < l0       # the optimizer is stepping
     finally:
         coocc_b200.set_precision("tf32")
+
+
+def test_pipelined_index_matches_plain_graph():
+    """Index pipelining (GraphedStep(..., next_inputs=...)): the neighbour-search tables of scene i+1 are computed on
+    a side branch of step i's graph.  Integer work: the tables a step consumes must be bit-identical to the ones
+    computed from scratch for that scene; the training run (AdamW inside the graphs, small learning rate as in
+    test_graph_training_steps_track_eager) must track the plain graph's: same losses, same accumulated update."""
+    from coocc_b200 import functional as CF
+    coocc_b200.set_precision("fp32")
+    try:
+        lr = 1e-5
+        seeds = (0, 1, 2, 1, 0, 2, 2)
+        scenes = [_scene("c1", s) for s in seeds]
+        m_a, o_a = _build("c1", lr=lr)
+        m_b, o_b = _build("c1", lr=lr)
+        p0 = copy.deepcopy(m_a.state_dict())
+        m_b.load_state_dict(copy.deepcopy(p0))
+        plain = coocc_b200.GraphedStep(m_a, o_a, None, KEYS, bucket=1 << 20, pipeline_index=False)
+        piped = coocc_b200.GraphedStep(m_b, o_b, None, KEYS, bucket=1 << 20, pipeline_index=True)
+        K = m_b.occ_fuser.knum
+        for i, sc in enumerate(scenes):
+            nx = scenes[(i + 1) % len(scenes)]
+            la = float(plain(*sc))
+            lb = float(piped(*sc, next_inputs=(nx[0], nx[1])))
+            piped.check()
+            assert abs(la - lb) <= 1e-3 * abs(la), (i, la, lb)
+            if i >= 1:
+                # the tables prepared for the NEXT scene by the step that just ran == a fresh computation
+                p = piped._par
+                pro = CF.gsf_prologue(nx[0], nx[1])
+                n_img, n_pts = (int(v) for v in pro["counts"].tolist())
+                ref = CF.gsf_index_tables(pro, piped._jobs(n_img, n_pts), K)
+                torch.cuda.synchronize()
+                for name in ("A", "B"):
+                    nq = n_pts if name == "A" else n_img
+                    for k in ("rep_idx", "topk_idx", "topk_d2"):
+                        assert torch.equal(piped._tables[p][name][k], ref[name][k]), (i, name, k)
+                    assert torch.equal(piped._tables[p][name]["winner"][:, :nq], ref[name]["winner"][:, :nq]), (i, name)
+        assert piped.stats["captures"] == 2                      # one graph per buffer parity
+        assert piped.stats.get("pipelined", 0) == len(scenes) - 2    # every step after the bootstrap used prepared tables
+        dot = ne = ng = 0.0
+        for (k, p_), q in zip(m_a.named_parameters(), m_b.parameters()):
+            de, dg = (p_.detach() - p0[k]).double(), (q.detach() - p0[k]).double()
+            dot, ne, ng = dot + float((de * dg).sum()), ne + float((de * de).sum()), ng + float((dg * dg).sum())
+        assert dot / (ne * ng) ** 0.5 > 0.9 and 0.9 < (ng / ne) ** 0.5 < 1.1, (dot / (ne * ng) ** 0.5, (ng / ne) ** 0.5)
+    finally:
+        coocc_b200.set_precision("tf32")
