@@ -50,6 +50,8 @@ _SIGS = {
     "coocc_gsf_compact": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "coocc_gsf_fps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "coocc_gsf_fps_tune": (c_int, [c_int, c_int]),
+    "coocc_gsf_fps_signal": (c_int, [c_int]),
+    "coocc_gsf_fps_gate": (c_int, [c_int, c_void_p]),
     "coocc_gsf_rep_topk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "coocc_gsf_ball_assign": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "coocc_gsf_direct_nn": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -74,6 +76,7 @@ _SIGS = {
     "coocc_render_box": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "coocc_render_box_gather": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "coocc_render_box_scatter_add": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "coocc_conv_set_sm_budget": (c_int, [c_int]),
     "coocc_relu_bias_bwd": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "coocc_render_box_gather_bf16": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "coocc_render_box_scatter_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),

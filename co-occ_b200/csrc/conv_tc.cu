@@ -1068,6 +1068,15 @@ static int pick_epi(const TcParams& p) {
   return kEpiWarps;
 }
 
+// SMs the persistent grids may use (0 = all).  graph.GraphedStep lowers it while it captures the convolutions that
+// run next to the FPS side branch (32 SMs for its two 16-CTA clusters): a persistent grid of 148 CTAs with 32 SMs
+// taken would run its last 32 CTAs as a second wave.
+static int g_sm_budget = 0;
+extern "C" int coocc_conv_set_sm_budget(int n) {
+  g_sm_budget = n > 0 ? n : 0;
+  return 0;
+}
+
 template <int ES>
 static int launch(const TcParams& p_in, int ntiles, cudaStream_t st) {
   TcParams p = p_in;
@@ -1091,7 +1100,8 @@ static int launch(const TcParams& p_in, int ntiles, cudaStream_t st) {
   cudaLaunchAttribute attr[1];
   if (p.mc) {
     // ntiles counts CTA pairs
-    const int pairs = ntiles < g_num_sms / 2 ? ntiles : g_num_sms / 2;
+    const int sms = (g_sm_budget > 0 && g_sm_budget < g_num_sms) ? g_sm_budget : g_num_sms;
+    const int pairs = ntiles < sms / 2 ? ntiles : sms / 2;
     cfg.gridDim = dim3(2 * pairs, 1, 1);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -1100,7 +1110,8 @@ static int launch(const TcParams& p_in, int ntiles, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    cfg.gridDim = dim3(ntiles < g_num_sms ? ntiles : g_num_sms, 1, 1);
+    const int sms = (g_sm_budget > 0 && g_sm_budget < g_num_sms) ? g_sm_budget : g_num_sms;
+    cfg.gridDim = dim3(ntiles < sms ? ntiles : sms, 1, 1);
   }
   cfg.blockDim = dim3(128 + 32 * p.epi, 1, 1);
   cfg.dynamicSmemBytes = kSmemBytes;

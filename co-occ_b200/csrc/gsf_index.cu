@@ -363,7 +363,7 @@ __device__ long long g_fps_trace[16 * 64 * 8];
 // warp touches 0-2 slots per round however many points it owns: the round latency no longer grows
 // with N.  Running distances and coordinates live in shared memory.
 __global__ void __launch_bounds__(kFpsThreads, 1)
-fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, int S) {
+fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, int S, int* started) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned CS = cluster.num_blocks();
   const unsigned rank = cluster.block_rank();
@@ -442,6 +442,9 @@ fps_kernel(FpsJob job0, FpsJob job1, int m, int Y, int Z, int log2bs_override, i
   }
   __syncthreads();
   cluster.sync();
+  // every CTA of this cluster is resident: tell a gate kernel on another stream (coocc_gsf_fps_gate) that the
+  // convolution it holds back may now take the remaining SMs
+  if (started != nullptr && rank == 0 && tid == 0) atomicAdd(started, 1);
 
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
@@ -765,7 +768,8 @@ extern "C" int coocc_gsf_compact(const unsigned char* flags, int V, int* list, i
   return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
 }
 
-static int g_fps_cs = 0, g_fps_flags = 0;
+static int g_fps_cs = 0, g_fps_flags = 0, g_fps_signal = 0;
+__device__ int g_fps_started = 0;
 
 static size_t fps_smem_bytes(int S) {
   return ((size_t)2 * S * kFpsThreads + (size_t)5 * kFpsWarps * S) * sizeof(uint32_t);
@@ -809,8 +813,34 @@ extern "C" int coocc_gsf_fps(const int* list0, const int* count0, int* out0, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, fps_kernel, j0, j1, m, Y, Z, -1, S);
+  int* started = nullptr;
+  if (g_fps_signal && cudaGetSymbolAddress(reinterpret_cast<void**>(&started), g_fps_started) != cudaSuccess)
+    return COOCC_ERR_CUDA;
+  e = cudaLaunchKernelEx(&cfg, fps_kernel, j0, j1, m, Y, Z, -1, S, started);
   return e == cudaSuccess ? 0 : COOCC_ERR_CUDA;
+}
+
+// Index pipelining (co-occ_b200/graph.py): the FPS clusters of the NEXT step run on a side branch next to the last
+// convolution of this step's backward, which is captured on the SMs they leave free.  Which of the two kernels the
+// block scheduler places first when both become ready is not defined (stream priorities are not honoured inside
+// an instantiated graph without per-node priorities), and a convolution placed first would scatter over all GPCs
+// and leave no 16 free SMs in one GPC for a cluster.  So the order is made explicit: launches issued while the signal
+// is on count their resident clusters in g_fps_started, and a one-thread gate kernel in front of the convolution
+// waits for them (and resets the counter).  The clusters do not depend on the gate, so this cannot deadlock.
+extern "C" int coocc_gsf_fps_signal(int on) {
+  g_fps_signal = on ? 1 : 0;
+  return 0;
+}
+__global__ void fps_gate_kernel(int* started, int nclusters) {
+  while (atomicAdd(started, 0) < nclusters) __nanosleep(200);
+  *started = 0;
+  __threadfence();
+}
+extern "C" int coocc_gsf_fps_gate(int nclusters, void* stream) {
+  int* started = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&started), g_fps_started) != cudaSuccess) return COOCC_ERR_CUDA;
+  fps_gate_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(started, nclusters);
+  return cudaGetLastError() == cudaSuccess ? 0 : COOCC_ERR_CUDA;
 }
 
 // tuning hook (benchmarks only): force the cluster size (0 = automatic) and exchange variant flags

@@ -224,6 +224,8 @@ class _Conv3dFn(torch.autograd.Function):
         _require_cuda(x2d, w5d)
         ctx.set_materialize_grads(False)
         ctx.flags = (bool(want_stats), bool(skip))
+        global PRE_TAIL_MARK
+        ctx.pre_tail, PRE_TAIL_MARK = PRE_TAIL_MARK, False
         cout, cin = w5d.shape[0], w5d.shape[1]
         dtype = _DT[_PRECISION["mode"]]
         out_bf16 = bool(out_bf16) and dtype == DT_BF16
@@ -306,6 +308,8 @@ class _Conv3dFn(torch.autograd.Function):
             else:
                 # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
                 dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
+        if ctx.pre_tail and PRE_TAIL_HOOK is not None:
+            PRE_TAIL_HOOK()        # graph.GraphedStep: fork the next step's index branch before the LAST convolution
         if ctx.needs_input_grad[0]:
             # the data gradient is written in the storage type of x (bf16 activations stay bf16)
             if ctx.x_bf16 and dtype == DT_BF16:
@@ -847,6 +851,11 @@ def gsf_index_tables(pro, fps_jobs, K, want_parts=False, out=None):
         res[name] = dict(rep_idx=rep, nrep=FPS_NUM, topk_idx=topk_idx, topk_d2=topk_d2, winner=winner, group=group)
     return res
 
+
+# set by BiFuser_N.forward right before the convolution that consumes the concat: its data gradient is the last
+# convolution of a step's backward.  PRE_TAIL_HOOK (graph.GraphedStep) runs just before that launch.
+PRE_TAIL_MARK = False
+PRE_TAIL_HOOK = None
 
 # graph.GraphedStep: called once at the start of the fuser's backward -- the point of a step behind which only
 # HBM-bound work is left (GSFusion backward, gradient reduction tail, optimizer): the next step's index tables are

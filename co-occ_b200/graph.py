@@ -71,6 +71,11 @@ class GraphedStep:
         self._par = 0
         self._ahead = None          # dict(img, pts, n_img, n_pts, par): what the last step prepared
         self._side = None
+        # fork before the last convolution of the backward (its grid shrunk to the SMs the index branch leaves free)
+        # instead of behind it: hides the whole 3.2 ms instead of the 1.8 ms of the non-conv tail
+        self.early_fork = os.environ.get("COOCC_PIPELINE_EARLY", "1") != "0"
+        self._num_sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count \
+            if torch.cuda.is_available() else 148
         self._tr_fixed, self._tr_len = None, 0
 
     # ------------------------------------------------------------------------------------
@@ -296,20 +301,41 @@ class GraphedStep:
         CF.GSF_OVERRIDE = ov
         CF.DEFERRED_ERRORS = deferred = []
         fired = [False]
+        lib = _lib.lib()
         if nxt is not None:
             if self._side is None:
-                self._side = torch.cuda.Stream()
+                self._side = torch.cuda.Stream(priority=-1)     # its clusters are placed before the next conv's CTAs
             side = self._side
 
-            def tail_hook():
-                # (called from the autograd thread at the start of the fuser's backward)
+            def fork(gate=False):
                 if fired[0]:
                     return
                 fired[0] = True
                 side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    CF.gsf_index_tables(nxt["prologue"], nxt["jobs"], nxt["K"], out=nxt["out"])
+                lib.coocc_gsf_fps_signal(1 if gate else 0)
+                try:
+                    with torch.cuda.stream(side):
+                        CF.gsf_index_tables(nxt["prologue"], nxt["jobs"], nxt["K"], out=nxt["out"])
+                finally:
+                    lib.coocc_gsf_fps_signal(0)
+                if gate:
+                    # hold the next kernel of this stream back until both FPS clusters are resident (csrc/gsf_index.cu)
+                    _lib.check(lib.coocc_gsf_fps_gate(len(nxt["jobs"]), CF._stream()), "gsf_fps_gate")
+
+            def pre_tail_hook():
+                # (autograd thread, before the data gradient of the fuser's first convolution -- the last convolution
+                # of the backward.)  The index branch takes 32 SMs (two 16-CTA FPS clusters): the convolution is
+                # captured with a persistent grid on the remaining ones instead of paying a second wave.
+                if self.early_fork:
+                    fork(gate=True)
+                    lib.coocc_conv_set_sm_budget(self._num_sms - 32)
+
+            def tail_hook():
+                # (start of the fuser's backward: only HBM-bound kernels from here on)
+                lib.coocc_conv_set_sm_budget(0)
+                fork()
             CF.TAIL_HOOK = tail_hook
+            CF.PRE_TAIL_HOOK = pre_tail_hook
         try:
             _dbg("capture begin key=%s" % (key,))
             # thread_local: NCCL's watchdog / heartbeat threads query events while this thread captures
@@ -332,6 +358,8 @@ class GraphedStep:
                         CF.gsf_index_tables(nxt["prologue"], nxt["jobs"], nxt["K"], out=nxt["out"])
         finally:
             CF.TAIL_HOOK = None
+            CF.PRE_TAIL_HOOK = None
+            lib.coocc_conv_set_sm_budget(0)
             CF.GSF_OVERRIDE = None
             CF.DEFERRED_ERRORS = None
             CF.zero_pool_end()

@@ -132,7 +132,9 @@ class BiFuser_N(nn.Module):
         dims = tuple(img_voxel_feats.shape[2:])
         cat = CF.gsfusion_concat(img_voxel_feats, pts_voxel_feats, self.knn_enc[0].weight,
                                  self.knn_enc[0].bias, self.knum, self.fix_k1_fps)
+        CF.PRE_TAIL_MARK = True      # (this convolution's data gradient is the last convolution of the backward)
         y, _ = conv_bn_act(cat, dims, self.con_enc[0], self.con_enc[1])
+        CF.PRE_TAIL_MARK = False
         y, _ = conv_bn_act(y, dims, self.con_enc[3], self.con_enc[4])
         return CF.to_5d(y, dims)
 

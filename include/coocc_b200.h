@@ -73,6 +73,9 @@ int coocc_conv3d_dgrad(const coocc_conv_desc* d, const void* dy, const void* w, 
  * bf16 output and stride 1 only; addend = [V][Cin] bf16 rows with row stride ld_add. */
 int coocc_conv3d_dgrad_add(const coocc_conv_desc* d, const void* dy, const void* w, void* dx, long long ldo,
                            const void* addend, long long ld_add, void* stream);
+/* SMs the persistent convolution grids may occupy from now on (0 = all): lowered by the step runner while it captures
+ * the launches that overlap the FPS side branch. */
+int coocc_conv_set_sm_budget(int n);
 
 /* dw[co][tap][ci] += ... (fp32; caller zero-fills dw; split-K partial sums are added atomically). */
 int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
@@ -103,6 +106,11 @@ int coocc_gsf_fps(const int* list0, const int* count0, int* out0, const int* lis
                   int* out1, int n_max, int m, int Y, int Z, void* stream);
 /* benchmark hook: force the FPS cluster size (0 = automatic) and exchange-variant flags */
 int coocc_gsf_fps_tune(int cluster_size, int flags);
+/* Ordering of a side-stream FPS launch against a persistent kernel on another stream (index pipelining of the step
+ * runner): FPS launches issued while the signal is on report their resident clusters; the gate is a one-thread kernel
+ * that returns once `nclusters` have started (and clears the count). */
+int coocc_gsf_fps_signal(int on);
+int coocc_gsf_fps_gate(int nclusters, void* stream);
 /* K nearest keys (d2 <= 176 <=> dist < 13.3) of each representative, order (d2 asc, key asc);
  * out_idx = position in the key list or -1, out_d2 = squared distance or -1. */
 int coocc_gsf_rep_topk(const int* rep_idx, int nrep, const int* qlist, const int* key_rank, int X, int Y,
