@@ -77,6 +77,7 @@ _SIGS = {
     "coocc_render_box_gather": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "coocc_render_box_scatter_add": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "coocc_conv_set_sm_budget": (c_int, [c_int]),
+    "coocc_conv_set_dynamic": (c_int, [c_int]),
     "coocc_relu_bias_bwd": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "coocc_render_box_gather_bf16": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "coocc_render_box_scatter_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),

@@ -48,6 +48,7 @@ constexpr int kRingBytes = 216 * 1024;                  // operand ring(s), cut 
 constexpr int kMaxBRing = 8;          // ky-fused path: weight-tile ring depth bound
 constexpr int kMaxARing = 4;          // ky-fused path: extended activation-tile ring depth bound
 constexpr int kMaxAcc = 4;            // TMEM accumulator buffers (512 columns / acc_stride)
+constexpr int kSched = 4;             // dynamic tile scheduler: ring of published tile indices
 constexpr int kStatAccBytes = 8192;   // per-CTA running BatchNorm sums: [epilogue warp][column chunk][lane] float2
 constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 512 /*barriers*/ + kStatAccBytes;
 static_assert(kSmemBytes <= 232448, "shared memory");
@@ -103,6 +104,7 @@ struct TcParams {
   int NA, NB;          // ring depths: extended A tiles (MT per entry), B tiles
   // parity-class launch of a stride-2 data gradient (dgrad_impl, `cls`): an explicit tap list -- im2col offsets and
   // weight taps are no longer tied to each other -- and output rows scattered to the fine grid
+  int* sched;                        // dynamic tile scheduler: {next tile, finished CTAs} in global memory, or nullptr
   const void* addend;                // lean bf16 epilogue: out = acc + addend (bf16 rows, the gradient arriving through
   long long ld_add;                  //   a skip connection; saves the separate add pass over the tensor)
   int b_kmajor;                      // dgrad: B is a transposed weight copy [Cin][taps][Cout] (K-major, like fprop)
@@ -251,7 +253,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   uint64_t* emptya_bar = fulla_bar + kMaxARing;
   uint64_t* tfull_bar = emptya_bar + kMaxARing; // [kMaxAcc] accumulator ready
   uint64_t* tempty_bar = tfull_bar + kMaxAcc;   // [kMaxAcc] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kMaxAcc);
+  uint64_t* sfull_bar = tempty_bar + kMaxAcc;   // [kSched] scheduled tile published
+  uint64_t* sempty_bar = sfull_bar + kSched;    // [kSched] ... and read by every consumer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty_bar + kSched);
+  int* sched_tile = reinterpret_cast<int*>(tmem_slot + 1);      // [kSched]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -284,6 +289,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       mbar_init(&fulla_bar[s], 1);
       mbar_init(&emptya_bar[s], 1);
     }
+    for (int s = 0; s < kSched; ++s) {
+      mbar_init(&sfull_bar[s], 1);
+      mbar_init(&sempty_bar[s], 1u + (uint32_t)p.epi);     // the MMA thread + one arrive per epilogue warp
+    }
     for (int s = 0; s < kMaxAcc; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], (uint32_t)p.epi);   // one arrive per epilogue warp
@@ -296,6 +305,52 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   if (p.mc) cluster_sync_all();       // peer barriers must exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // ---- tile scheduler --------------------------------------------------------------------
+  // static (p.sched == nullptr): CTA c takes tiles c, c + grid, ...  Dynamic: tiles are handed out by an atomic counter,
+  // so a CTA that gets its SM late (another kernel -- the FPS side branch of the step runner, NCCL -- holds it when
+  // the grid launches) finds the remaining tiles or none at all instead of a static share that would run as a
+  // second wave.  The producer thread fetches (one tile ahead, the atomic's latency is off the critical path) and
+  // publishes the index through a small shared-memory ring; the MMA thread and the epilogue warps read it there.
+  // The last CTA to see the end resets the counters for the next launch that uses them.
+  const bool dyn = p.sched != nullptr;
+  int sched_next = 0;                                       // producer thread only
+  auto tile_produce = [&](int it_) -> int {
+    if (!dyn) {
+      const int t = cidx + it_ * cnum;
+      return t < ntiles ? t : -1;
+    }
+    const int slot = it_ % kSched;
+    mbar_wait(&sempty_bar[slot], (uint32_t)((it_ / kSched) & 1) ^ 1u);
+    int t = (it_ == 0) ? atomicAdd(&p.sched[0], 1) : sched_next;
+    if (t >= ntiles) t = -1;
+    sched_tile[slot] = t;
+    mbar_arrive(&sfull_bar[slot]);
+    if (t >= 0) {
+      sched_next = atomicAdd(&p.sched[0], 1);
+    } else if (atomicAdd(&p.sched[1], 1) == (int)gridDim.x - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
+    return t;
+  };
+  auto tile_consume = [&](int it_, bool whole_warp) -> int {
+    if (!dyn) {
+      const int t = cidx + it_ * cnum;
+      return t < ntiles ? t : -1;
+    }
+    const int slot = it_ % kSched;
+    mbar_wait(&sfull_bar[slot], (uint32_t)((it_ / kSched) & 1));
+    const int t = *reinterpret_cast<volatile int*>(&sched_tile[slot]);
+    if (whole_warp) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sempty_bar[slot]);
+    } else {
+      mbar_arrive(&sempty_bar[slot]);
+    }
+    return t;
+  };
 
   const uint32_t a_bytes = kABytes * (uint32_t)p.MT;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
@@ -314,7 +369,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         const uint32_t stage_b = (uint32_t)nchA * a_chunk + (uint32_t)nchB * (uint32_t)p.ext_bytes;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = cidx; tile < ntiles; tile += cnum) {
+        for (int it_ = 0;; ++it_) {
+          const int tile = tile_produce(it_);
+          if (tile < 0) break;
           int t = tile;
           const int sp = t % p.ksplit; t /= p.ksplit;
           const int nt = t % ntn; t /= ntn;
@@ -348,7 +405,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         int sa_i = 0, sb_i = 0;
         uint32_t pa = 0, pb = 0;
         const int ngroups = 9 * kb_per_tap;
-        for (int tile = cidx; tile < ntiles; tile += cnum) {
+        for (int it_ = 0;; ++it_) {
+          const int tile = tile_produce(it_);
+          if (tile < 0) break;
           const int nt = tile % ntn;
           const int mt = tile / ntn;
           const int nhalf = max(0, min(p.MT, nmb - mt * p.MT));
@@ -387,7 +446,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     } else if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cidx; tile < ntiles; tile += cnum) {
+      for (int it_ = 0;; ++it_) {
+          const int tile = tile_produce(it_);
+          if (tile < 0) break;
         int mt, nt, it0, it1;          // it = flattened (tap, k-block) iteration
         int wg_tap = 0, cls = 0;
         if (!wgrad) {
@@ -506,10 +567,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         const uint32_t ky_step = (uint32_t)p.gZ * 128u;
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = cidx; tile < ntiles; tile += cnum) {
+        for (int it_ = 0;; ++it_) {
+          const int tile = tile_consume(it_, false);
+          if (tile < 0) break;
           const int sp = tile % p.ksplit;
           const int nk = (int)((long long)p.nvb * (sp + 1) / p.ksplit) - (int)((long long)p.nvb * sp / p.ksplit);
-          mbar_wait(&tempty_bar[0], (uint32_t)(((tile - cidx) / cnum) & 1) ^ 1);
+          mbar_wait(&tempty_bar[0], (uint32_t)(it_ & 1) ^ 1);
           tc_fence_after();
           for (int k = 0; k < nk; ++k) {
             mbar_wait(&full_bar[stage], phase);
@@ -546,7 +609,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         int acc = 0;
         uint32_t acc_phase = 0;
         const int ngroups = 9 * kb_per_tap;
-        for (int tile = cidx; tile < ntiles; tile += cnum) {
+        for (int it_ = 0;; ++it_) {
+          const int tile = tile_consume(it_, false);
+          if (tile < 0) break;
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
@@ -584,7 +649,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cidx; tile < ntiles; tile += cnum) {
+      for (int it_ = 0;; ++it_) {
+          const int tile = tile_consume(it_, false);
+          if (tile < 0) break;
         int nk, ntap = 1;
         {
           const int sp = tile % p.ksplit;
@@ -661,7 +728,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       for (int sl = 0; sl < nslots; ++sl) sts_f32x2(stat_acc + (uint32_t)(sl * 256), 0.f, 0.f);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cidx; tile < ntiles; tile += cnum) {
+    for (int it_ = 0;; ++it_) {
+      const int tile = tile_consume(it_, true);
+      if (tile < 0) break;
       int mt, nt, tap = 0, nk = 1;
       int opx = p.opx, opy = p.opy, opz = p.opz;
       if (!wgrad) {
@@ -1077,10 +1146,31 @@ extern "C" int coocc_conv_set_sm_budget(int n) {
   return 0;
 }
 
+// Dynamic tile scheduling (see the kernel): counters come from a ring of 64 pairs, one per launch in turn, so kernels
+// of different streams that overlap do not share one; the last CTA of a launch resets its pair.
+__device__ int g_tile_sched[64][2];
+static int g_dyn_sched = 0;
+static unsigned g_sched_seq = 0;
+extern "C" int coocc_conv_set_dynamic(int on) {
+  g_dyn_sched = on ? 1 : 0;
+  return 0;
+}
+
 template <int ES>
 static int launch(const TcParams& p_in, int ntiles, cudaStream_t st) {
   TcParams p = p_in;
   p.epi = pick_epi(p);
+  p.sched = nullptr;
+  static int dyn_always = -1;
+  if (dyn_always < 0) {
+    const char* e = getenv("COOCC_CONV_DYNAMIC");
+    dyn_always = (e && e[0] == '2') ? 1 : 0;          // 2: every launch (experiments); else only where the runner asks
+  }
+  if ((g_dyn_sched || dyn_always) && !p.mc) {
+    static int* base = nullptr;
+    if (!base && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tile_sched) != cudaSuccess) return COOCC_ERR_CUDA;
+    p.sched = base + 2 * (g_sched_seq++ % 64u);
+  }
   if (p.acc_stride == 0) p.acc_stride = kMaxBN;
   static int stat_smem = -1;
   if (stat_smem < 0) {
@@ -1110,7 +1200,7 @@ static int launch(const TcParams& p_in, int ntiles, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    const int sms = (g_sm_budget > 0 && g_sm_budget < g_num_sms) ? g_sm_budget : g_num_sms;
+    const int sms = (g_sm_budget > 0 && g_sm_budget < g_num_sms && !p.sched) ? g_sm_budget : g_num_sms;
     cfg.gridDim = dim3(ntiles < sms ? ntiles : sms, 1, 1);
   }
   cfg.blockDim = dim3(128 + 32 * p.epi, 1, 1);

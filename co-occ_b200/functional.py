@@ -309,7 +309,7 @@ class _Conv3dFn(torch.autograd.Function):
                 # gradient in the parameter's own (channels_last_3d) layout: a view, no copy
                 dw = dw2d.reshape(cout, k, k, k, cin).permute(0, 4, 1, 2, 3)
         if ctx.pre_tail and PRE_TAIL_HOOK is not None:
-            PRE_TAIL_HOOK()        # graph.GraphedStep: fork the next step's index branch before the LAST convolution
+            PRE_TAIL_HOOK("dgrad")  # graph.GraphedStep: fork the next step's index branch before the LAST convolution
         if ctx.needs_input_grad[0]:
             # the data gradient is written in the storage type of x (bf16 activations stay bf16)
             if ctx.x_bf16 and dtype == DT_BF16:

@@ -74,6 +74,11 @@ class GraphedStep:
         # fork before the last convolution of the backward (its grid shrunk to the SMs the index branch leaves free)
         # instead of behind it: hides the whole 3.2 ms instead of the 1.8 ms of the non-conv tail
         self.early_fork = os.environ.get("COOCC_PIPELINE_EARLY", "1") != "0"
+        self.dynamic_tiles = os.environ.get("COOCC_PIPELINE_DYNAMIC", "1") != "0"
+        # where the branch forks: "dgrad" = before the last convolution of the backward (big grids: that convolution
+        # alone is as long as the FPS), "fuser" = at the start of the fuser's backward (the reference's own grids, where
+        # the FPS is as long as the fuser's whole backward), "auto" = by grid size
+        self.fork_at = os.environ.get("COOCC_PIPELINE_FORK", "auto")
         self._num_sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count \
             if torch.cuda.is_available() else 148
         self._tr_fixed, self._tr_len = None, 0
@@ -322,18 +327,32 @@ class GraphedStep:
                     # hold the next kernel of this stream back until both FPS clusters are resident (csrc/gsf_index.cu)
                     _lib.check(lib.coocc_gsf_fps_gate(len(nxt["jobs"]), CF._stream()), "gsf_fps_gate")
 
-            def pre_tail_hook():
-                # (autograd thread, before the data gradient of the fuser's first convolution -- the last convolution
-                # of the backward.)  The index branch takes 32 SMs (two 16-CTA FPS clusters): the convolution is
-                # captured with a persistent grid on the remaining ones instead of paying a second wave.
-                if self.early_fork:
-                    fork(gate=True)
+            def share_sms():
+                # The index branch takes 32 SMs (two 16-CTA FPS clusters).  The convolutions that run next to it are
+                # captured with the dynamic tile scheduler (CTAs that get their SM late -- when the clusters are done
+                # -- take the tiles that are left), or, COOCC_PIPELINE_DYNAMIC=0, with a static grid on the other SMs;
+                # a plain 148-CTA grid would run its last 32 CTAs as a second wave.
+                if self.dynamic_tiles:
+                    lib.coocc_conv_set_dynamic(1)
+                else:
                     lib.coocc_conv_set_sm_budget(self._num_sms - 32)
 
+            def pre_tail_hook(where):
+                # (autograd thread.)  where = "dgrad": in front of the data gradient of the fuser's first convolution,
+                # the last convolution of the backward; "fuser": at the start of the fuser's con_enc backward
+                if self.early_fork and where == self._fork_at and not fired[0]:
+                    fork(gate=True)
+                    share_sms()
+
             def tail_hook():
-                # (start of the fuser's backward: only HBM-bound kernels from here on)
+                # (start of the fuser's GSFusion backward: only HBM-bound kernels from here on)
                 lib.coocc_conv_set_sm_budget(0)
+                lib.coocc_conv_set_dynamic(0)
                 fork()
+            V_ = 1
+            for n_ in ov["prologue"]["dims"]:
+                V_ *= n_
+            self._fork_at = self.fork_at if self.fork_at != "auto" else ("dgrad" if V_ >= 320000 else "fuser")
             CF.TAIL_HOOK = tail_hook
             CF.PRE_TAIL_HOOK = pre_tail_hook
         try:
@@ -360,6 +379,7 @@ class GraphedStep:
             CF.TAIL_HOOK = None
             CF.PRE_TAIL_HOOK = None
             lib.coocc_conv_set_sm_budget(0)
+            lib.coocc_conv_set_dynamic(0)
             CF.GSF_OVERRIDE = None
             CF.DEFERRED_ERRORS = None
             CF.zero_pool_end()

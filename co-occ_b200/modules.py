@@ -136,6 +136,9 @@ class BiFuser_N(nn.Module):
         y, _ = conv_bn_act(cat, dims, self.con_enc[0], self.con_enc[1])
         CF.PRE_TAIL_MARK = False
         y, _ = conv_bn_act(y, dims, self.con_enc[3], self.con_enc[4])
+        if CF.PRE_TAIL_HOOK is not None and y.requires_grad:
+            hook = CF.PRE_TAIL_HOOK              # (bound now: the global is cleared when the capture ends)
+            y.register_hook(lambda g: hook("fuser"))          # runs when the fuser's backward starts
         return CF.to_5d(y, dims)
 
 

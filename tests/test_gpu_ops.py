@@ -125,3 +125,47 @@ def test_conv_epilogue_bf16_output_is_rounded_fp32_output(shape):
         assert rel_err(stats[1], (y32 * y32).sum(0)) < 1e-3
     finally:
         coocc_b200.set_precision("tf32")
+
+
+@pytest.mark.parametrize("shape", [(40, 40, 16, 64, 64, 3, 1), (64, 60, 10, 32, 64, 3, 1), (30, 20, 8, 64, 40, 1, 1),
+                                   (26, 22, 8, 32, 64, 3, 2), (100, 100, 8, 128, 128, 3, 1)])
+def test_conv_dynamic_tile_scheduler_matches_static(shape):
+    """coocc_conv_set_dynamic(1): tiles handed out by an atomic counter instead of the static round-robin.  fwd and
+    dgrad without split-K are bit-identical (the same tiles, computed the same way, by other CTAs); statistics and
+    wgrad sum in a different order."""
+    import ctypes
+    from coocc_b200 import _lib
+    L = _lib.lib()
+    X, Y, Z, Cin, Cout, k, s = shape
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    V = X * Y * Z
+    od = [CF.out_dim(n, k, s) for n in (X, Y, Z)]
+    Vo = od[0] * od[1] * od[2]
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = torch.randn(V, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, k ** 3 * Cin, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    gy = torch.randn(Vo, Cout, device="cuda", generator=g).to(torch.bfloat16)
+    d = _lib.ConvDesc(X, Y, Z, Cin, Cout, k, s, 1, Cin, Cout, 1)
+    res = []
+    try:
+        for dyn in (0, 1, 1):
+            L.coocc_conv_set_dynamic(dyn)
+            y = torch.empty(Vo, Cout, device="cuda", dtype=torch.bfloat16)
+            dx = torch.zeros(V, Cin, device="cuda", dtype=torch.bfloat16)
+            dw = torch.zeros(Cout, k ** 3 * Cin, device="cuda")
+            stats = torch.zeros(2, Cout, device="cuda")
+            _lib.check(L.coocc_conv3d_fwd(ctypes.byref(d), x.data_ptr(), w.data_ptr(), y.data_ptr(), Cout, None, 0,
+                                          stats.data_ptr(), st()), "fwd")
+            _lib.check(L.coocc_conv3d_dgrad(ctypes.byref(d), gy.data_ptr(), w.data_ptr(), dx.data_ptr(), Cin, st()), "dgrad")
+            _lib.check(L.coocc_conv3d_wgrad(ctypes.byref(d), x.data_ptr(), gy.data_ptr(), dw.data_ptr(), st()), "wgrad")
+            torch.cuda.synchronize()
+            res.append((y.float(), dx.float(), dw, stats))
+    finally:
+        L.coocc_conv_set_dynamic(0)
+    for r in res[1:]:
+        assert (r[0] - res[0][0]).abs().max() <= 1e-2 * res[0][0].abs().max()      # (split-K layers: fp32 atomics order)
+        assert (r[1] - res[0][1]).abs().max() <= 1e-2 * res[0][1].abs().max()
+        assert (r[2] - res[0][2]).abs().max() <= 1e-4 * res[0][2].abs().max()
+        assert (r[3] - res[0][3]).abs().max() <= 1e-4 * res[0][3].abs().max()
+    if shape[0] == 100:        # big enough for the unsplit persistent path: identical bits
+        assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
