@@ -182,3 +182,46 @@ def test_pipelined_index_matches_plain_graph():
         assert dot / (ne * ng) ** 0.5 > 0.9 and 0.9 < (ng / ne) ** 0.5 < 1.1, (dot / (ne * ng) ** 0.5, (ng / ne) ** 0.5)
     finally:
         coocc_b200.set_precision("tf32")
+
+
+def test_pipelined_step_with_arena_and_fused_adamw_tracks_plain_graph():
+    """The bench's own step composition -- gradient arena (weight and BatchNorm gradients accumulated in place),
+    FusedAdamW with the config's recipe, bf16 -- run through the plain graph and through the pipelined one (two graph
+    parities sharing one optimizer, convolutions with the dynamic tile scheduler next to the index branch): same losses,
+    same accumulated update."""
+    from coocc_b200.ddp import GradArena
+    from coocc_b200.optim import FusedAdamW, norm_decay_mults
+    coocc_b200.set_precision("bf16")
+    try:
+        cfg = S.CONFIGS["c1"]
+        seeds = (0, 1, 0, 2, 1, 0, 2)
+        scenes = [_scene("c1", s) for s in seeds]
+
+        def build():
+            torch.manual_seed(0)
+            model = coocc_b200.HotPath(coocc_b200.model_cfg(cfg["C"], cfg["K"]), cfg["C"]).to(DEV).train()
+            params = [p for p in model.parameters() if p.requires_grad]
+            arena = GradArena(params)
+            opt = FusedAdamW(params, lr=1e-5, weight_decay=0.01, shadow=True, arena=arena,
+                             param_mults=norm_decay_mults(model, 0.0), max_norm=5.0)
+            return model, opt
+        m_a, o_a = build()
+        m_b, o_b = build()
+        p0 = copy.deepcopy(m_a.state_dict())
+        m_b.load_state_dict(copy.deepcopy(p0))
+        plain = coocc_b200.GraphedStep(m_a, o_a, None, KEYS, bucket=1 << 20, pipeline_index=False)
+        piped = coocc_b200.GraphedStep(m_b, o_b, None, KEYS, bucket=1 << 20, pipeline_index=True)
+        for i, sc in enumerate(scenes):
+            nx = scenes[(i + 1) % len(scenes)]
+            la = float(plain(*sc))
+            lb = float(piped(*sc, next_inputs=(nx[0], nx[1])))
+            assert abs(la - lb) <= 2e-2 * abs(la), (i, la, lb)          # bf16 steps are not bit-reproducible
+        assert piped.stats["captures"] == 2 and piped.stats.get("pipelined", 0) == len(scenes) - 2
+        dot = ne = ng = 0.0
+        for (k, p_), q in zip(m_a.named_parameters(), m_b.parameters()):
+            de, dg = (p_.detach() - p0[k]).double(), (q.detach() - p0[k]).double()
+            dot, ne, ng = dot + float((de * dg).sum()), ne + float((de * de).sum()), ng + float((dg * dg).sum())
+        assert ne > 0 and ng > 0
+        assert dot / (ne * ng) ** 0.5 > 0.8 and 0.8 < (ng / ne) ** 0.5 < 1.25, (dot / (ne * ng) ** 0.5, (ng / ne) ** 0.5)
+    finally:
+        coocc_b200.set_precision("tf32")
