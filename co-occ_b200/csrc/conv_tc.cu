@@ -1151,8 +1151,8 @@ extern "C" int coocc_conv_set_sm_budget(int n) {
 __device__ int g_tile_sched[64][2];
 static int g_dyn_sched = 0;
 static unsigned g_sched_seq = 0;
-extern "C" int coocc_conv_set_dynamic(int on) {
-  g_dyn_sched = on ? 1 : 0;
+extern "C" int coocc_conv_set_dynamic(int mode) {
+  g_dyn_sched = (mode == 1 || mode == 2) ? mode : 0;      // 1: every launch, 2: launches with many long tiles only
   return 0;
 }
 
@@ -1166,7 +1166,14 @@ static int launch(const TcParams& p_in, int ntiles, cudaStream_t st) {
     const char* e = getenv("COOCC_CONV_DYNAMIC");
     dyn_always = (e && e[0] == '2') ? 1 : 0;          // 2: every launch (experiments); else only where the runner asks
   }
-  if ((g_dyn_sched || dyn_always) && !p.mc) {
+  bool want_dyn = g_dyn_sched == 1 || dyn_always;
+  if (g_dyn_sched == 2 && p.ksplit <= 1 && ntiles >= 2 * g_num_sms) {
+    // long tiles only: a short tile would wait for its scheduler atomic (+3 % over a whole step when used everywhere)
+    const int bke = 128 / (p.es ? p.es : 2);
+    const int kb = p.mode == MODE_WGRAD ? p.nvb : (p.ky ? 27 : (p.ncls ? 4 : p.taps)) * ((p.Kc + bke - 1) / bke);
+    want_dyn = kb >= 27;
+  }
+  if (want_dyn && !p.mc) {
     static int* base = nullptr;
     if (!base && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_tile_sched) != cudaSuccess) return COOCC_ERR_CUDA;
     p.sched = base + 2 * (g_sched_seq++ % 64u);

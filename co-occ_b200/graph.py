@@ -307,6 +307,12 @@ class GraphedStep:
         CF.DEFERRED_ERRORS = deferred = []
         fired = [False]
         lib = _lib.lib()
+        # data parallel: NCCL's all-reduce CTAs hold SMs while the backward's convolutions launch; with the static
+        # round-robin a persistent grid then runs the CTAs of those SMs as a second wave.  The long-tile launches of
+        # the captured step use the dynamic tile scheduler instead (mode 2; COOCC_DDP_DYNAMIC=0 disables).
+        base_dyn = 2 if (self.reducer is not None and getattr(self.reducer, "world", 1) > 1
+                         and os.environ.get("COOCC_DDP_DYNAMIC", "1") != "0") else 0
+        lib.coocc_conv_set_dynamic(base_dyn)
         if nxt is not None:
             if self._side is None:
                 self._side = torch.cuda.Stream(priority=-1)     # its clusters are placed before the next conv's CTAs
@@ -347,7 +353,7 @@ class GraphedStep:
             def tail_hook():
                 # (start of the fuser's GSFusion backward: only HBM-bound kernels from here on)
                 lib.coocc_conv_set_sm_budget(0)
-                lib.coocc_conv_set_dynamic(0)
+                lib.coocc_conv_set_dynamic(base_dyn)
                 fork()
             V_ = 1
             for n_ in ov["prologue"]["dims"]:

@@ -79,7 +79,7 @@ int coocc_conv_set_sm_budget(int n);
 /* Dynamic tile scheduling for the convolution launches issued from now on (0 = static round-robin, the default): tiles
  * are handed out by an atomic counter, so CTAs that start late because another kernel holds their SM take what is
  * left instead of running a static share as a second wave. */
-int coocc_conv_set_dynamic(int on);
+int coocc_conv_set_dynamic(int mode);   /* 0 static, 1 every launch, 2 only launches with >= 2 x SMs tiles of >= 27 k-blocks */
 
 /* dw[co][tap][ci] += ... (fp32; caller zero-fills dw; split-K partial sums are added atomically). */
 int coocc_conv3d_wgrad(const coocc_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
